@@ -1,0 +1,117 @@
+"""Mint tests/golden/*.npz by EXECUTING the reference (build container only).
+
+    python -m oracle.make_golden
+
+The reference ships no fixtures, so these are outputs of its own code
+(fithic.py patched in memory per ref_loader.py; blueberry.pyx compiled verbatim)
+run in this image: python 3.12.3, numpy 2.3.5, scipy 1.18.1, scikit-learn 1.9.0.
+Inputs are stored beside the outputs so the GPU box needs nothing but the .npz.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from blueberry_b200 import synth            # noqa: E402
+from oracle import ref_loader, run_reference  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _pass_case(name, bins, R, max_dist, min_dist, depth, seed, with_bias, keep_zeros, n_bins=100, messy=False):
+    bias = synth.make_bias(bins, seed) if with_bias else None
+    fc, fm = synth.make_fragments(bins, R)
+    c = synth.make_contacts(bins, R, max_dist if max_dist > 0 else 10**9, depth, seed, bias, keep_zeros=keep_zeros)
+    chr1, chr2 = c["chrom"].copy(), c["chrom"].copy()
+    mid1, mid2, cnt = c["mid1"].copy(), c["mid2"].copy(), c["count"].copy()
+    if messy:
+        rng = np.random.default_rng(seed + 1)
+        n = len(cnt)
+        # inter-chromosomal rows whose midpoint difference is in range (fithic.py:247,256 never checks chr)
+        k = rng.choice(n, 200, replace=False)
+        chr2[k] = (chr2[k] + 1) % len(bins)
+        # off-grid distances (counted in S, not in mainDic: fithic.py:260-263), negative distances, duplicates
+        k = rng.choice(n, 100, replace=False)
+        mid2[k] += 1234
+        k = rng.choice(n, 50, replace=False)
+        mid1[k], mid2[k] = mid2[k].copy(), mid1[k].copy()
+        dup = rng.choice(n, 300, replace=False)
+        chr1, chr2 = np.concatenate([chr1, chr1[dup]]), np.concatenate([chr2, chr2[dup]])
+        mid1, mid2, cnt = np.concatenate([mid1, mid1[dup]]), np.concatenate([mid2, mid2[dup]]), np.concatenate([cnt, cnt[dup]])
+        perm = rng.permutation(len(cnt))
+        chr1, chr2, mid1, mid2, cnt = chr1[perm], chr2[perm], mid1[perm], mid2[perm], cnt[perm]
+    barr = None
+    if with_bias:
+        bc = np.concatenate([np.full(b, i, dtype=np.int32) for i, b in enumerate(bins)])
+        bv = np.concatenate(bias)
+        bm = fm.copy()
+        if messy:  # a duplicated locus (first occurrence wins, fithic.py:153) and a missing one (default 1.0, :418-425)
+            bc, bm, bv = np.concatenate([bc[:1], bc[:-1]]), np.concatenate([bm[:1], bm[:-1]]), np.concatenate([[1.5], bv[:-1]])
+        barr = (bc, bm, bv)
+    ref = run_reference.run_reference_pass(fc, fm, chr1, mid1, chr2, mid2, cnt, R, n_bins=n_bins,
+                                           min_dist=min_dist, max_dist=max_dist, bias=barr)
+    out = ref["out"]
+    save = dict(
+        resolution=R, n_bins=n_bins, min_dist_arg=min_dist, max_dist_arg=max_dist,
+        frag_chrom=fc, frag_mid=fm, chr1=chr1, mid1=mid1, chr2=chr2, mid2=mid2, count=cnt,
+        has_bias=with_bias,
+        bias_chrom=barr[0] if barr else np.zeros(0, np.int32),
+        bias_mid=barr[1] if barr else np.zeros(0, np.int32),
+        bias_val=barr[2] if barr else np.zeros(0),
+        ref_possible=ref["possible"], ref_observed=ref["observed"], ref_x=ref["x"], ref_y=ref["y"],
+        ref_spline_x=ref["spline_x"], ref_spline_y=ref["spline_y"], ref_residual=ref["residual"],
+        ref_out_chr1=out["chr1"], ref_out_mid1=out["mid1"], ref_out_chr2=out["chr2"], ref_out_mid2=out["mid2"],
+        ref_out_count=out["count"], ref_out_p=out["p"], ref_out_q=out["q"],
+    )
+    for k in ("S", "intra_in_range_count", "intra_all_sum", "intra_all_count", "inter_all_sum", "inter_all_count",
+              "min_obs_dist", "max_obs_dist", "max_possible_dist", "possible_intra_in_range",
+              "possible_intra_all", "possible_inter_all", "min_dist", "max_dist"):
+        save["ref_" + k] = np.int64(ref[k])
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **save)
+    print(name, "pairs", len(cnt), "kept", len(out["p"]), "bins", len(ref["x"]), "S", ref["S"])
+
+
+def _bh_case():
+    ref = ref_loader.load_reference_fithic()
+    cy = ref_loader.load_reference_cython()
+    rng = np.random.default_rng(11)
+    cases = {}
+    p = rng.random(1000)
+    p[rng.choice(1000, 200, replace=False)] = 1.0          # the count==0 rows
+    p[rng.choice(1000, 50, replace=False)] = p[0]          # ties
+    p[:5] = [0.0, 1e-300, 5e-324, 1.0, 0.5]
+    for tag, arr, n in (("a", p, 1000), ("b", p, 25000), ("c", p[:7], 3),
+                        ("doc", np.array([0.03, 0.4, 0.7, 0.01]), 10)):     # fithic.py:460 usage comment
+        cases["p_" + tag] = arr
+        cases["n_" + tag] = np.int64(n)
+        cases["q_py_" + tag] = np.array(ref.benjamini_hochberg_correction(list(arr), n), dtype=np.float64)
+        srt = np.sort(arr)
+        cases["q_cy_sorted_" + tag] = np.asarray(cy.benjamini_hochberg(srt, n), dtype=np.float64)
+    reg = np.sort(rng.choice(40000, 3000, replace=False)).astype(np.float64) * 5000 + 2500
+    cases["regions_sorted"] = reg
+    cases["band_sorted"] = np.int64(cy.count_band_regions(reg))
+    shuf = reg[rng.permutation(len(reg))][:1500].copy()
+    cases["regions_shuffled"] = shuf
+    cases["band_shuffled"] = np.int64(cy.count_band_regions(shuf))
+    np.savez_compressed(os.path.join(GOLDEN, "bh_band.npz"), **cases)
+    print("bh_band", {k: v.shape for k, v in cases.items() if k.startswith("q_py")}, cases["band_sorted"], cases["band_shuffled"])
+
+
+def main():
+    if not ref_loader.reference_available():
+        raise SystemExit("needs /root/reference (build container only)")
+    os.makedirs(GOLDEN, exist_ok=True)
+    # with ICE biases, zeros kept, two chromosomes (the shape of the BASELINE configs, shrunk)
+    _pass_case("pass_bias_dense", [260, 170], 10000, 1500000, -1, 150.0, 5, True, True)
+    # no bias file, zeros dropped (what real Fit-Hi-C input looks like), default 10 Mb cap larger than the chromosome
+    _pass_case("pass_nobias_sparse", [900], 5000, -1, -1, 8.0, 6, False, False)
+    # everything the reference tolerates: inter rows, off-grid / negative distances, duplicates, shuffled order,
+    # min_dist > 0, bias file with a duplicate and a missing locus, n_bins != 100
+    _pass_case("pass_messy", [300, 220, 90], 5000, 1000000, 20000, 60.0, 7, True, True, n_bins=40, messy=True)
+    _bh_case()
+
+
+if __name__ == "__main__":
+    main()

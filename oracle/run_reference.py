@@ -1,0 +1,98 @@
+"""Drive the REAL reference (patched in memory, see ref_loader.py) on arrays.
+
+Build container only (needs /root/reference).  TEST INFRASTRUCTURE ONLY.
+"""
+import gzip
+import os
+import tempfile
+
+import numpy as np
+
+from . import ref_loader
+
+
+def _chrom_name(c):
+    return "chr%d" % (int(c) + 1)
+
+
+def write_interactions(path, chr1, mid1, chr2, mid2, count):
+    """The reference's interactions format, fithic.py:245: chr1 mid1 chr2 mid2 count."""
+    with gzip.open(path, "wt", compresslevel=1) as fh:
+        for a, b, c, d, e in zip(chr1, mid1, chr2, mid2, count):
+            fh.write("%s\t%d\t%s\t%d\t%d\n" % (_chrom_name(a), b, _chrom_name(c), d, e))
+
+
+def write_fragments(path, frag_chrom, frag_mid):
+    """fithic.py:288 reads the first two columns: chr mid."""
+    with gzip.open(path, "wt", compresslevel=1) as fh:
+        for c, m in zip(frag_chrom, frag_mid):
+            fh.write("%s\t%d\t0\t0\t0\n" % (_chrom_name(c), m))
+
+
+def write_biases(path, bias_chrom, bias_mid, bias_val):
+    """fithic.py:143: chr mid bias."""
+    with gzip.open(path, "wt", compresslevel=1) as fh:
+        for c, m, b in zip(bias_chrom, bias_mid, bias_val):
+            fh.write("%s\t%d\t%r\n" % (_chrom_name(c), m, float(b)))
+
+
+def parse_significances(path):
+    """Parse the reference's output (fithic.py:410-435) into arrays."""
+    c1, m1, c2, m2, cnt, p, q = [], [], [], [], [], [], []
+    with gzip.open(path, "rt") as fh:
+        header = fh.readline()
+        for line in fh:
+            a, b, c, d, e, f, g = line.rstrip().split("\t")
+            c1.append(int(a[3:]) - 1); m1.append(int(b)); c2.append(int(c[3:]) - 1); m2.append(int(d))
+            cnt.append(int(e)); p.append(float(f)); q.append(float(g))
+    return {"header": header, "chr1": np.array(c1, np.int32), "mid1": np.array(m1, np.int64),
+            "chr2": np.array(c2, np.int32), "mid2": np.array(m2, np.int64),
+            "count": np.array(cnt, np.int64), "p": np.array(p, np.float64), "q": np.array(q, np.float64)}
+
+
+def run_reference_pass(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, resolution,
+                       n_bins=100, min_dist=-1, max_dist=-1, bias=None, workdir=None):
+    """Run fithic.py's stages exactly as fithic() does (fithic.py:110-133), capturing intermediates.
+
+    min_dist / max_dist use FitHiC.__init__'s sentinels (fithic.py:82-83).
+    bias: None or (bias_chrom, bias_mid, bias_val).
+    """
+    ref = ref_loader.load_reference_fithic()
+    tmp = workdir or tempfile.mkdtemp(prefix="bbk_ref_")
+    inter = os.path.join(tmp, "interactions.gz")
+    frags = os.path.join(tmp, "fragments.gz")
+    write_interactions(inter, chr1, mid1, chr2, mid2, count)
+    write_fragments(frags, frag_chrom, frag_mid)
+    biasfile = "none"
+    if bias is not None:
+        biasfile = os.path.join(tmp, "biases.gz")
+        write_biases(biasfile, *bias)
+    model = ref.FitHiC(os.path.join(tmp, "lib"), resolution, n_bins=n_bins, max_dist=max_dist, min_dist=min_dist)
+    lo, hi = model.min_dist, model.max_dist
+    main = ref.generate_FragPairs(frags, resolution, lo, hi, False)
+    bias_dic = ref.read_bias_file(biasfile, False) if biasfile != "none" else {}
+    main = ref.read_interactions(main, inter, lo, hi, False)
+    x, y, yerr = ref.calculate_probabilities(main, n_bins, resolution, lo, hi, os.path.join(tmp, "lib.fithic_pass1"), False)
+    spline_x, new_y, residual = ref.fit_spline(main, x, y, yerr, inter, os.path.join(tmp, "lib.spline_pass1"),
+                                               bias_dic, resolution, lo, hi, False)
+    out = parse_significances(os.path.join(tmp, "lib.spline_pass1.res%d.significances.txt.gz" % resolution))
+    keys = sorted(main)
+    return {
+        "min_dist": lo, "max_dist": hi,
+        "possible": np.array([main[k][0] for k in keys], np.int64),
+        "observed": np.array([main[k][1] for k in keys], np.int64),
+        "x": np.array(x, np.float64), "y": np.array(y, np.float64),
+        "spline_x": np.array(spline_x, np.int64), "spline_y": np.array(new_y, np.float64),
+        "residual": float(residual),
+        "S": int(ref.observedIntraInRangeSum),
+        "intra_in_range_count": int(ref.observedIntraInRangeCount),
+        "intra_all_sum": int(ref.observedIntraAllSum), "intra_all_count": int(ref.observedIntraAllCount),
+        "inter_all_sum": int(ref.observedInterAllSum), "inter_all_count": int(ref.observedInterAllCount),
+        "min_obs_dist": int(ref.minObservedGenomicDist), "max_obs_dist": int(ref.maxObservedGenomicDist),
+        "max_possible_dist": int(ref.maxPossibleGenomicDist),
+        "possible_intra_in_range": int(ref.possibleIntraInRangeCount),
+        "possible_intra_all": int(ref.possibleIntraAllCount),
+        "possible_inter_all": int(ref.possibleInterAllCount),
+        "out": out,
+        "ref_module": ref,
+    }

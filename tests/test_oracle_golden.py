@@ -1,0 +1,69 @@
+"""The numpy oracle must reproduce what the reference itself produced (tests/golden/*.npz)."""
+import numpy as np
+import pytest
+
+from oracle import fithic_oracle as fo
+from helpers import PASS_CASES, load_golden, golden_bias_dict
+
+
+@pytest.mark.parametrize("name", PASS_CASES)
+def test_pass_matches_reference_output(name):
+    g = load_golden(name)
+    R = int(g["resolution"])
+    lo, hi = int(g["ref_min_dist"]), int(g["ref_max_dist"])
+    o = fo.fithic_arrays(g["frag_chrom"], g["frag_mid"], g["chr1"], g["mid1"], g["chr2"], g["mid2"], g["count"],
+                         R, int(g["n_bins"]), lo, hi, bias=golden_bias_dict(g))
+    # integers: bit exact
+    assert np.array_equal(o.frag.possible, g["ref_possible"])
+    assert np.array_equal(o.contacts.observed, g["ref_observed"])
+    for k in ("S", "intra_in_range_count", "intra_all_sum", "intra_all_count", "inter_all_sum",
+              "inter_all_count", "min_obs_dist", "max_obs_dist"):
+        assert getattr(o.contacts, k) == int(g["ref_" + k]), k
+    assert o.frag.max_possible_dist == int(g["ref_max_possible_dist"])
+    assert o.frag.possible_intra_in_range == int(g["ref_possible_intra_in_range"])
+    assert o.frag.possible_intra_all == int(g["ref_possible_intra_all"])
+    assert o.frag.possible_inter_all == int(g["ref_possible_inter_all"])
+    # floats: the oracle makes the same library calls on the same values -> bit exact too
+    assert np.array_equal(np.array(o.x), g["ref_x"])
+    assert np.array_equal(np.array(o.y), g["ref_y"])
+    assert o.k0 * R == int(g["ref_spline_x"][0]) and len(o.spline_y) == len(g["ref_spline_x"])
+    assert np.array_equal(o.spline_y, g["ref_spline_y"])
+    assert o.residual == float(g["ref_residual"])
+    # the rows the reference wrote, in order, with its p-values (q column is the literal -1, fithic.py:435)
+    keep = o.keep
+    assert np.array_equal(g["mid1"][keep], g["ref_out_mid1"])
+    assert np.array_equal(g["mid2"][keep], g["ref_out_mid2"])
+    assert np.array_equal(g["count"][keep], g["ref_out_count"])
+    assert np.array_equal(o.p[keep], g["ref_out_p"])
+    assert (g["ref_out_q"] == -1).all()
+
+
+def test_spline_index_closed_form_is_bisect():
+    g = load_golden("pass_messy")
+    R = int(g["resolution"])
+    k0, L = int(g["ref_spline_x"][0]) // R, len(g["ref_spline_x"])
+    d = (g["mid2"].astype(np.int64) - g["mid1"])[:5000]
+    a = fo.spline_index(d, k0, L, R, float(g["ref_x"].min()), float(g["ref_x"].max()))
+    b = fo.spline_index_closed_form(d, k0, L, R)
+    assert np.array_equal(a, b)
+
+
+def test_bh_and_band_match_reference():
+    g = load_golden("bh_band")
+    for tag in ("a", "b", "c", "doc"):
+        p, n = g["p_" + tag], int(g["n_" + tag])
+        assert np.array_equal(fo.benjamini_hochberg_correction(p, n), g["q_py_" + tag])
+        assert np.array_equal(fo.benjamini_hochberg_sorted(np.sort(p), n), g["q_cy_sorted_" + tag])
+    assert fo.count_band_regions(g["regions_sorted"]) == int(g["band_sorted"])
+    assert fo.count_band_regions(g["regions_shuffled"]) == int(g["band_shuffled"])
+
+
+def test_bh_is_forward_running_max_not_textbook():
+    # the reference's BH differs from the textbook reverse cumulative-min
+    rng = np.random.default_rng(3)
+    p = rng.random(1000)
+    q = fo.benjamini_hochberg_correction(p, 1000)
+    order = np.argsort(p)
+    textbook = np.minimum.accumulate((np.sort(p) * 1000 / np.arange(1, 1001))[::-1])[::-1]
+    tb = np.empty(1000); tb[order] = np.minimum(textbook, 1)
+    assert (q != tb).sum() > 100

@@ -1,0 +1,37 @@
+"""Build-container only: the oracle against the reference executed live (skipped without /root/reference)."""
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference absent (GPU box)")
+
+
+def test_live_reference_small_pass():
+    from blueberry_b200 import synth
+    from oracle import run_reference as rr, fithic_oracle as fo
+    R, bins = 20000, [150, 90]
+    bias = synth.make_bias(bins, 3)
+    fc, fm = synth.make_fragments(bins, R)
+    c = synth.make_contacts(bins, R, 1_000_000, 40.0, 9, bias)
+    bc = np.concatenate([np.full(b, i) for i, b in enumerate(bins)])
+    ref = rr.run_reference_pass(fc, fm, c["chrom"], c["mid1"], c["chrom"], c["mid2"], c["count"], R,
+                                n_bins=50, max_dist=1_000_000, bias=(bc, fm, np.concatenate(bias)))
+    bd, _ = fo.read_bias_arrays(bc, fm, np.concatenate(bias))
+    o = fo.fithic_arrays(fc, fm, c["chrom"], c["mid1"], c["chrom"], c["mid2"], c["count"], R, 50,
+                         ref["min_dist"], ref["max_dist"], bias=bd)
+    assert np.array_equal(o.frag.possible, ref["possible"])
+    assert np.array_equal(o.contacts.observed, ref["observed"])
+    assert np.array_equal(np.array(o.y), ref["y"]) and np.array_equal(np.array(o.x), ref["x"])
+    assert np.array_equal(o.spline_y, ref["spline_y"])
+    assert np.array_equal(o.p[o.keep], ref["out"]["p"])
+
+
+def test_live_reference_cython_helpers():
+    from oracle import fithic_oracle as fo
+    cy = ref_loader.load_reference_cython()
+    rng = np.random.default_rng(0)
+    p = np.sort(rng.random(500))
+    assert np.array_equal(np.asarray(cy.benjamini_hochberg(p, 777)), fo.benjamini_hochberg_sorted(p, 777))
+    reg = np.sort(rng.choice(10**6, 800, replace=False)).astype(np.float64) * 37
+    assert cy.count_band_regions(reg) == fo.count_band_regions(reg)
