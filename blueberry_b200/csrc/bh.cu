@@ -1,0 +1,521 @@
+// bh.cu - K5: Benjamini-Hochberg q-values the way the reference computes them
+// (benjamini_hochberg_correction fithic.py:466-487, benjamini_hochberg blueberry.pyx:40-75):
+//     sort p ascending; q_(i) = max(q_(i-1), min(p_(i) * N / i, 1))     - a FORWARD running max.
+//
+// Consequences used here (all exact, no approximation):
+//   * tied p share the q of the first of them, so only "1 + number of strictly smaller p" matters;
+//   * once some sorted position reaches p*N/i >= 1 every later q is exactly 1.0.  A coarse
+//     histogram of p (4096 buckets = exponent + top mantissa bit, filled by K4 or by a pass here)
+//     gives the first bucket whose FIRST element is guaranteed to have p*N/rank >= 1; everything
+//     from that bucket on (and every p == 1.0 row, i.e. every zero-count pair) gets q = 1.0 without
+//     being sorted.  Only the "candidates" below it are radix-sorted - typically a few percent.
+//   * the q formula keeps the reference's two roundings: (p * N) / rank.
+// Device pipeline (no host synchronisation; candidate count lives on the device):
+//   [coarse hist] -> threshold (1 CTA) -> compact + write q=1/NaN (the 16 B/pair pass)
+//   -> LSD radix sort of (key, index), 8 x 8 bits, passes with a uniform digit skipped
+//   -> head flags + running max (3-phase scan) -> scatter q (and rank) to input order.
+// BBK_BH_POSITIONAL (blueberry.pyx:40: input already sorted) skips everything but the scan.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BH_THREADS = 256;
+constexpr int SORT_IPT = 8;                         // items per thread per tile in the scatter
+constexpr int SORT_WARPS = BH_THREADS / 32;
+constexpr int SORT_TILE = BH_THREADS * SORT_IPT;
+constexpr int NPASS = 8;
+
+struct BhState {                    // device-resident control block (first bytes of the workspace)
+    unsigned long long n_cand;      // candidates appended so far / total after compaction
+    unsigned long long n_ones, n_nan, n_valid;
+    unsigned long long tau_key;     // keys >= tau_key are saturated (q = 1.0)
+    long long n_tests;              // N
+    double q_ones;                  // q of the p == 1.0 group
+    double total_max;               // running max over all candidates
+    int need_ones_fix;              // q_ones != 1.0 -> rewrite the ones
+    int skip[NPASS];
+    int pad;
+};
+
+struct BhLayout {
+    BhState* st;
+    long long* phist;               // [BBK_PHIST_BINS + 2]
+    unsigned* block_hist;           // [256 * G]
+    double* part_max;               // [G]
+    long long* part_head;           // [G]
+    unsigned long long* keys[2];    // [m] each
+    unsigned* idx[2];               // [m] each
+    int G;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t bh_layout(void* base, long long m, int G, BhLayout* L) {
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return b ? b + o : nullptr; };
+    BhState* st = (BhState*)take(sizeof(BhState));
+    long long* ph = (long long*)take(sizeof(long long) * (BBK_PHIST_BINS + 2));
+    unsigned* bhist = (unsigned*)take(sizeof(unsigned) * 256 * (size_t)G);
+    double* pm = (double*)take(sizeof(double) * (size_t)G);
+    long long* phd = (long long*)take(sizeof(long long) * (size_t)G);
+    unsigned long long* k0 = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)m);
+    unsigned long long* k1 = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)m);
+    unsigned* i0 = (unsigned*)take(sizeof(unsigned) * (size_t)m);
+    unsigned* i1 = (unsigned*)take(sizeof(unsigned) * (size_t)m);
+    if (L) { L->st = st; L->phist = ph; L->block_hist = bhist; L->part_max = pm; L->part_head = phd;
+             L->keys[0] = k0; L->keys[1] = k1; L->idx[0] = i0; L->idx[1] = i1; L->G = G; }
+    return off;
+}
+
+// order-preserving map double -> u64 (total order of IEEE values; -0 < +0)
+__device__ __forceinline__ unsigned long long key_of(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ int bucket_of(double v) {      // v >= 0, not NaN, != 1.0
+    return (int)(((unsigned long long)__double_as_longlong(v) >> 51) & (BBK_PHIST_BINS - 1));
+}
+
+__global__ void bh_init_kernel(BhState* st, long long* phist, const long long* phist_in, long long n_tests) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < BBK_PHIST_BINS + 2) phist[i] = phist_in ? phist_in[i] : 0;
+    if (i == 0) {
+        st->n_cand = 0; st->n_ones = 0; st->n_nan = 0; st->n_valid = 0; st->tau_key = ~0ull;
+        st->n_tests = n_tests; st->q_ones = 1.0; st->total_max = 0.0; st->need_ones_fix = 0;
+        for (int p = 0; p < NPASS; ++p) st->skip[p] = 0;
+    }
+}
+
+// coarse histogram of p (only when K4 did not provide it): 8 B/pair read
+__global__ void __launch_bounds__(BH_THREADS) bh_hist_kernel(const double* p, long long m, long long* phist) {
+    __shared__ unsigned sh[BBK_PHIST_BINS];
+    for (int i = threadIdx.x; i < BBK_PHIST_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    unsigned ones = 0, nans = 0;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        double v = ld_stream_double(p + i);
+        if (isnan(v)) nans++;
+        else if (v == 1.0) ones++;
+        else if (v >= 0.0) atomicAdd(&sh[bucket_of(v)], 1u);
+        else atomicAdd(&sh[0], 1u);                         // negative "p": smallest bucket (never saturates early)
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BBK_PHIST_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd((unsigned long long*)&phist[i], (unsigned long long)sh[i]);
+    unsigned o = __reduce_add_sync(0xffffffffu, ones), z = __reduce_add_sync(0xffffffffu, nans);
+    if ((threadIdx.x & 31) == 0) {
+        if (o) atomicAdd((unsigned long long*)&phist[BBK_PHIST_BINS], (unsigned long long)o);
+        if (z) atomicAdd((unsigned long long*)&phist[BBK_PHIST_BINS + 1], (unsigned long long)z);
+    }
+}
+
+// one CTA: totals, N, and the saturation bucket
+__global__ void bh_threshold_kernel(BhState* st, const long long* phist, int prune) {
+    __shared__ long long cum[BBK_PHIST_BINS + 1];
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int b = 0; b < BBK_PHIST_BINS; ++b) { cum[b] = run; run += phist[b]; }
+        cum[BBK_PHIST_BINS] = run;
+        long long ones = phist[BBK_PHIST_BINS];
+        st->n_ones = (unsigned long long)ones;
+        st->n_nan = (unsigned long long)phist[BBK_PHIST_BINS + 1];
+        st->n_valid = (unsigned long long)(run + ones);
+        if (st->n_tests < 0) st->n_tests = run + ones;      // default N: the number of ranked p-values
+        unsigned long long tau = ~0ull;
+        if (prune) {
+            double N = (double)st->n_tests;
+            for (int b = 1; b < BBK_PHIST_BINS; ++b) {       // bucket 0 also holds negatives: never a threshold
+                if (phist[b] == 0) continue;
+                double v_lo = __longlong_as_double((long long)b << 51);
+                // first element of the bucket: p >= v_lo, rank == cum[b] + 1.  Margin 2^-40 covers both roundings.
+                if (v_lo * N >= (double)(cum[b] + 1) * (1.0 + 9.1e-13)) {
+                    tau = ((unsigned long long)b << 51) | 0x8000000000000000ull;     // key_of(v_lo)
+                    break;
+                }
+            }
+        }
+        st->tau_key = tau;
+    }
+}
+
+// the 16 B/pair pass: q = 1.0 for saturated / p == 1.0 rows, NaN for NaN rows, candidates appended
+__global__ void __launch_bounds__(BH_THREADS) bh_compact_kernel(const double* p, long long m, double* q, BhState* st,
+                                                                unsigned long long* keys, unsigned* idx, int keep_ones,
+                                                                long long* rank) {
+    const unsigned long long tau = st->tau_key;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    long long stride = (long long)gridDim.x * blockDim.x;
+    long long n_iter = (m + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long it = 0; it < n_iter; ++it, i += stride) {
+        bool live = i < m;
+        double v = live ? ld_stream_double(p + i) : qnan;
+        bool isn = isnan(v);
+        unsigned long long k = key_of(v);
+        bool cand = live && !isn && k < tau && (keep_ones || v != 1.0);
+        if (live && !cand) { st_stream_double(q + i, isn ? qnan : 1.0); if (rank) rank[i] = 0; }
+        unsigned mask = __ballot_sync(0xffffffffu, cand);
+        if (mask) {
+            int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == __ffs(mask) - 1) base = atomicAdd(&st->n_cand, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+            if (cand) {
+                unsigned long long pos = base + __popc(mask & ((1u << lane) - 1));
+                keys[pos] = k;
+                idx[pos] = (unsigned)i;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int sort_parity(const BhState* st, int pass) {
+    int par = 0;
+    for (int p = 0; p < pass; ++p) par ^= (st->skip[p] ? 0 : 1);
+    return par;
+}
+
+struct Chunk { long long lo, hi; };
+__device__ __forceinline__ Chunk chunk_of(long long n, int G, int b) {
+    long long per = (n + G - 1) / G;
+    per = (per + SORT_TILE - 1) / SORT_TILE * SORT_TILE;     // whole tiles per block
+    Chunk c;
+    c.lo = (long long)b * per;
+    c.hi = c.lo + per;
+    if (c.lo > n) c.lo = n;
+    if (c.hi > n) c.hi = n;
+    return c;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) sort_hist_kernel(BhLayout L, int pass) {
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const BhState* st = L.st;
+    const long long n = (long long)st->n_cand;
+    const unsigned long long* keys = L.keys[sort_parity(st, pass)];
+    Chunk c = chunk_of(n, L.G, blockIdx.x);
+    const int shift = 8 * pass;
+    for (long long i = c.lo + threadIdx.x; i < c.hi; i += blockDim.x)
+        atomicAdd(&sh[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    L.block_hist[(size_t)threadIdx.x * L.G + blockIdx.x] = sh[threadIdx.x];
+}
+
+// one CTA of 1024 threads: exclusive scan of the digit-major table, skip detection
+__global__ void __launch_bounds__(1024) sort_scan_kernel(BhLayout L, int pass) {
+    __shared__ unsigned part[1024];
+    __shared__ int uniform;
+    const int total = 256 * L.G;
+    const int per = (total + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, total);
+    unsigned s = 0;
+    for (int i = lo; i < hi; ++i) s += L.block_hist[i];
+    part[threadIdx.x] = s;
+    if (threadIdx.x == 0) uniform = 0;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                    // Hillis-Steele inclusive scan
+        unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (int i = lo; i < hi; ++i) { unsigned v = L.block_hist[i]; L.block_hist[i] = run; run += v; }
+    __syncthreads();
+    const unsigned n = (unsigned)L.st->n_cand;
+    if (threadIdx.x < 256) {
+        unsigned start = L.block_hist[(size_t)threadIdx.x * L.G];
+        unsigned end = threadIdx.x == 255 ? n : L.block_hist[(size_t)(threadIdx.x + 1) * L.G];
+        if (end - start == n && n > 0) uniform = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) L.st->skip[pass] = (uniform || n == 0) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) sort_scatter_kernel(BhLayout L, int pass) {
+    __shared__ unsigned base[256];
+    __shared__ unsigned whist[SORT_WARPS][256];
+    const BhState* st = L.st;
+    if (st->skip[pass]) return;
+    const long long n = (long long)st->n_cand;
+    const int par = sort_parity(st, pass);
+    const unsigned long long* kin = L.keys[par];
+    const unsigned* iin = L.idx[par];
+    unsigned long long* kout = L.keys[par ^ 1];
+    unsigned* iout = L.idx[par ^ 1];
+    const int shift = 8 * pass;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    base[threadIdx.x] = L.block_hist[(size_t)threadIdx.x * L.G + blockIdx.x];
+    Chunk c = chunk_of(n, L.G, blockIdx.x);
+    for (long long tile = c.lo; tile < c.hi; tile += SORT_TILE) {
+        for (int d = lane; d < 256; d += 32) whist[warp][d] = 0;
+        __syncthreads();
+        unsigned long long key[SORT_IPT];
+        unsigned val[SORT_IPT], loc[SORT_IPT];
+        const long long wbase = tile + (long long)warp * (32 * SORT_IPT);
+#pragma unroll
+        for (int it = 0; it < SORT_IPT; ++it) {
+            long long i = wbase + it * 32 + lane;
+            bool live = i < c.hi;
+            key[it] = live ? kin[i] : 0;
+            val[it] = live ? iin[i] : 0;
+            unsigned dg = live ? ((unsigned)(key[it] >> shift) & 255u) : 256u;
+            unsigned peers = __match_any_sync(0xffffffffu, dg);
+            unsigned rank = __popc(peers & ((1u << lane) - 1));
+            unsigned before = live ? whist[warp][dg] : 0;
+            __syncwarp();
+            if (live && rank == 0) whist[warp][dg] = before + __popc(peers);
+            __syncwarp();
+            loc[it] = before + rank;
+        }
+        __syncthreads();
+        {   // exclusive scan over warps, per digit; advance the running base of this block
+            unsigned run = base[threadIdx.x];
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) { unsigned v = whist[w][threadIdx.x]; whist[w][threadIdx.x] = run; run += v; }
+            base[threadIdx.x] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < SORT_IPT; ++it) {
+            long long i = wbase + it * 32 + lane;
+            if (i < c.hi) {
+                unsigned dg = (unsigned)(key[it] >> shift) & 255u;
+                unsigned pos = whist[warp][dg] + loc[it];
+                kout[pos] = key[it];
+                iout[pos] = val[it];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- running max over the sorted candidates --------------------------------------------------
+// element i contributes (value, head): value = head ? min((p*N)/(i+1), 1) : -inf ; head index = i or -1
+struct ScanParams {
+    BhLayout L;
+    const double* p_in;      // positional mode: the input p (no keys)
+    long long m;             // positional mode length
+    double* q;               // output (input order)
+    long long* rank;         // optional
+    int positional;
+};
+
+__device__ __forceinline__ void scan_elem(const ScanParams& S, const unsigned long long* keys, long long i, double N,
+                                          double& val, long long& head, bool& reset) {
+    reset = false;
+    if (S.positional) {
+        double pv = S.p_in[i];
+        double bh = (pv * N) / (double)(i + 1);              // two roundings, as fithic.py:474 / blueberry.pyx:68
+        bh = (1.0 < bh) ? 1.0 : bh;                          // min(bh, 1): NaN stays NaN
+        val = bh;
+        head = i;
+        reset = isnan(bh);                                   // max(nan, prev) = nan, and the chain restarts after it
+        return;
+    }
+    unsigned long long k = keys[i];
+    bool is_head = (i == 0) || (keys[i - 1] != k);
+    if (is_head) {
+        double bh = (value_of(k) * N) / (double)(i + 1);
+        val = (1.0 < bh) ? 1.0 : bh;
+        head = i;
+    } else {
+        val = -INFINITY;
+        head = -1;
+    }
+}
+
+// combine for the (segmented) running max: right operand wins a reset
+struct MaxSeg { double v; long long h; int reset; };
+__device__ __forceinline__ MaxSeg seg_combine(const MaxSeg& a, const MaxSeg& b) {
+    MaxSeg r;
+    if (b.reset) { r = b; return r; }
+    r.reset = a.reset;
+    r.v = (a.v > b.v) ? a.v : b.v;                           // prev wins only when strictly greater (reference's max)
+    r.h = a.h > b.h ? a.h : b.h;
+    return r;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) scan_partial_kernel(ScanParams S) {
+    __shared__ MaxSeg red[BH_THREADS];
+    const BhState* st = S.L.st;
+    const long long n = S.positional ? S.m : (long long)st->n_cand;
+    const double N = (double)st->n_tests;
+    const unsigned long long* keys = S.positional ? nullptr : S.L.keys[sort_parity(st, NPASS)];
+    Chunk c = chunk_of(n, S.L.G, blockIdx.x);
+    // thread t scans a contiguous slice of the chunk so that order is preserved
+    long long len = c.hi - c.lo, per = (len + blockDim.x - 1) / blockDim.x;
+    long long lo = c.lo + (long long)threadIdx.x * per, hi = lo + per;
+    if (lo > c.hi) lo = c.hi;
+    if (hi > c.hi) hi = c.hi;
+    MaxSeg acc = {-INFINITY, -1, 0};
+    for (long long i = lo; i < hi; ++i) {
+        MaxSeg e; bool rs;
+        scan_elem(S, keys, i, N, e.v, e.h, rs);
+        e.reset = rs ? 1 : 0;
+        if (rs) e.v = -INFINITY;                             // after a NaN the chain restarts from nothing
+        acc = seg_combine(acc, e);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MaxSeg r = red[0];
+        for (int t = 1; t < BH_THREADS; ++t) r = seg_combine(r, red[t]);
+        S.L.part_max[blockIdx.x] = r.v;
+        S.L.part_head[blockIdx.x] = r.h * 2 + r.reset;       // pack reset flag in the low bit
+    }
+}
+
+__global__ void scan_prefix_kernel(ScanParams S) {           // one thread: G partials
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    BhState* st = S.L.st;
+    MaxSeg run = {-INFINITY, -1, 0};
+    for (int b = 0; b < S.L.G; ++b) {
+        MaxSeg e = {S.L.part_max[b], S.L.part_head[b] >> 1, (int)(S.L.part_head[b] & 1)};
+        S.L.part_max[b] = run.v;                             // exclusive prefix
+        S.L.part_head[b] = run.h;
+        run = seg_combine(run, e);
+    }
+    if (!S.positional) {
+        st->total_max = run.v;
+        // the p == 1.0 group: one tie group after every candidate (when nothing saturated before it)
+        double N = (double)st->n_tests;
+        double bh = (1.0 * N) / (double)(st->n_cand + 1);
+        bh = (1.0 < bh) ? 1.0 : bh;
+        double qo = (run.v > bh) ? run.v : bh;
+        if (st->tau_key != ~0ull) qo = 1.0;                  // saturated before the ones
+        st->q_ones = qo;
+        st->need_ones_fix = (qo != 1.0 && st->n_ones > 0) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(BH_THREADS) scan_apply_kernel(ScanParams S) {
+    __shared__ MaxSeg red[BH_THREADS];
+    const BhState* st = S.L.st;
+    const long long n = S.positional ? S.m : (long long)st->n_cand;
+    const double N = (double)st->n_tests;
+    const int par = S.positional ? 0 : sort_parity(st, NPASS);
+    const unsigned long long* keys = S.positional ? nullptr : S.L.keys[par];
+    const unsigned* idx = S.positional ? nullptr : S.L.idx[par];
+    Chunk c = chunk_of(n, S.L.G, blockIdx.x);
+    long long len = c.hi - c.lo, per = (len + blockDim.x - 1) / blockDim.x;
+    long long lo = c.lo + (long long)threadIdx.x * per, hi = lo + per;
+    if (lo > c.hi) lo = c.hi;
+    if (hi > c.hi) hi = c.hi;
+    MaxSeg acc = {-INFINITY, -1, 0};
+    for (long long i = lo; i < hi; ++i) {
+        MaxSeg e; bool rs;
+        scan_elem(S, keys, i, N, e.v, e.h, rs);
+        e.reset = rs ? 1 : 0;
+        if (rs) e.v = -INFINITY;
+        acc = seg_combine(acc, e);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    // exclusive prefix over threads (sequential by thread 0: 256 combines), seeded with the block prefix
+    if (threadIdx.x == 0) {
+        MaxSeg run = {S.L.part_max[blockIdx.x], S.L.part_head[blockIdx.x], 0};
+        for (int t = 0; t < BH_THREADS; ++t) { MaxSeg e = red[t]; red[t] = run; run = seg_combine(run, e); }
+    }
+    __syncthreads();
+    MaxSeg run = red[threadIdx.x];
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    for (long long i = lo; i < hi; ++i) {
+        MaxSeg e; bool rs;
+        scan_elem(S, keys, i, N, e.v, e.h, rs);
+        e.reset = rs ? 1 : 0;
+        if (rs) e.v = -INFINITY;
+        run = seg_combine(run, e);
+        double qv = rs ? qnan : run.v;
+        if (S.positional) {
+            S.q[i] = qv;
+            if (S.rank) S.rank[i] = i + 1;
+        } else {
+            unsigned o = idx[i];
+            S.q[o] = qv;
+            if (S.rank) S.rank[o] = run.h + 1;
+        }
+    }
+}
+
+// rare: q of the p == 1.0 group is below 1 (N smaller than the number of candidates)
+__global__ void __launch_bounds__(BH_THREADS) ones_fix_kernel(const double* p, long long m, double* q, const BhState* st) {
+    if (!st->need_ones_fix) return;
+    const double qo = st->q_ones;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+        if (p[i] == 1.0) q[i] = qo;
+}
+
+int sort_blocks() { return bbk_num_sms() * 4; }
+
+}  // namespace
+
+extern "C" size_t bbk_bh_workspace_bytes(int64_t m) {
+    if (m < 0) return 0;
+    return bh_layout(nullptr, m, sort_blocks(), nullptr) + 256;
+}
+
+extern "C" int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int32_t mode, const int64_t* d_p_hist,
+                              double* d_q, int64_t* d_rank, void* d_workspace, size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(m >= 0 && m < (1ll << 32), "bbk_bh_qvalues: m must be in [0, 2^32)");
+    BBK_REQUIRE(mode == BBK_BH_UNSORTED || mode == BBK_BH_POSITIONAL, "bbk_bh_qvalues: unknown mode");
+    if (m == 0) return BBK_OK;
+    BBK_REQUIRE(d_p && d_q && d_workspace, "bbk_bh_qvalues: null pointer");
+    BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_qvalues: workspace must be 256-byte aligned");
+    const int G = sort_blocks();
+    BhLayout L;
+    size_t need = bh_layout(d_workspace, m, G, &L);
+    if (workspace_bytes < need) {
+        bbk_set_error("bbk_bh_qvalues: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return BBK_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = bbk_num_sms();
+    bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist,
+                                                                     mode == BBK_BH_POSITIONAL && n_tests < 0 ? m : n_tests);
+    BBK_CHECK_LAUNCH("bh_init_kernel");
+    ScanParams S;
+    S.L = L; S.p_in = d_p; S.m = m; S.q = d_q; S.rank = (long long*)d_rank; S.positional = mode == BBK_BH_POSITIONAL;
+    if (mode == BBK_BH_UNSORTED) {
+        long long want = (m + BH_THREADS - 1) / BH_THREADS;
+        int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+        if (!d_p_hist) {
+            bh_hist_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, L.phist);
+            BBK_CHECK_LAUNCH("bh_hist_kernel");
+        }
+        const int want_rank = d_rank != nullptr;
+        bh_threshold_kernel<<<1, 32, 0, st>>>(L.st, L.phist, want_rank ? 0 : 1);
+        BBK_CHECK_LAUNCH("bh_threshold_kernel");
+        bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, L.keys[0], L.idx[0], want_rank, (long long*)d_rank);
+        BBK_CHECK_LAUNCH("bh_compact_kernel");
+        for (int pass = 0; pass < NPASS; ++pass) {
+            sort_hist_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
+            BBK_CHECK_LAUNCH("sort_hist_kernel");
+            sort_scan_kernel<<<1, 1024, 0, st>>>(L, pass);
+            BBK_CHECK_LAUNCH("sort_scan_kernel");
+            sort_scatter_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
+            BBK_CHECK_LAUNCH("sort_scatter_kernel");
+        }
+    }
+    scan_partial_kernel<<<G, BH_THREADS, 0, st>>>(S);
+    BBK_CHECK_LAUNCH("scan_partial_kernel");
+    scan_prefix_kernel<<<1, 32, 0, st>>>(S);
+    BBK_CHECK_LAUNCH("scan_prefix_kernel");
+    scan_apply_kernel<<<G, BH_THREADS, 0, st>>>(S);
+    BBK_CHECK_LAUNCH("scan_apply_kernel");
+    if (mode == BBK_BH_UNSORTED && !d_rank) {
+        long long want = (m + BH_THREADS - 1) / BH_THREADS;
+        int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+        ones_fix_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st);
+        BBK_CHECK_LAUNCH("ones_fix_kernel");
+    }
+    return BBK_OK;
+}

@@ -1,0 +1,314 @@
+// fit_stage.cu - K2 + K3: possible pairs per distance, equal-occupancy binning, smoothing spline,
+// spline evaluation on the distance grid and antitonic regression, in ONE single-CTA kernel so the
+// pass never leaves the device between the histogram (K1) and the p-value kernel (K4).
+//
+// Reference: generate_FragPairs fithic.py:302-311, calculate_probabilities fithic.py:160-227,
+// fit_spline fithic.py:340-374.  All of this is O(D) FP64 work (D ~ 2-5 thousand distances,
+// ~100 bins): latency-bound, not bandwidth-bound.  The arithmetic lives in fit_stage.h /
+// fit_coop.h, which are also compiled on the host by tests/host_harness and checked there against
+// scipy/sklearn; this file only stages data in shared memory and runs the phases.
+//
+// Compiled with -fmad=false: the knot search makes discrete decisions on FP64 values, and the
+// CPU libraries it must agree with do not contract a*b+c.
+#include "common.cuh"
+#include "fit_coop.h"
+
+namespace {
+
+constexpr int FIT_THREADS = 128;
+
+struct FitParams {
+    const long long* possible;
+    const long long* observed;
+    const long long* totals;
+    const double* x_in;      // stage-injection: bins given (possible/observed unused)
+    const double* y_in;
+    int m_in;
+    int nkeys;
+    int n_bins;
+    long long R, min_dist, max_dist;
+    int max_bins;
+    BbkFitResult* result;
+    double* x;
+    double* y;
+    int* bin_of_key;
+    double* spline_y;
+    double* spline_raw;
+    double* knots;
+    double* coefs;
+    double* gws;             // global workspace (fallback when a phase does not fit in shared memory)
+    size_t pool_doubles;     // dynamic shared memory pool, in doubles
+};
+
+struct FitShared {
+    BbkCoopState st;
+    int status, n_out, k0, L, nk_eff;
+    long long S;
+    double s, min_x, max_x;
+};
+
+__device__ __forceinline__ double* pick(double* pool, size_t pool_doubles, size_t need, double* global_fallback) {
+    return need <= pool_doubles ? pool : global_fallback;
+}
+
+__global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
+    extern __shared__ double pool[];
+    __shared__ FitShared sh;
+    const int tid = threadIdx.x;
+    const bool injected = P.x_in != nullptr;
+
+    if (tid == 0) {
+        sh.status = BBK_FIT_OK;
+        sh.n_out = 0; sh.k0 = 0; sh.L = 0;
+        sh.S = injected ? 0 : P.totals[0];
+        long long eff = P.nkeys;
+        if (P.max_dist > -1) { long long lim = P.max_dist / P.R + 1; if (lim < eff) eff = lim; }
+        sh.nk_eff = (int)eff;
+        sh.st.n = 0; sh.st.fp = 0.0; sh.st.ier = 0;
+    }
+    for (int k = tid; k < P.nkeys; k += FIT_THREADS) if (P.bin_of_key) P.bin_of_key[k] = -1;
+    __syncthreads();
+
+    int m = 0;
+    if (!injected) {
+        // ---------------- equal-occupancy binning (fithic.py:160-227)
+        const int nk = sh.nk_eff;
+        const long long S = sh.S;
+        // stage observed[0..nk) (and possible) in shared memory when they fit; bin bounds after them
+        size_t need = (size_t)2 * nk + (size_t)P.max_bins + 2;    // 2 int64 tables + 2 int32 bound arrays
+        double* base = pick(pool, P.pool_doubles, need, P.gws);
+        long long* obs_s = (long long*)base;
+        long long* pos_s = obs_s + nk;
+        int* bstart = (int*)(pos_s + nk);
+        int* bend = bstart + P.max_bins;
+        for (int k = tid; k < nk; k += FIT_THREADS) { obs_s[k] = P.observed[k]; pos_s[k] = P.possible[k]; }
+        __syncthreads();
+        if (tid == 0) {
+            int nout = 0;
+            int stc = BBK_FIT_OK;
+            if (S == 0) {
+                bool any = false;
+                for (int k = 0; k < nk && !any; ++k) any = bbk_in_range((long long)k * P.R, P.min_dist, P.max_dist);
+                stc = any ? BBK_FIT_S_ZERO : BBK_FIT_OK;
+            } else {
+                stc = bbk_eo_boundaries((const int64_t*)obs_s, nk, S, P.n_bins, P.R, P.min_dist, P.max_dist,
+                                        bstart, bend, P.max_bins, &nout);
+            }
+            sh.status = stc;
+            sh.n_out = nout;
+        }
+        __syncthreads();
+        m = sh.n_out;
+        if (sh.status == BBK_FIT_OK) {
+            for (int j = tid; j < m; j += FIT_THREADS) {
+                double xv = 0.0, yv = 0.0;
+                int stc = bbk_eo_bin_stats((const int64_t*)pos_s, (const int64_t*)obs_s, bstart[j], bend[j], S, P.R, &xv, &yv);
+                P.x[j] = xv;
+                P.y[j] = yv;
+                if (stc != BBK_FIT_OK) atomicMin(&sh.status, stc);
+                if (P.bin_of_key) for (int k = bstart[j]; k <= bend[j]; ++k) P.bin_of_key[k] = j;
+            }
+        }
+        __syncthreads();
+    } else {
+        m = P.m_in;
+        for (int j = tid; j < m; j += FIT_THREADS) { P.x[j] = P.x_in[j]; P.y[j] = P.y_in[j]; }
+        if (tid == 0) sh.n_out = m;
+        __syncthreads();
+    }
+
+    // ---------------- smoothing spline UnivariateSpline(x, y, s=min(y)**2)   (fithic.py:340-343)
+    if (sh.status == BBK_FIT_OK && m < 4 && tid == 0) sh.status = BBK_FIT_TOO_FEW_BINS;
+    __syncthreads();
+    if (sh.status == BBK_FIT_OK) {
+        size_t need = bbk_coop_ws_doubles(m) + (size_t)2 * m;
+        double* base = pick(pool, P.pool_doubles, need, P.gws);
+        double* xs = base;
+        double* ys = base + m;
+        for (int j = tid; j < m; j += FIT_THREADS) { xs[j] = P.x[j]; ys[j] = P.y[j]; }
+        __syncthreads();
+        if (tid == 0) {
+            double ymin = ys[0], xmin = xs[0], xmax = xs[0];
+            bool nondecr = true, strict = true;
+            for (int j = 1; j < m; ++j) {
+                ymin = ys[j] < ymin ? ys[j] : ymin;
+                xmin = xs[j] < xmin ? xs[j] : xmin;
+                xmax = xs[j] > xmax ? xs[j] : xmax;
+                nondecr = nondecr && (xs[j] - xs[j - 1] >= 0.0);
+                strict = strict && (xs[j] - xs[j - 1] > 0.0);
+            }
+            sh.s = ymin * ymin;                              // fithic.py:340
+            sh.min_x = xmin;                                 // fithic.py:350
+            sh.max_x = xmax;
+            if (!(sh.s > 0.0 ? nondecr : strict)) sh.status = BBK_FIT_X_NOT_INCREASING;
+        }
+        __syncthreads();
+        if (sh.status == BBK_FIT_OK) {
+            BbkCoopWs cw;
+            bbk_coop_ws_carve(base + 2 * m, m, &cw);
+            bbk_coop_univariate_spline(xs, ys, m, sh.s, &sh.st, &cw);
+            __syncthreads();
+            const int n = sh.st.n;
+            for (int i = tid; i < m + 4; i += FIT_THREADS) {
+                P.knots[i] = i < n ? cw.w.t[i] : 0.0;
+                P.coefs[i] = i < n ? cw.w.c[i] : 0.0;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- splineX = keys within [min(x), max(x)], splineY = ius(splineX)   (fithic.py:350-359)
+    if (sh.status == BBK_FIT_OK) {
+        if (tid == 0) {
+            // first key k with k*R >= min_x and last key with k*R <= max_x (keys are ints, x are doubles)
+            long long k0 = (long long)ceil(sh.min_x / (double)P.R);
+            if (k0 < 0) k0 = 0;
+            while (k0 > 0 && (double)((k0 - 1) * P.R) >= sh.min_x) --k0;
+            while ((double)(k0 * P.R) < sh.min_x) ++k0;
+            long long k1 = (long long)floor(sh.max_x / (double)P.R);
+            while ((double)((k1 + 1) * P.R) <= sh.max_x) ++k1;
+            while (k1 >= 0 && (double)(k1 * P.R) > sh.max_x) --k1;
+            if (k1 > P.nkeys - 1) k1 = P.nkeys - 1;
+            long long L = k1 - k0 + 1;
+            if (L <= 0) { sh.status = BBK_FIT_EMPTY_GRID; L = 0; }
+            sh.k0 = (int)k0;
+            sh.L = (int)L;
+        }
+        __syncthreads();
+    }
+    if (sh.status == BBK_FIT_OK) {
+        const int L = sh.L, n = sh.st.n;
+        // knots / coefficients back into shared memory for the evaluation
+        size_t need = (size_t)2 * (m + 4) + (size_t)3 * L + 8;
+        double* base = pick(pool, P.pool_doubles, need, P.gws);
+        double* tk = base;
+        double* ck = base + (m + 4);
+        double* wmean = ck + (m + 4);
+        double* wcount = wmean + L;
+        int* wstart = (int*)(wcount + L);
+        for (int i = tid; i < n; i += FIT_THREADS) { tk[i] = P.knots[i]; ck[i] = P.coefs[i]; }
+        __syncthreads();
+        for (int i = tid; i < L; i += FIT_THREADS) {
+            int cur = 4;
+            double arg = (double)((long long)(sh.k0 + i) * P.R);
+            P.spline_raw[i] = bbk_spline_eval(tk, n, ck, arg, &cur);
+        }
+        __syncthreads();
+        // ---------------- antitonic regression (fithic.py:361-362) and the residual (fithic.py:374)
+        if (tid == 0) {
+            bbk_antitonic_pava(P.spline_raw, L, P.spline_y, wmean, wcount, wstart);
+            double res = 0.0;
+            int cur = 4;
+            for (int j = 0; j < m; ++j) {
+                double dv = P.y[j] - bbk_spline_eval(tk, n, ck, P.x[j], &cur);
+                res = res + dv * dv;
+            }
+            P.result->residual = res;
+        }
+        for (int i = L + tid; i < P.nkeys; i += FIT_THREADS) { P.spline_y[i] = 0.0; P.spline_raw[i] = 0.0; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        BbkFitResult* r = P.result;
+        r->status = sh.status;
+        r->n_out = sh.n_out;
+        r->k0 = sh.k0;
+        r->L = sh.L;
+        r->n_knots = sh.st.n;
+        r->ier = sh.st.ier;
+        r->S = sh.S;
+        r->min_x = sh.min_x;
+        r->max_x = sh.max_x;
+        r->fp = sh.st.fp;
+        r->smoothing = sh.s;
+        if (sh.status != BBK_FIT_OK) r->residual = 0.0;
+    }
+}
+
+__global__ void possible_pairs_kernel(const long long* n_frags, const long long* max_frag, int n_chrom, long long R,
+                                      int nkeys, long long* possible) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    long long d = (long long)k * R, tot = 0;
+    for (int c = 0; c < n_chrom; ++c)
+        if (d <= max_frag[c]) tot += n_frags[c] - k;          // fithic.py:309-311
+    possible[k] = tot;
+}
+
+size_t fit_pool_bytes() { return 200 * 1024; }
+
+int launch_fit(FitParams& P, size_t workspace_bytes, cudaStream_t st) {
+    size_t need = bbk_fit_workspace_bytes(P.max_bins, P.nkeys);
+    if (workspace_bytes < need || !P.gws) {
+        bbk_set_error("bbk_fit: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return BBK_E_WORKSPACE;
+    }
+    size_t pool = fit_pool_bytes();
+    P.pool_doubles = pool / sizeof(double);
+    BBK_CHECK_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool));
+    fit_kernel<<<1, FIT_THREADS, pool, st>>>(P);
+    BBK_CHECK_LAUNCH("fit_kernel");
+    return BBK_OK;
+}
+
+}  // namespace
+
+extern "C" size_t bbk_fit_workspace_bytes(int32_t max_bins, int32_t nkeys) {
+    size_t m = max_bins > 4 ? (size_t)max_bins : 4;
+    size_t a = (size_t)2 * nkeys + m + 2;
+    size_t b = bbk_coop_ws_doubles((int)m) + 2 * m;
+    size_t c = 2 * (m + 4) + (size_t)3 * nkeys + 8;
+    size_t mx = a > b ? a : b;
+    mx = mx > c ? mx : c;
+    return (mx + 16) * sizeof(double);
+}
+
+extern "C" int bbk_possible_pairs(const int64_t* d_n_frags, const int64_t* d_max_frag, int32_t n_chrom, int64_t resolution,
+                                  int32_t nkeys, int64_t* d_possible, void* stream) {
+    BBK_REQUIRE(d_n_frags && d_max_frag && d_possible, "bbk_possible_pairs: null pointer");
+    BBK_REQUIRE(n_chrom >= 0 && nkeys >= 0 && resolution > 0, "bbk_possible_pairs: bad sizes");
+    if (nkeys == 0) return BBK_OK;
+    possible_pairs_kernel<<<(nkeys + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)d_n_frags, (const long long*)d_max_frag, n_chrom, resolution, nkeys, (long long*)d_possible);
+    BBK_CHECK_LAUNCH("possible_pairs_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_fit(const int64_t* d_possible, const int64_t* d_obs_sum, int32_t nkeys, const int64_t* d_totals,
+                       int32_t n_bins, int64_t resolution, int64_t min_dist, int64_t max_dist, int32_t max_bins,
+                       BbkFitResult* d_result, double* d_x, double* d_y, int32_t* d_bin_of_key, double* d_spline_y,
+                       double* d_spline_raw, double* d_knots, double* d_coefs, void* d_workspace, size_t workspace_bytes,
+                       void* stream) {
+    BBK_REQUIRE(d_possible && d_obs_sum && d_totals && d_result && d_x && d_y && d_spline_y && d_spline_raw && d_knots && d_coefs,
+                "bbk_fit: null pointer");
+    BBK_REQUIRE(nkeys > 0 && max_bins >= 4 && resolution > 0, "bbk_fit: bad sizes");
+    FitParams P = {};
+    P.possible = (const long long*)d_possible; P.observed = (const long long*)d_obs_sum; P.totals = (const long long*)d_totals;
+    P.x_in = nullptr; P.y_in = nullptr; P.m_in = 0;
+    P.nkeys = nkeys; P.n_bins = n_bins; P.R = resolution; P.min_dist = min_dist; P.max_dist = max_dist; P.max_bins = max_bins;
+    P.result = d_result; P.x = d_x; P.y = d_y; P.bin_of_key = d_bin_of_key; P.spline_y = d_spline_y; P.spline_raw = d_spline_raw;
+    P.knots = d_knots; P.coefs = d_coefs; P.gws = (double*)d_workspace;
+    return launch_fit(P, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int bbk_fit_from_bins(const double* d_x_in, const double* d_y_in, int32_t m, int32_t nkeys, int64_t resolution,
+                                 BbkFitResult* d_result, double* d_spline_y, double* d_spline_raw, double* d_knots,
+                                 double* d_coefs, void* d_workspace, size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(d_x_in && d_y_in && d_result && d_spline_y && d_spline_raw && d_knots && d_coefs, "bbk_fit_from_bins: null pointer");
+    BBK_REQUIRE(m >= 1 && nkeys > 0 && resolution > 0, "bbk_fit_from_bins: bad sizes");
+    // x / y scratch copies live at the end of the caller's workspace
+    size_t need = bbk_fit_workspace_bytes(m, nkeys) + (size_t)2 * m * sizeof(double);
+    if (workspace_bytes < need) {
+        bbk_set_error("bbk_fit_from_bins: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return BBK_E_WORKSPACE;
+    }
+    FitParams P = {};
+    P.x_in = d_x_in; P.y_in = d_y_in; P.m_in = m;
+    P.nkeys = nkeys; P.n_bins = 0; P.R = resolution; P.min_dist = 0; P.max_dist = -1; P.max_bins = m > 4 ? m : 4;
+    P.result = d_result;
+    P.x = (double*)((char*)d_workspace + bbk_fit_workspace_bytes(m, nkeys));
+    P.y = P.x + m;
+    P.bin_of_key = nullptr; P.spline_y = d_spline_y; P.spline_raw = d_spline_raw; P.knots = d_knots; P.coefs = d_coefs;
+    P.gws = (double*)d_workspace;
+    return launch_fit(P, bbk_fit_workspace_bytes(m, nkeys), (cudaStream_t)stream);
+}

@@ -1,0 +1,242 @@
+// hist.cu - K1: contact histogram by genomic distance (reference: read_interactions, fithic.py:229-270).
+//
+// HBM-bound integer kernel: 12 B/pair in (mid1, mid2, count as int32 SoA), O(D) out.
+//   * 128-bit streaming loads (L1::no_allocate), two groups of 4 records in flight per thread;
+//   * per-CTA shared-memory histogram (u32, flushed to the global int64 table before it can
+//     overflow); warp-aggregated: when every active lane of a warp hits the same distance
+//     (diagonal-major input) the counts are summed with REDUX and one lane issues the atomic,
+//     otherwise lanes issue their own shared-memory atomics (row-major input touches 32
+//     consecutive bins - the histogram is stored permuted so those land in 32 distinct banks);
+//   * zero counts never touch the histogram (most records at 1 kb);
+//   * scalar totals are carried in registers and reduced warp -> CTA -> one global atomic each;
+//   * persistent grid: a multiple of the SM count.
+#include "common.cuh"
+
+namespace {
+
+constexpr int HIST_THREADS = 512;
+constexpr int SMALL_COUNT_LIMIT = 4096;          // counts below this go through the u32 shared histogram
+constexpr long long FLUSH_PAIRS = 1ll << 20;     // 2^20 pairs * 4095 < 2^32: flush before a bin can overflow
+constexpr int MAX_SMEM_KEYS = 40960;             // 160 KB of u32 bins
+
+struct HistParams {
+    const int32_t* chr1;
+    const int32_t* chr2;
+    const int32_t* mid1;
+    const int32_t* mid2;
+    const int32_t* count;
+    long long n_pairs;
+    long long min_dist, max_dist;
+    FastDiv div;
+    int nkeys;        // len(mainDic)
+    int nkeys_s;      // bins kept in shared memory (prefix of the table), 0 = none
+    int quarter;      // permuted layout: phys(k) = (k >> 2) + (k & 3) * quarter
+    long long* obs_sum;
+    long long* totals;
+};
+
+struct Acc {
+    long long S, in_range, intra_sum, intra_cnt, inter_sum, inter_cnt, dmin, dmax;
+};
+
+__device__ __forceinline__ int phys_bin(int k, int quarter) { return (k >> 2) + (k & 3) * quarter; }
+
+template <bool HAS_CHR>
+__device__ __forceinline__ void process_record(const HistParams& P, unsigned* sh, int m1, int m2, int c, int c1, int c2,
+                                               bool live, Acc& a) {
+    long long d = (long long)m2 - (long long)m1;                      // fithic.py:247 (no abs, no chromosome test)
+    bool lo = (P.min_dist == -1) || (P.min_dist > -1 && d > P.min_dist);   // fithic.py:256
+    bool hi = (P.max_dist == -1) || (P.max_dist > -1 && d <= P.max_dist);  // fithic.py:257
+    bool in_range = live && lo && hi;
+    if (HAS_CHR) {
+        bool inter = live && (c1 != c2);                               // fithic.py:249-254
+        bool intra = live && (c1 == c2);
+        a.inter_sum += inter ? c : 0;
+        a.inter_cnt += inter ? 1 : 0;
+        a.intra_sum += intra ? c : 0;
+        a.intra_cnt += intra ? 1 : 0;
+    } else {
+        a.intra_sum += live ? c : 0;
+        a.intra_cnt += live ? 1 : 0;
+    }
+    if (in_range) {
+        a.dmin = d < a.dmin ? d : a.dmin;                              // fithic.py:258-259
+        a.dmax = d > a.dmax ? d : a.dmax;
+        a.S += c;                                                      // fithic.py:262 (even when d is not a key)
+        a.in_range += 1;                                               // fithic.py:263
+    }
+    // "if distance in mainDic" (fithic.py:260): d >= 0, a multiple of R, below the table end
+    bool key_ok = false;
+    unsigned k = 0;
+    if (in_range && d >= 0 && c != 0) {
+        unsigned ud = (unsigned)d;
+        k = fastdiv(ud, P.div);
+        key_ok = (k * P.div.R == ud) && (k < (unsigned)P.nkeys);
+    }
+    bool small = key_ok && (unsigned)c < (unsigned)SMALL_COUNT_LIMIT && k < (unsigned)P.nkeys_s;
+    bool big = key_ok && !small;
+    if (big) atomicAdd((unsigned long long*)&P.obs_sum[k], (unsigned long long)(long long)c);
+    unsigned smask = __ballot_sync(0xffffffffu, small);
+    if (smask == 0) return;
+    int leader = __ffs(smask) - 1;
+    unsigned k0 = __shfl_sync(0xffffffffu, k, leader);
+    bool uniform = __all_sync(0xffffffffu, !small || k == k0);
+    if (uniform) {
+        unsigned tot = __reduce_add_sync(0xffffffffu, small ? (unsigned)c : 0u);
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&sh[phys_bin((int)k0, P.quarter)], tot);
+    } else if (small) {
+        atomicAdd(&sh[phys_bin((int)k, P.quarter)], (unsigned)c);
+    }
+}
+
+__device__ __forceinline__ void flush_hist(const HistParams& P, unsigned* sh) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < P.nkeys_s; k += blockDim.x) {
+        int ph = phys_bin(k, P.quarter);
+        unsigned v = sh[ph];
+        if (v) {
+            atomicAdd((unsigned long long*)&P.obs_sum[k], (unsigned long long)v);
+            sh[ph] = 0;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool HAS_CHR>
+__global__ void __launch_bounds__(HIST_THREADS, 2) hist_pairs_kernel(HistParams P) {
+    extern __shared__ unsigned sh[];
+    __shared__ long long red[8][HIST_THREADS / 32];
+    for (int i = threadIdx.x; i < 4 * P.quarter; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+
+    Acc a = {0, 0, 0, 0, 0, 0, 500000000ll, 0ll};                      // fithic.py:40-41 initial min / max
+    const long long n_groups = P.n_pairs >> 2;                         // groups of 4 records (one int4 per column)
+    const int4* m1v = reinterpret_cast<const int4*>(P.mid1);
+    const int4* m2v = reinterpret_cast<const int4*>(P.mid2);
+    const int4* cv = reinterpret_cast<const int4*>(P.count);
+    const int4* c1v = reinterpret_cast<const int4*>(P.chr1);
+    const int4* c2v = reinterpret_cast<const int4*>(P.chr2);
+    long long since_flush = 0;
+    // CTA tiles of 2*blockDim groups: the trip count is uniform across the CTA, so the barrier in
+    // flush_hist and the warp collectives in process_record are reached by every thread
+    const long long tile_groups = 2ll * blockDim.x;
+    const long long n_tiles = (n_groups + tile_groups - 1) / tile_groups;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long g0 = tile * tile_groups + threadIdx.x;
+        long long g1 = g0 + blockDim.x;
+        bool l0 = g0 < n_groups, l1 = g1 < n_groups;
+        int4 z = make_int4(0, 0, 0, 0);
+        int4 a1 = l0 ? ld_stream_int4(m1v + g0) : z, a2 = l0 ? ld_stream_int4(m2v + g0) : z, ac = l0 ? ld_stream_int4(cv + g0) : z;
+        int4 b1 = l1 ? ld_stream_int4(m1v + g1) : z, b2 = l1 ? ld_stream_int4(m2v + g1) : z, bc = l1 ? ld_stream_int4(cv + g1) : z;
+        int4 ax = z, ay = z, bx = z, by = z;
+        if (HAS_CHR) {
+            if (l0) { ax = ld_stream_int4(c1v + g0); ay = ld_stream_int4(c2v + g0); }
+            if (l1) { bx = ld_stream_int4(c1v + g1); by = ld_stream_int4(c2v + g1); }
+        }
+        process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0, a);
+        process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0, a);
+        process_record<HAS_CHR>(P, sh, a1.z, a2.z, ac.z, ax.z, ay.z, l0, a);
+        process_record<HAS_CHR>(P, sh, a1.w, a2.w, ac.w, ax.w, ay.w, l0, a);
+        process_record<HAS_CHR>(P, sh, b1.x, b2.x, bc.x, bx.x, by.x, l1, a);
+        process_record<HAS_CHR>(P, sh, b1.y, b2.y, bc.y, bx.y, by.y, l1, a);
+        process_record<HAS_CHR>(P, sh, b1.z, b2.z, bc.z, bx.z, by.z, l1, a);
+        process_record<HAS_CHR>(P, sh, b1.w, b2.w, bc.w, bx.w, by.w, l1, a);
+        since_flush += 4 * tile_groups;
+        if (since_flush >= FLUSH_PAIRS) {      // uniform across the CTA
+            flush_hist(P, sh);
+            since_flush = 0;
+        }
+    }
+    // tail: the last n_pairs % 4 records, by the first warp of block 0
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        long long i = (n_groups << 2) + threadIdx.x;
+        bool live = threadIdx.x < (P.n_pairs & 3);
+        int m1 = live ? P.mid1[i] : 0, m2 = live ? P.mid2[i] : 0, c = live ? P.count[i] : 0;
+        int c1 = 0, c2 = 0;
+        if (HAS_CHR && live) { c1 = P.chr1[i]; c2 = P.chr2[i]; }
+        process_record<HAS_CHR>(P, sh, m1, m2, c, c1, c2, live, a);
+    }
+    flush_hist(P, sh);
+
+    // scalar totals: warp shuffle -> shared -> one global atomic per CTA and quantity
+    long long v[8] = {a.S, a.in_range, a.intra_sum, a.intra_cnt, a.inter_sum, a.inter_cnt, a.dmin, a.dmax};
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        long long r = (q == 6) ? warp_min_ll(v[q]) : (q == 7) ? warp_max_ll(v[q]) : warp_sum_ll(v[q]);
+        if (lane == 0) red[q][warp] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        int q = threadIdx.x;
+        long long r = red[q][0];
+        for (int w = 1; w < HIST_THREADS / 32; ++w) {
+            long long x = red[q][w];
+            r = (q == 6) ? (x < r ? x : r) : (q == 7) ? (x > r ? x : r) : r + x;
+        }
+        if (q == 6) atomicMin(&P.totals[6], r);
+        else if (q == 7) atomicMax(&P.totals[7], r);
+        else if (r != 0) atomicAdd((unsigned long long*)&P.totals[q], (unsigned long long)r);
+    }
+}
+
+__global__ void hist_init_kernel(long long* obs, int nkeys, long long* totals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nkeys) obs[i] = 0;
+    if (i < 8) totals[i] = (i == 6) ? 500000000ll : 0ll;               // fithic.py:25-41
+}
+
+}  // namespace
+
+extern "C" int bbk_hist_init(int64_t* d_obs_sum, int32_t nkeys, int64_t* d_totals, void* stream) {
+    BBK_REQUIRE(d_obs_sum && d_totals && nkeys >= 0, "bbk_hist_init: null table or negative nkeys");
+    int n = nkeys > 8 ? nkeys : 8;
+    hist_init_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((long long*)d_obs_sum, nkeys, (long long*)d_totals);
+    BBK_CHECK_LAUNCH("hist_init_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                              const int32_t* d_count, int64_t n_pairs, int64_t resolution, int64_t min_dist,
+                              int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream) {
+    BBK_REQUIRE(n_pairs >= 0 && nkeys >= 0, "bbk_hist_pairs: negative size");
+    BBK_REQUIRE(resolution > 0 && resolution < (1ll << 32), "bbk_hist_pairs: resolution must be in [1, 2^32)");
+    BBK_REQUIRE((d_chr1 == nullptr) == (d_chr2 == nullptr), "bbk_hist_pairs: chr1/chr2 must both be given or both NULL");
+    BBK_REQUIRE(d_obs_sum && d_totals, "bbk_hist_pairs: null output");
+    if (n_pairs == 0) return BBK_OK;
+    BBK_REQUIRE(d_mid1 && d_mid2 && d_count, "bbk_hist_pairs: null input column");
+    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_chr1 | (uintptr_t)d_chr2;
+    BBK_REQUIRE((align & 15) == 0, "bbk_hist_pairs: columns must be 16-byte aligned");
+
+    HistParams P;
+    P.chr1 = d_chr1; P.chr2 = d_chr2; P.mid1 = d_mid1; P.mid2 = d_mid2; P.count = d_count;
+    P.n_pairs = n_pairs; P.min_dist = min_dist; P.max_dist = max_dist;
+    P.div = make_fastdiv((uint64_t)resolution);
+    P.nkeys = nkeys;
+    // only keys that can be in range need a shared bin: k*R <= max_dist
+    long long want = nkeys;
+    if (max_dist > -1) { long long lim = max_dist / resolution + 1; if (lim < want) want = lim; }
+    if (want > MAX_SMEM_KEYS) want = MAX_SMEM_KEYS;     // the rest goes straight to the global table
+    P.nkeys_s = (int)want;
+    P.quarter = ((P.nkeys_s + 3) / 4 + 31) / 32 * 32 + 1;   // odd multiple-of-32 offset keeps the 4 quarters on distinct banks
+    if (P.nkeys_s == 0) P.quarter = 0;
+    P.obs_sum = (long long*)d_obs_sum; P.totals = (long long*)d_totals;
+    size_t smem = (size_t)4 * P.quarter * sizeof(unsigned);
+
+    int sms = bbk_num_sms();
+    long long groups = n_pairs >> 2;
+    long long need = (groups + 2ll * HIST_THREADS - 1) / (2ll * HIST_THREADS);
+    int per_sm = smem > 100 * 1024 ? 1 : 2;
+    long long grid = (long long)sms * per_sm;
+    if (need < grid) grid = need > 0 ? need : 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_chr1) {
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hist_pairs_kernel<true><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
+    } else {
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hist_pairs_kernel<false><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
+    }
+    BBK_CHECK_LAUNCH("hist_pairs_kernel");
+    return BBK_OK;
+}

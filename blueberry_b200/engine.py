@@ -1,0 +1,187 @@
+"""Device-side driver of one Fit-Hi-C significance pass (the reference's fithic(), fithic.py:110-133).
+
+    K1 hist_pairs  ->  [allreduce of the distance table across ranks]  ->  K2/K3 fit (one CTA)
+    ->  K4 pvalues  ->  K5 Benjamini-Hochberg q-values (opt-in; the reference writes -1, fithic.py:435)
+
+Everything between the first and last kernel is enqueued on one CUDA stream with no host
+synchronisation; S, the spline range and the candidate count of the q-value step stay on the device.
+PyTorch is used for device memory, streams and torch.distributed only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Shard(object):
+    """Contact records of one shard (a chromosome or a diagonal band), as int32 CUDA tensors.
+
+    chr1/chr2 may be None: every record is on chromosome `chrom` (the compact 12 B/pair layout).
+    """
+
+    def __init__(self, mid1, mid2, count, chr1=None, chr2=None, chrom=0):
+        for t in (mid1, mid2, count, chr1, chr2):
+            if t is not None:
+                if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+                    raise ValueError("shard columns must be contiguous int32 CUDA tensors")
+        if (chr1 is None) != (chr2 is None):
+            raise ValueError("chr1 and chr2 must both be given or both be None")
+        self.mid1, self.mid2, self.count, self.chr1, self.chr2 = mid1, mid2, count, chr1, chr2
+        self.chrom = int(chrom)
+        self.n = int(mid1.numel())
+        if mid2.numel() != self.n or count.numel() != self.n:
+            raise ValueError("shard columns differ in length")
+
+
+class BiasTables(object):
+    """Dense per-chromosome bias tables on the device (biasDic of fithic.py:136-158).
+
+    values[c]: float64 array over the grid mid0[c] + i*resolution; NaN = locus absent (lookup gives 1.0).
+    Out-of-range biases must already be mapped to -1 (read_bias_file does that, fithic.py:147-149).
+    """
+
+    def __init__(self, values, mid0, device):
+        self.n_chrom = len(values)
+        base = np.zeros(self.n_chrom + 1, dtype=np.int64)
+        for c, v in enumerate(values):
+            base[c + 1] = base[c] + len(v)
+        flat = np.concatenate([np.asarray(v, dtype=np.float64) for v in values]) if self.n_chrom else np.zeros(0)
+        self.bias = torch.from_numpy(flat).to(device)
+        self.chrom_base = torch.from_numpy(base).to(device)
+        self.mid0 = torch.from_numpy(np.asarray(mid0, dtype=np.int64)).to(device)
+        self.struct = _lib.BiasTable(self.bias.data_ptr(), self.chrom_base.data_ptr(), self.mid0.data_ptr(), self.n_chrom)
+
+
+class PassEngine(object):
+    """Buffers + kernel sequence for one pass over a set of shards resident on this GPU."""
+
+    def __init__(self, resolution, n_bins, min_dist, max_dist, nkeys, device=None, max_bins=None):
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.R = int(resolution)
+        self.n_bins = int(n_bins)
+        self.min_dist = int(min_dist)
+        self.max_dist = int(max_dist)
+        self.nkeys = int(nkeys)
+        if self.nkeys <= 0:
+            raise ValueError("the fragment list gives no genomic distances (nkeys == 0)")
+        # more than n_bins bins can come out (fithic.py:208); every distance could close one
+        self.max_bins = int(max_bins) if max_bins else max(4, min(self.nkeys, max(4 * self.n_bins, 512)))
+        dev = self.device
+        self.possible = torch.zeros(self.nkeys, dtype=torch.int64, device=dev)
+        self.obs_sum = torch.zeros(self.nkeys, dtype=torch.int64, device=dev)
+        self.totals = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.fit_result = torch.zeros(ctypes.sizeof(_lib.FitResult), dtype=torch.uint8, device=dev)
+        self.x = torch.zeros(self.max_bins, dtype=torch.float64, device=dev)
+        self.y = torch.zeros(self.max_bins, dtype=torch.float64, device=dev)
+        self.bin_of_key = torch.zeros(self.nkeys, dtype=torch.int32, device=dev)
+        self.spline_y = torch.zeros(self.nkeys, dtype=torch.float64, device=dev)
+        self.spline_raw = torch.zeros(self.nkeys, dtype=torch.float64, device=dev)
+        self.knots = torch.zeros(self.max_bins + 4, dtype=torch.float64, device=dev)
+        self.coefs = torch.zeros(self.max_bins + 4, dtype=torch.float64, device=dev)
+        ws = int(self.lib.bbk_fit_workspace_bytes(self.max_bins, self.nkeys))
+        self.fit_ws = torch.zeros(ws, dtype=torch.uint8, device=dev)
+        self.p_hist = torch.zeros(_lib.PHIST_LEN, dtype=torch.int64, device=dev)
+        self.bias = None
+        self.bh_ws = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ setup
+    def set_fragments(self, n_frags, max_frag):
+        """possible[] from per-chromosome fragment counts (fithic.py:302-311)."""
+        nf = torch.tensor(list(n_frags), dtype=torch.int64, device=self.device)
+        mf = torch.tensor(list(max_frag), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.bbk_possible_pairs(_lib.ptr(nf), _lib.ptr(mf), len(n_frags), self.R, self.nkeys,
+                                               _lib.ptr(self.possible), _lib.stream_ptr()), "bbk_possible_pairs")
+        self.launches += 1
+
+    def set_bias(self, tables):
+        self.bias = tables
+
+    # ------------------------------------------------------------------ stages
+    def hist(self, shards):
+        st = _lib.stream_ptr()
+        _lib.check(self.lib.bbk_hist_init(_lib.ptr(self.obs_sum), self.nkeys, _lib.ptr(self.totals), st), "bbk_hist_init")
+        self.launches += 1
+        for sh in shards:
+            if sh.n == 0:
+                continue
+            _lib.check(self.lib.bbk_hist_pairs(_lib.ptr(sh.chr1), _lib.ptr(sh.chr2), _lib.ptr(sh.mid1), _lib.ptr(sh.mid2),
+                                               _lib.ptr(sh.count), sh.n, self.R, self.min_dist, self.max_dist, self.nkeys,
+                                               _lib.ptr(self.obs_sum), _lib.ptr(self.totals), st), "bbk_hist_pairs")
+            self.launches += 1
+
+    def allreduce_stats(self, group=None):
+        """Sum the distance table and totals over ranks (integers: order-free, bit-exact)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        dist.all_reduce(self.obs_sum, op=dist.ReduceOp.SUM, group=group)
+        sums = self.totals[:6].clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        mn = self.totals[6:7].clone()
+        mx = self.totals[7:8].clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        self.totals[:6] = sums
+        self.totals[6:7] = mn
+        self.totals[7:8] = mx
+
+    def fit(self):
+        _lib.check(self.lib.bbk_fit(_lib.ptr(self.possible), _lib.ptr(self.obs_sum), self.nkeys, _lib.ptr(self.totals),
+                                    self.n_bins, self.R, self.min_dist, self.max_dist, self.max_bins,
+                                    _lib.ptr(self.fit_result), _lib.ptr(self.x), _lib.ptr(self.y), _lib.ptr(self.bin_of_key),
+                                    _lib.ptr(self.spline_y), _lib.ptr(self.spline_raw), _lib.ptr(self.knots),
+                                    _lib.ptr(self.coefs), _lib.ptr(self.fit_ws), self.fit_ws.numel(), _lib.stream_ptr()),
+                   "bbk_fit")
+        self.launches += 1
+
+    def pvalues(self, shard, p_out, with_hist=False):
+        bias = ctypes.byref(self.bias.struct) if self.bias is not None else None
+        _lib.check(self.lib.bbk_pvalues(_lib.ptr(shard.chr1), _lib.ptr(shard.chr2), _lib.ptr(shard.mid1), _lib.ptr(shard.mid2),
+                                        _lib.ptr(shard.count), shard.n, shard.chrom, self.R, self.min_dist, self.max_dist,
+                                        _lib.ptr(self.fit_result), _lib.ptr(self.spline_y), bias, _lib.ptr(p_out),
+                                        _lib.ptr(self.p_hist) if with_hist else None, _lib.stream_ptr()), "bbk_pvalues")
+        self.launches += 1
+
+    def qvalues(self, p, q, n_tests=-1, use_hist=False, rank=None, mode=_lib.BH_UNSORTED):
+        m = int(p.numel())
+        need = int(self.lib.bbk_bh_workspace_bytes(m))
+        if self.bh_ws is None or self.bh_ws.numel() < need:
+            self.bh_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.bbk_bh_qvalues(_lib.ptr(p), m, int(n_tests), mode, _lib.ptr(self.p_hist) if use_hist else None,
+                                           _lib.ptr(q), _lib.ptr(rank), _lib.ptr(self.bh_ws), self.bh_ws.numel(),
+                                           _lib.stream_ptr()), "bbk_bh_qvalues")
+        self.launches += (4 if mode == _lib.BH_POSITIONAL else 33 - (1 if use_hist else 0))
+
+    # ------------------------------------------------------------------ results
+    def read_fit(self):
+        """Copy the fit status back (synchronises) and raise what the reference would raise."""
+        raw = self.fit_result.cpu().numpy().tobytes()
+        res = _lib.FitResult.from_buffer_copy(raw)
+        err = _lib.FIT_STATUS.get(res.status, (RuntimeError, "fit stage failed with status %d" % res.status))
+        if err is not None:
+            raise err[0](err[1])
+        return res
+
+    def run(self, shards, p_outs, q_outs=None, n_tests=-1, group=None):
+        """The whole pass over `shards`; p_outs[i] (float64, len shards[i].n) receives the p-values.
+
+        q_outs (optional): per-shard q buffers.  q-values are computed per call over ALL shards
+        given here when they share one contiguous p buffer (see fithic.fit_transform_arrays).
+        """
+        self.hist(shards)
+        self.allreduce_stats(group)
+        self.fit()
+        fuse_hist = q_outs is not None and len(shards) == 1
+        if fuse_hist:
+            self.p_hist.zero_()
+        for sh, p in zip(shards, p_outs):
+            if sh.n:
+                self.pvalues(sh, p, with_hist=fuse_hist)
+        if q_outs is not None:
+            for p, q in zip(p_outs, q_outs):
+                if p.numel():
+                    self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist)

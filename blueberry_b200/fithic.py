@@ -1,0 +1,538 @@
+"""Drop-in for blueberry/fithic.py - same names, argument order, files and return types - with the
+work done by the sm_100a kernels of libbbk.so.
+
+Reference entry points mirrored here (paths relative to the reference root):
+    FitHiC(libname, resolution, n_bins=100, n_passes=2, max_dist=-1, min_dist=-1)   fithic.py:49-83
+    FitHiC.fit_transform(interactions, fragments, biases="none", verbose=False)      fithic.py:85-108
+    fithic(libname, resolution, n_bins, min_dist, max_dist, n_passes, interactions, frags, biases, verbose)  :110
+    generate_FragPairs / read_bias_file / read_interactions / calculate_probabilities / fit_spline
+    in_range_check(interactionDistance, min_dist, max_dist)                           fithic.py:445
+    benjamini_hochberg_correction(p_values, num_total_tests)                          fithic.py:466
+
+Added (the reference parses gzip text line by line; that is not GPU work):
+    FitHiC.fit_transform_arrays(...) -> PassOutput      records in / p (and q) out as arrays
+
+Deliberate deviations: the reference keeps all totals in module globals that
+are never reset (fithic.py:25-42), so a second call in one process accumulates onto the first; here
+every generate_FragPairs starts from the initial values (fresh-process semantics).  The module
+attributes of the same names are still updated after each stage.  n_passes is accepted and ignored,
+as in the reference (fithic.py:121-133 runs one pass).  No PNG is drawn.
+
+There is no CPU fallback: without libbbk.so and a CUDA device these functions raise.
+"""
+import gzip
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import BiasTables, PassEngine, Shard
+
+# ---- module globals of the reference (fithic.py:25-45), refreshed by the stage functions ----
+possibleIntraInRangeCount = 0
+observedIntraInRangeCount = 0
+observedIntraInRangeSum = 0
+possibleIntraAllCount = 0
+observedIntraAllCount = 0
+observedIntraAllSum = 0
+possibleInterAllCount = 0
+observedInterAllCount = 0
+observedInterAllSum = 0
+baselineIntraChrProb = 0
+interChrProb = 0
+minObservedGenomicDist = 500000000
+maxObservedGenomicDist = 0
+maxPossibleGenomicDist = 0
+distScaling = 10000.0
+
+_this = sys.modules[__name__]
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.BbkError("blueberry_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def in_range_check(interactionDistance, min_dist, max_dist):
+    """fithic.py:445-449."""
+    if (min_dist == -1 or (min_dist > -1 and interactionDistance > min_dist)) and \
+            (max_dist == -1 or (max_dist > -1 and interactionDistance <= max_dist)):
+        return True
+    return False
+
+
+# =================================================================================================
+# text ingest (host): the reference's three gzip formats -> arrays
+# =================================================================================================
+class _ChromIds(object):
+    """Chromosome name -> small integer id (order of first appearance)."""
+
+    def __init__(self):
+        self.ids = {}
+        self.names = []
+
+    def encode(self, names):
+        uniq, inv = np.unique(np.asarray(names, dtype=object), return_inverse=True)
+        lut = np.empty(len(uniq), dtype=np.int32)
+        for i, u in enumerate(uniq):
+            if u not in self.ids:
+                self.ids[u] = len(self.names)
+                self.names.append(u)
+            lut[i] = self.ids[u]
+        return lut[inv]
+
+
+def _read_table(path, ncols):
+    import pandas as pd
+    # whitespace split like str.split() (fithic.py:143,245,288); too few columns -> ValueError like the unpack
+    df = pd.read_csv(path, sep=r"\s+", header=None, compression="gzip", dtype=str, engine="c")
+    if df.shape[1] < ncols:
+        raise ValueError("not enough values to unpack (expected %d, got %d)" % (ncols, df.shape[1]))
+    return df
+
+
+def _parse_fragments(path, chroms):
+    df = _read_table(path, 2)                                  # fithic.py:288: first two columns
+    return chroms.encode(df[0].values), df[1].values.astype(np.int64)
+
+
+def _parse_interactions(path, chroms):
+    df = _read_table(path, 5)                                  # fithic.py:245
+    if df.shape[1] != 5:
+        raise ValueError("too many values to unpack (expected 5)")
+    return (chroms.encode(df[0].values), df[1].values.astype(np.int64), chroms.encode(df[2].values),
+            df[3].values.astype(np.int64), df[4].values.astype(np.int64))
+
+
+# =================================================================================================
+# fragments -> possible pairs (host bookkeeping, device table)
+# =================================================================================================
+class _FragInfo(object):
+    __slots__ = ("n_frags", "max_frag", "n_total", "max_possible", "nkeys", "possible_inter_all", "possible_intra_all")
+
+
+def _frag_info(frag_chrom, frag_mid, resolution):
+    """Per-chromosome fragment counts and the derived totals (fithic.py:284-318)."""
+    R = int(resolution)
+    frag_chrom = np.asarray(frag_chrom)
+    frag_mid = np.asarray(frag_mid, dtype=np.int64)
+    info = _FragInfo()
+    info.n_frags, info.max_frag = [], []
+    n_total, max_possible = 0, 0                               # module global starts at 0 (:42)
+    # allFragsDic[chr] is a dict keyed by mid: duplicates collapse (:289-291)
+    key = frag_chrom.astype(np.int64) * (1 << 40) + (frag_mid + (1 << 39))
+    uniq = np.unique(key)
+    uc = (uniq >> 40).astype(np.int64)
+    um = (uniq & ((1 << 40) - 1)) - (1 << 39)
+    for c in np.unique(uc):
+        sel = um[uc == c]
+        n = int(sel.size)
+        mf = int(sel.max()) - R // 2                           # :298 (py2 integer division)
+        info.n_frags.append(n)
+        info.max_frag.append(mf)
+        n_total += n
+        max_possible = max(max_possible, mf)                   # :300
+    inter, intra = 0, 0
+    for n in info.n_frags:
+        inter += n * (n_total - n)                             # :313
+        intra += (n * (n + 1)) // 2                            # :314
+    info.n_total = n_total
+    info.max_possible = max_possible
+    info.nkeys = len(range(0, max_possible + 1, R))            # :302
+    info.possible_inter_all = inter // 2                       # :316
+    info.possible_intra_all = intra
+    return info
+
+
+def _bias_tables(bias_dic, resolution, device, n_chrom_hint=0):
+    """biasDic {chrom id: {mid: bias}} -> dense device tables on the grid mid0 + i*R."""
+    R = int(resolution)
+    n_chrom = max([n_chrom_hint] + [c + 1 for c in bias_dic])
+    values, mid0 = [], []
+    for c in range(n_chrom):
+        sub = bias_dic.get(c)
+        if not sub:
+            values.append(np.zeros(0))
+            mid0.append(0)
+            continue
+        mids = np.fromiter(sub.keys(), dtype=np.int64, count=len(sub))
+        vals = np.fromiter(sub.values(), dtype=np.float64, count=len(sub))
+        m0 = int(mids.min())
+        off = mids - m0
+        if (off % R).any():
+            raise NotImplementedError("bias loci of chromosome id %d are not on one %d-bp grid; the device bias "
+                                      "table is dense (fixed-size windows)" % (c, R))
+        tab = np.full(int(off.max() // R) + 1, np.nan)
+        tab[off // R] = vals
+        values.append(tab)
+        mid0.append(m0)
+    return BiasTables(values, mid0, device)
+
+
+# =================================================================================================
+# the array entry point
+# =================================================================================================
+class PassOutput(object):
+    """Everything one pass produces, as numpy arrays / Python scalars."""
+    __slots__ = ("p", "q", "keep", "x", "y", "spline_x", "spline_y", "spline_y_raw", "residual", "possible",
+                 "observed", "bin_of_key", "totals", "frag", "fit", "gpu_launches")
+
+
+def _pad16(n):
+    return (n + 1) & ~1          # float64 slices must stay 16-byte aligned
+
+
+def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count,
+              bias_dic=None, want_q=False, n_tests=None, keep_device=False):
+    dev = _device()
+    info = _frag_info(frag_chrom, frag_mid, resolution)
+    eng = PassEngine(resolution, n_bins, min_dist, max_dist, info.nkeys, dev)
+    eng.set_fragments(info.n_frags, info.max_frag)
+    if bias_dic:
+        eng.set_bias(_bias_tables(bias_dic, resolution, dev))
+
+    def to_dev(a):
+        a = np.asarray(a)
+        if a.size and (a.min() < -2**31 or a.max() >= 2**31):
+            raise OverflowError("coordinates / counts must fit in int32 on the device")
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+
+    same = chr1 is None or (np.asarray(chr1) == np.asarray(chr2)).all() and np.unique(np.asarray(chr1)).size <= 1
+    if same:
+        chrom = int(np.asarray(chr1).flat[0]) if chr1 is not None and len(chr1) else 0
+        shard = Shard(to_dev(mid1), to_dev(mid2), to_dev(count), chrom=chrom)
+    else:
+        shard = Shard(to_dev(mid1), to_dev(mid2), to_dev(count), to_dev(chr1), to_dev(chr2))
+    n = shard.n
+    p = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n]
+    q = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n] if want_q else None
+    eng.run([shard], [p], [q] if want_q else None, n_tests=-1 if n_tests is None else int(n_tests))
+    fit = eng.read_fit()                                        # raises what the reference would raise
+
+    out = PassOutput()
+    out.fit = fit
+    out.frag = info
+    out.p = p.cpu().numpy()
+    out.q = q.cpu().numpy() if want_q else None
+    out.keep = out.p <= 1                                       # fithic.py:434 (NaN = not scored or dropped)
+    out.x = eng.x[:fit.n_out].cpu().numpy()
+    out.y = eng.y[:fit.n_out].cpu().numpy()
+    out.spline_x = (np.arange(fit.L, dtype=np.int64) + fit.k0) * int(resolution)
+    out.spline_y = eng.spline_y[:fit.L].cpu().numpy()
+    out.spline_y_raw = eng.spline_raw[:fit.L].cpu().numpy()
+    out.residual = float(fit.residual)
+    out.possible = eng.possible.cpu().numpy()
+    out.observed = eng.obs_sum.cpu().numpy()
+    out.bin_of_key = eng.bin_of_key.cpu().numpy()
+    t = eng.totals.cpu().numpy()
+    out.totals = {
+        "observedIntraInRangeSum": int(t[0]), "observedIntraInRangeCount": int(t[1]),
+        "observedIntraAllSum": int(t[2]), "observedIntraAllCount": int(t[3]),
+        "observedInterAllSum": int(t[4]), "observedInterAllCount": int(t[5]),
+        "minObservedGenomicDist": int(t[6]), "maxObservedGenomicDist": int(t[7]),
+        "maxPossibleGenomicDist": info.max_possible,
+        "possibleIntraAllCount": info.possible_intra_all, "possibleInterAllCount": info.possible_inter_all,
+        "possibleIntraInRangeCount": int(sum(int(v) for k, v in enumerate(out.possible)
+                                             if in_range_check(k * int(resolution), min_dist, max_dist))),
+    }
+    out.gpu_launches = eng.launches
+    return out
+
+
+class FitHiC(object):
+    """Fit-Hi-C transformer object (fithic.py:49-108) - same constructor, same fit_transform."""
+
+    def __init__(self, libname, resolution, n_bins=100, n_passes=2, max_dist=-1, min_dist=-1):
+        self.libname = libname
+        self.resolution = resolution
+        self.n_bins = n_bins
+        self.n_passes = n_passes
+        self.max_dist = max_dist if max_dist != -1 else 10000000     # fithic.py:82
+        self.min_dist = min_dist if min_dist != -1 else 0            # fithic.py:83
+
+    def fit_transform(self, interactions, fragments, biases="none", verbose=False):
+        """Paths in, files out, returns None - exactly fithic.py:85-108."""
+        fithic(self.libname, self.resolution, self.n_bins, self.min_dist, self.max_dist, self.n_passes,
+               interactions, fragments, biases, verbose)
+
+    def fit_transform_arrays(self, chr1, mid1, chr2, mid2, count, frag_chrom, frag_mid, bias=None,
+                             q_values=False, n_tests=None):
+        """The same pass on in-memory records.
+
+        chr1/chr2: integer chromosome ids per record (None: all records on one chromosome).
+        bias: None or (bias_chrom, bias_mid, bias_value) arrays in file order (fithic.py:143).
+        q_values: also compute Benjamini-Hochberg q-values over the emitted rows (the reference
+        writes the literal -1, fithic.py:435); n_tests defaults to the number of emitted rows.
+        """
+        bias_dic = None
+        if bias is not None:
+            bias_dic = _bias_dict_from_arrays(*bias)
+        return _run_pass(self.resolution, self.n_bins, self.min_dist, self.max_dist, frag_chrom, frag_mid,
+                         chr1, mid1, chr2, mid2, count, bias_dic, want_q=q_values, n_tests=n_tests)
+
+
+def _bias_dict_from_arrays(bias_chrom, bias_mid, bias_val):
+    """read_bias_file on arrays: out-of-[0.5,2] -> -1 (:147-149), first occurrence wins (:153-154)."""
+    bias_chrom = np.asarray(bias_chrom)
+    bias_mid = np.asarray(bias_mid, dtype=np.int64)
+    v = np.asarray(bias_val, dtype=np.float64).copy()
+    v[(v < 0.5) | (v > 2)] = -1.0
+    out = {}
+    key = bias_chrom.astype(np.int64) * (1 << 40) + (bias_mid + (1 << 39))
+    _, first = np.unique(key, return_index=True)
+    for i in np.sort(first):
+        out.setdefault(int(bias_chrom[i]), {})[int(bias_mid[i])] = float(v[i])
+    return out
+
+
+# =================================================================================================
+# the path-based pass and the reference's stage functions
+# =================================================================================================
+class _Session(object):
+    """State the reference keeps in module globals between its stage functions."""
+    chroms = None
+    frag = None
+    frag_arrays = None
+    contacts = None
+    result = None
+
+
+_session = _Session()
+
+
+def _publish(**kw):
+    for k, v in kw.items():
+        setattr(_this, k, v)
+
+
+def read_bias_file(infilename, verbose):
+    """fithic.py:136-158 -> {chr name: {mid: bias}}."""
+    if verbose:
+        sys.stderr.write("\n\nReading ICE biases. \n")
+    df = _read_table(infilename, 3)
+    if df.shape[1] != 3:
+        raise ValueError("too many values to unpack (expected 3)")
+    names = df[0].values
+    mids = df[1].values.astype(np.int64)
+    vals = df[2].values.astype(np.float64)
+    bad = (vals < 0.5) | (vals > 2)
+    vals = np.where(bad, -1.0, vals)
+    biases = {}
+    for c, m, b in zip(names, mids, vals):
+        sub = biases.setdefault(c, {})
+        if int(m) not in sub:
+            sub[int(m)] = -1 if b == -1.0 else float(b)
+    if verbose:
+        print("Out of " + str(len(df)) + " loci " + str(int(bad.sum())) + " were discarded with biases not in range [0.5 2]\n\n")
+    return biases
+
+
+def generate_FragPairs(infilename, resolution, min_dist, max_dist, verbose):
+    """fithic.py:272-332 -> mainDic {distance: [possible pairs, 0]}."""
+    if verbose:
+        print("\nEnumerating all possible intra-chromosomal fragment pairs in-range\n")
+        print("------------------------------------------------------------------------------------\n")
+    _session.chroms = _ChromIds()
+    fc, fm = _parse_fragments(infilename, _session.chroms)
+    info = _frag_info(fc, fm, resolution)
+    _session.frag = info
+    _session.frag_arrays = (fc, fm)
+    dev = _device()
+    eng = PassEngine(resolution, 100, min_dist, max_dist, info.nkeys, dev)
+    eng.set_fragments(info.n_frags, info.max_frag)
+    possible = eng.possible.cpu().numpy()
+    in_rng = sum(int(v) for k, v in enumerate(possible) if in_range_check(k * resolution, min_dist, max_dist))
+    _publish(maxPossibleGenomicDist=info.max_possible, possibleIntraAllCount=info.possible_intra_all,
+             possibleInterAllCount=info.possible_inter_all, possibleIntraInRangeCount=in_rng,
+             interChrProb=(1.0 / info.possible_inter_all if info.possible_inter_all > 0 else 0),
+             baselineIntraChrProb=1.0 / info.possible_intra_all,
+             observedIntraInRangeCount=0, observedIntraInRangeSum=0, observedIntraAllCount=0, observedIntraAllSum=0,
+             observedInterAllCount=0, observedInterAllSum=0, minObservedGenomicDist=500000000, maxObservedGenomicDist=0)
+    if verbose:
+        print("Number of all fragments= " + str(info.n_total) + "\t resolution= " + str(resolution))
+        print("Possible, Intra-chr in range: pairs= " + str(in_rng))
+        print("Possible, Intra-chr all: pairs= " + str(info.possible_intra_all))
+        print("Possible, Inter-chr all: pairs= " + str(info.possible_inter_all))
+        print("Desired genomic distance range	[%d %d]" % (min_dist, max_dist) + "\n")
+        print("Range of possible genomic distances	[0	%d]" % (info.max_possible) + "\n")
+    return {int(k) * int(resolution): [int(v), 0] for k, v in enumerate(possible)}
+
+
+def _main_dic_tables(mainDic, resolution):
+    keys = sorted(mainDic)
+    R = int(resolution)
+    if keys != [k * R for k in range(len(keys))]:
+        raise ValueError("mainDic keys must be 0, R, 2R, ... as generate_FragPairs builds them")
+    return (np.array([mainDic[k][0] for k in keys], dtype=np.int64),
+            np.array([mainDic[k][1] for k in keys], dtype=np.int64))
+
+
+def read_interactions(mainDic, infile, min_dist, max_dist, verbose):
+    """fithic.py:229-270: adds the contact counts per distance to mainDic (K1 on the device)."""
+    if verbose:
+        print("\nReading all the contact counts\n")
+        print("------------------------------------------------------------------------------------\n")
+    if _session.chroms is None:
+        _session.chroms = _ChromIds()
+    c1, m1, c2, m2, cnt = _parse_interactions(infile, _session.chroms)
+    _session.contacts = (c1, m1, c2, m2, cnt)
+    resolution = sorted(mainDic)[1] if len(mainDic) > 1 else 1
+    dev = _device()
+    eng = PassEngine(resolution, 100, min_dist, max_dist, len(mainDic), dev)
+    t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    eng.hist([Shard(t32(m1), t32(m2), t32(cnt), t32(c1), t32(c2))])
+    obs = eng.obs_sum.cpu().numpy()
+    t = eng.totals.cpu().numpy()
+    for k, key in enumerate(sorted(mainDic)):
+        mainDic[key][1] += int(obs[k])
+    _publish(observedIntraInRangeSum=_this.observedIntraInRangeSum + int(t[0]),
+             observedIntraInRangeCount=_this.observedIntraInRangeCount + int(t[1]),
+             observedIntraAllSum=_this.observedIntraAllSum + int(t[2]),
+             observedIntraAllCount=_this.observedIntraAllCount + int(t[3]),
+             observedInterAllSum=_this.observedInterAllSum + int(t[4]),
+             observedInterAllCount=_this.observedInterAllCount + int(t[5]),
+             minObservedGenomicDist=min(_this.minObservedGenomicDist, int(t[6])),
+             maxObservedGenomicDist=max(_this.maxObservedGenomicDist, int(t[7])))
+    if verbose:
+        print("Observed, Intra-chr in range: pairs= " + str(_this.observedIntraInRangeCount) + "\t totalCount= " + str(_this.observedIntraInRangeSum))
+        print("Observed, Intra-chr all: pairs= " + str(_this.observedIntraAllCount) + "\t totalCount= " + str(_this.observedIntraAllSum))
+        print("Observed, Inter-chr all: pairs= " + str(_this.observedInterAllCount) + "\t totalCount= " + str(_this.observedInterAllSum))
+        print("Range of observed genomic distances [%d %d]" % (_this.minObservedGenomicDist, _this.maxObservedGenomicDist) + "\n")
+    return mainDic
+
+
+def _fit_from_tables(possible, observed, S, n_bins, resolution, min_dist, max_dist):
+    dev = _device()
+    eng = PassEngine(resolution, n_bins, min_dist, max_dist, len(possible), dev)
+    eng.possible.copy_(torch.from_numpy(possible))
+    eng.obs_sum.copy_(torch.from_numpy(observed))
+    eng.totals.zero_()
+    eng.totals[0] = int(S)
+    eng.fit()
+    return eng
+
+
+def calculate_probabilities(mainDic, n_bins, resolution, min_dist, max_dist, filename, verbose):
+    """fithic.py:160-227 -> (x, y, yerr) lists.  Like the reference it opens (and never writes)
+    `filename + '.res<R>.txt'`."""
+    if verbose:
+        print("\nCalculating probability means and standard deviations by equal-occupancy binning of contact counts\n")
+        print("------------------------------------------------------------------------------------\n")
+    open(filename + '.res' + str(resolution) + '.txt', 'w').close()        # fithic.py:164
+    possible, observed = _main_dic_tables(mainDic, resolution)
+    S = _this.observedIntraInRangeSum
+    if verbose:
+        print("observed intra-chr read counts in range\t" + repr(S) + ",\tdesired number of contacts per bin\t" +
+              repr(S // n_bins) + ",\tnumber of bins\t" + repr(n_bins) + "\n")
+    eng = _fit_from_tables(possible, observed, S, n_bins, resolution, min_dist, max_dist)
+    raw = _lib.FitResult.from_buffer_copy(eng.fit_result.cpu().numpy().tobytes())
+    if raw.status in (-11, -13, -14):                         # binning errors; spline errors belong to fit_spline
+        err = _lib.FIT_STATUS[raw.status]
+        raise err[0](err[1])
+    n = raw.n_out
+    x = eng.x[:n].cpu().numpy().tolist()
+    y = eng.y[:n].cpu().numpy().tolist()
+    return x, y, [0.0] * n
+
+
+def fit_spline(mainDic, x, y, yerr, infilename, outfilename, biasDic, resolution, min_dist, max_dist, verbose):
+    """fithic.py:334-437: spline + antitonic fit on (x, y), then score every record of `infilename`
+    and write `<outfilename>.res<R>.significances.txt.gz`.  Returns (splineX, newSplineY, residual)."""
+    if verbose:
+        print("\nFit a univariate spline to the probability means\n")
+        print("------------------------------------------------------------------------------------\n")
+    dev = _device()
+    lib = _lib.load()
+    nkeys = len(mainDic)
+    m = len(x)
+    if m < 4:
+        raise ValueError("m > k must hold")
+    eng = PassEngine(resolution, max(m, 4), min_dist, max_dist, nkeys, dev, max_bins=max(m, 4))
+    xs = torch.tensor(list(x), dtype=torch.float64, device=dev)
+    ys = torch.tensor(list(y), dtype=torch.float64, device=dev)
+    ws_bytes = int(lib.bbk_fit_workspace_bytes(max(m, 4), nkeys)) + 16 * m + 64
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.bbk_fit_from_bins(_lib.ptr(xs), _lib.ptr(ys), m, nkeys, int(resolution), _lib.ptr(eng.fit_result),
+                                     _lib.ptr(eng.spline_y), _lib.ptr(eng.spline_raw), _lib.ptr(eng.knots),
+                                     _lib.ptr(eng.coefs), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "bbk_fit_from_bins")
+    # the scoring kernel reads S from the fit record
+    S = int(_this.observedIntraInRangeSum)
+    fit = eng.read_fit()
+    fit.S = S
+    eng.fit_result.copy_(torch.frombuffer(bytearray(bytes(fit)), dtype=torch.uint8))
+    splineX = [(fit.k0 + i) * int(resolution) for i in range(fit.L)]
+    newSplineY = eng.spline_y[:fit.L].cpu().numpy().tolist()
+    residual = float(fit.residual)
+
+    if verbose:
+        print("lower bound on mid-range distances  " + repr(min_dist) + ", upper bound on mid-range distances  " + repr(max_dist) + "\n")
+    chroms = _session.chroms if _session.chroms is not None else _ChromIds()
+    c1, m1, c2, m2, cnt = _parse_interactions(infilename, chroms)
+    if len(biasDic) > 0:
+        ids = {chroms.ids[name]: sub for name, sub in biasDic.items() if name in chroms.ids}
+        eng.set_bias(_bias_tables(ids, resolution, dev, n_chrom_hint=len(chroms.names)))
+    t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    shard = Shard(t32(m1), t32(m2), t32(cnt), t32(c1), t32(c2))
+    p = torch.empty(_pad16(shard.n), dtype=torch.float64, device=dev)[:shard.n]
+    eng.pvalues(shard, p)
+    pv = p.cpu().numpy()
+    _write_significances('{}.res{}.significances.txt.gz'.format(outfilename, resolution), chroms, c1, m1, c2, m2, cnt, pv, None)
+    _session.result = (pv,)
+    return splineX, newSplineY, residual
+
+
+def _write_significances(path, chroms, c1, m1, c2, m2, cnt, p, q):
+    """fithic.py:410-435: header + one row per record with p_val <= 1; q column is the literal -1
+    unless q-values were asked for."""
+    import pandas as pd
+    keep = p <= 1
+    names = np.asarray(chroms.names, dtype=object)
+    df = pd.DataFrame({
+        "chr1": names[c1[keep]], "fragmentMid1": m1[keep], "chr2": names[c2[keep]], "fragmentMid2": m2[keep],
+        "contactCount": cnt[keep], "p-value": p[keep],
+        "q-value": (np.full(int(keep.sum()), -1, dtype=np.int64) if q is None else q[keep]),
+    })
+    with gzip.open(path, "wt", compresslevel=1) as fh:
+        df.to_csv(fh, sep="\t", index=False, lineterminator="\n")
+
+
+def fithic(libname, resolution, n_bins, min_dist, max_dist, n_passes, interactions, frags, biases, verbose,
+           q_values=False):
+    """fithic.py:110-133: one pass (n_passes is ignored, as in the reference), files in / files out."""
+    chroms = _ChromIds()
+    fc, fm = _parse_fragments(frags, chroms)
+    bias_dic = None
+    if biases != 'none':
+        named = read_bias_file(biases, verbose)
+        for name in named:
+            chroms.encode([name])
+        bias_dic = {chroms.ids[name]: sub for name, sub in named.items()}
+    c1, m1, c2, m2, cnt = _parse_interactions(interactions, chroms)
+    if verbose:
+        print("\n\t\tSPLINE FIT PASS 1 (spline-1) \n")
+    open(libname + ".fithic_pass1" + '.res' + str(resolution) + '.txt', 'w').close()          # fithic.py:164
+    out = _run_pass(resolution, n_bins, min_dist, max_dist, fc, fm, c1, m1, c2, m2, cnt, bias_dic, want_q=q_values)
+    _publish(**out.totals)
+    _write_significances('{}.res{}.significances.txt.gz'.format(libname + ".spline_pass1", resolution),
+                         chroms, c1, m1, c2, m2, cnt, out.p, out.q)
+    if verbose:
+        print("\nExecution of fit-hic completed successfully. \n\n")
+    return
+
+
+def benjamini_hochberg_correction(p_values, num_total_tests):
+    """fithic.py:466-487: unsorted p in, q in input order out, as a list."""
+    dev = _device()
+    lib = _lib.load()
+    p = torch.tensor(np.asarray(p_values, dtype=np.float64), device=dev)
+    m = p.numel()
+    if m == 0:
+        return []
+    pp = torch.empty(_pad16(m), dtype=torch.float64, device=dev)[:m].copy_(p)
+    q = torch.empty(_pad16(m), dtype=torch.float64, device=dev)[:m]
+    ws = torch.empty(int(lib.bbk_bh_workspace_bytes(m)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.bbk_bh_qvalues(_lib.ptr(pp), m, int(num_total_tests), _lib.BH_UNSORTED, None, _lib.ptr(q), None,
+                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_bh_qvalues")
+    return q.cpu().numpy().tolist()

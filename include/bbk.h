@@ -1,0 +1,178 @@
+/* bbk.h - C ABI of libbbk.so, the B200 (sm_100a) kernels behind blueberry's Fit-Hi-C
+ * significance pass.
+ *
+ * The reference (jmschrei/blueberry) has no FFI or plugin interface: its boundary is a set of
+ * Python entry points in blueberry/fithic.py and blueberry/blueberry.pyx.  Each entry point below
+ * names the reference code it replaces (paths relative to the reference root).  The Python host
+ * in blueberry_b200/ keeps the reference's names and argument order and calls these functions
+ * through ctypes; INTEGRATION.md shows the binding a maintainer would add to the reference.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller; the library never allocates,
+ *     frees or keeps caller buffers.  Scratch is caller-provided after a *_workspace_bytes query.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 on
+ *     success or a negative BBK_E_* code, and leaves a message for bbk_last_error().
+ *   - no hidden global state: two calls never interact (the reference's module globals,
+ *     fithic.py:25-42, accumulate across calls - a documented deviation).
+ *   - results that later stages need (S, spline range, ...) stay on the device in BbkFitResult, so
+ *     the whole pass can be enqueued without a host synchronisation.
+ */
+#ifndef BBK_H
+#define BBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBK_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define BBK_OK 0
+#define BBK_E_INVALID (-1)      /* bad argument */
+#define BBK_E_CUDA (-2)         /* a CUDA runtime call failed; see bbk_last_error */
+#define BBK_E_WORKSPACE (-3)    /* workspace too small */
+#define BBK_E_UNSUPPORTED (-4)
+/* status codes the fit kernel leaves in BbkFitResult.status (see blueberry_b200/csrc/fit_stage.h) */
+#define BBK_FIT_OK 0
+#define BBK_FIT_ZERO_PAIRS_BIN (-11)   /* reference: ZeroDivisionError at fithic.py:216 */
+#define BBK_FIT_TOO_FEW_BINS (-12)     /* scipy: "m > k must hold" */
+#define BBK_FIT_TOO_MANY_BINS (-13)
+#define BBK_FIT_S_ZERO (-14)           /* reference: ZeroDivisionError at fithic.py:216 */
+#define BBK_FIT_X_NOT_INCREASING (-15)
+#define BBK_FIT_EMPTY_GRID (-16)       /* no distance key inside [min(x), max(x)] */
+
+int bbk_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int bbk_last_error(char* buf, size_t buflen);
+/* number of SMs of the current device (grid sizing is a multiple of it) */
+int bbk_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  contact histogram by genomic distance            replaces read_interactions, fithic.py:229-270
+ *
+ * totals[8] (int64): 0 observedIntraInRangeSum (S)   1 observedIntraInRangeCount
+ *                    2 observedIntraAllSum            3 observedIntraAllCount
+ *                    4 observedInterAllSum            5 observedInterAllCount
+ *                    6 minObservedGenomicDist         7 maxObservedGenomicDist
+ * bbk_hist_init sets obs_sum to 0 and totals to the reference's initial values (fithic.py:25-41);
+ * bbk_hist_pairs ACCUMULATES, so several shards (chromosomes, diagonal bands, ranks after an
+ * allreduce) can feed one table.  d_chr1/d_chr2 may both be NULL: all records intra-chromosomal.
+ * obs_sum[k] is mainDic[k*resolution][1]; nkeys = len(mainDic).
+ * ------------------------------------------------------------------------------------------- */
+int bbk_hist_init(int64_t* d_obs_sum, int32_t nkeys, int64_t* d_totals, void* stream);
+int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                   const int32_t* d_count, int64_t n_pairs, int64_t resolution, int64_t min_dist,
+                   int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2a possible pairs per distance                      replaces generate_FragPairs, fithic.py:302-311
+ * d_n_frags[c] = number of distinct fragment mids of chromosome c, d_max_frag[c] = max(mid) - R/2.
+ * possible[k] = sum_c (k*R <= max_frag[c] ? n_frags[c] - k : 0)        (goes negative like the
+ * reference when the fragment list is sparse).
+ * ------------------------------------------------------------------------------------------- */
+int bbk_possible_pairs(const int64_t* d_n_frags, const int64_t* d_max_frag, int32_t n_chrom, int64_t resolution,
+                       int32_t nkeys, int64_t* d_possible, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2b+K3  equal-occupancy binning, smoothing spline, antitonic regression
+ *         replaces calculate_probabilities (fithic.py:160-227) and the fit part of fit_spline
+ *         (fithic.py:340-374: UnivariateSpline(x, y, s=min(y)**2), ius(splineX),
+ *         IsotonicRegression(increasing=False)).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct BbkFitResult {
+    int32_t status;      /* BBK_FIT_* */
+    int32_t n_out;       /* number of bins emitted (len(x)) */
+    int32_t k0;          /* splineX[0] / resolution */
+    int32_t L;           /* len(splineX) */
+    int32_t n_knots;     /* knots of the spline (incl. the 2*4 boundary knots) */
+    int32_t ier;         /* FITPACK-style status of the spline search */
+    int64_t S;           /* observedIntraInRangeSum used */
+    double min_x, max_x; /* min(x), max(x) */
+    double residual;     /* sum((y - ius(x))**2), fithic.py:374 */
+    double fp;           /* weighted sum of squared residuals of the smoothing spline */
+    double smoothing;    /* s = min(y)**2 */
+} BbkFitResult;
+
+/* bytes of scratch bbk_fit needs for up to max_bins bins and nkeys distances */
+size_t bbk_fit_workspace_bytes(int32_t max_bins, int32_t nkeys);
+/* d_totals: the table K1 filled (S is read from d_totals[0] on the device).
+ * outputs: d_result (1 struct), d_x/d_y [max_bins], d_bin_of_key [nkeys] (-1 = none),
+ *          d_spline_y [nkeys] (entries 0..L-1 = newSplineY), d_spline_raw [nkeys] (ius(splineX)),
+ *          d_knots/d_coefs [max_bins+4]. */
+int bbk_fit(const int64_t* d_possible, const int64_t* d_obs_sum, int32_t nkeys, const int64_t* d_totals,
+            int32_t n_bins, int64_t resolution, int64_t min_dist, int64_t max_dist, int32_t max_bins,
+            BbkFitResult* d_result, double* d_x, double* d_y, int32_t* d_bin_of_key, double* d_spline_y,
+            double* d_spline_raw, double* d_knots, double* d_coefs, void* d_workspace, size_t workspace_bytes,
+            void* stream);
+/* stage-injection entry for tests: the spline + antitonic part alone on given bin means x, y */
+int bbk_fit_from_bins(const double* d_x_in, const double* d_y_in, int32_t m, int32_t nkeys, int64_t resolution,
+                      BbkFitResult* d_result, double* d_spline_y, double* d_spline_raw, double* d_knots,
+                      double* d_coefs, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  per-pair binomial survival p-values              replaces the scoring loop, fithic.py:413-435
+ *     p = bdtrc(count-1, S, newSplineY[i] * (bias1*bias2)),  i = min(bisect_left(splineX, clamp(d)), L-1)
+ * Rows the reference does not score (d outside [min_dist, max_dist], :427) or drops (p_val <= 1
+ * false, :434: negative prior from a -1 bias, prior > 1) get p = NaN.
+ * Bias lookup (biasDic[chr][mid], default 1.0, :418-425) is a dense per-chromosome table:
+ *   bias = d_bias[chrom_base[c] + (mid - mid0[c]) / resolution]  when (mid - mid0[c]) is a
+ *   non-negative multiple of resolution below the table end and the entry is not NaN; else 1.0.
+ * d_chr1/d_chr2 NULL: every record is on chromosome `shard_chrom`.
+ * d_p_hist (nullable, int64[BBK_PHIST_LEN]): K4 adds the coarse p-value histogram the BH step uses
+ * for pruning, saving BH one pass over p.  Bucket of a p in [0, 1) = (IEEE bits >> 51) & 4095
+ * (exponent + top mantissa bit); entry [4096] counts p == 1.0 exactly, entry [4097] counts NaN.
+ * ------------------------------------------------------------------------------------------- */
+#define BBK_PHIST_BINS 4096
+#define BBK_PHIST_LEN (BBK_PHIST_BINS + 2)
+typedef struct BbkBiasTable {
+    const double* d_bias;        /* concatenated per-chromosome tables (NaN = locus absent), NULL = no biases */
+    const int64_t* d_chrom_base; /* [n_chrom + 1] offsets into d_bias */
+    const int64_t* d_mid0;       /* [n_chrom] mid of entry 0 of each chromosome */
+    int32_t n_chrom;
+} BbkBiasTable;
+
+int bbk_pvalues(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                const int32_t* d_count, int64_t n_pairs, int32_t shard_chrom, int64_t resolution, int64_t min_dist,
+                int64_t max_dist, const BbkFitResult* d_fit, const double* d_spline_y, const BbkBiasTable* bias,
+                double* d_p, int64_t* d_p_hist, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  Benjamini-Hochberg q-values as the reference computes them: a FORWARD running max of
+ *     min(p * N / rank, 1)   (fithic.py:466-487, blueberry.pyx:40-75) - not the textbook reverse
+ *     cumulative minimum.  q comes back in input order; NaN p (dropped rows) -> NaN q, not ranked.
+ * mode BBK_BH_UNSORTED   : benjamini_hochberg_correction(p_values, N)   (fithic.py:466)
+ * mode BBK_BH_POSITIONAL : benjamini_hochberg(p_values, n) of blueberry.pyx:40 - the input is taken
+ *                          as already sorted, rank = position + 1, no tie handling.
+ * d_p_hist: optional coarse histogram from bbk_pvalues (NULL: computed here).
+ * d_rank (nullable, int64[m]): 1 + number of strictly smaller p among the ranked rows.
+ * ------------------------------------------------------------------------------------------- */
+#define BBK_BH_UNSORTED 0
+#define BBK_BH_POSITIONAL 1
+size_t bbk_bh_workspace_bytes(int64_t m);
+int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int32_t mode, const int64_t* d_p_hist,
+                   double* d_q, int64_t* d_rank, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  count_band_regions                               replaces blueberry.pyx:77-91
+ *     t = #{(i, j) : j < i, low <= regions[i] - regions[j] <= high}
+ * d_result: TWO int64 (device): [0] the count, [1] scratch.  Exact for sorted and unsorted input.
+ * ------------------------------------------------------------------------------------------- */
+int bbk_count_band(const double* d_regions, int64_t n, double low, double high, int64_t* d_result, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic contact records of the BASELINE shapes, generated on the device (bench only).
+ * Fills mid1/mid2/count for one chromosome of n_bins bins: all (i, i+d), 0 <= d <= K, row-major.
+ * d_bias (nullable): per-bin visibility multiplying the Poisson mean.  Returns records written
+ * through *n_written (host).
+ * ------------------------------------------------------------------------------------------- */
+int64_t bbk_synth_n_pairs(int64_t n_bins, int64_t K);
+int bbk_synth_contacts(int64_t n_bins, int64_t K, int64_t resolution, double depth, double decay, uint64_t seed,
+                       const double* d_bias, int32_t* d_mid1, int32_t* d_mid2, int32_t* d_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBK_H */

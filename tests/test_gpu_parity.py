@@ -1,0 +1,345 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libbbk.so) against the CPU oracle and the
+golden vectors minted from the reference.  Run on the B200 box with `pytest -m gpu`.
+
+Bars (DESIGN.md "Parity contract"):
+  * bit-exact: possible pairs, per-distance sums, all totals, bin membership, bin x / y, spline knots,
+    BH q-values given the same p, BH ranks, count_band_regions;
+  * |delta log10 p| <= 1e-6 against the reference's own output (golden files, S up to 2e5);
+  * |delta log10 p| <= 1e-5 against scipy.special.bdtrc at S up to 2^31 (cephes' own error there is
+    3e-6, measured against 60-digit arithmetic) and <= 1e-9 against the 60-digit value.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import PASS_CASES, golden_bias_dict, load_golden, log10_close
+
+pytestmark = pytest.mark.gpu
+
+P_TOL_GOLDEN = 1e-6
+P_TOL_SCIPY = 1e-5
+P_TOL_TRUTH = 1e-9
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _bias_arg(g):
+    if not bool(g["has_bias"]):
+        return None
+    return (g["bias_chrom"], g["bias_mid"], g["bias_val"])
+
+
+def _run_case(g, q_values=False):
+    from blueberry_b200.fithic import FitHiC
+    model = FitHiC("unused", int(g["resolution"]), n_bins=int(g["n_bins"]),
+                   max_dist=int(g["max_dist_arg"]), min_dist=int(g["min_dist_arg"]))
+    return model.fit_transform_arrays(g["chr1"], g["mid1"], g["chr2"], g["mid2"], g["count"],
+                                      g["frag_chrom"], g["frag_mid"], bias=_bias_arg(g), q_values=q_values)
+
+
+@pytest.mark.parametrize("name", PASS_CASES)
+def test_pass_against_reference_golden(name, torch_cuda):
+    g = load_golden(name)
+    out = _run_case(g)
+    # K2a / K1: integers, bit exact
+    assert np.array_equal(out.possible, g["ref_possible"])
+    assert np.array_equal(out.observed, g["ref_observed"])
+    t = out.totals
+    assert t["observedIntraInRangeSum"] == int(g["ref_S"])
+    assert t["observedIntraInRangeCount"] == int(g["ref_intra_in_range_count"])
+    assert t["observedIntraAllSum"] == int(g["ref_intra_all_sum"])
+    assert t["observedIntraAllCount"] == int(g["ref_intra_all_count"])
+    assert t["observedInterAllSum"] == int(g["ref_inter_all_sum"])
+    assert t["observedInterAllCount"] == int(g["ref_inter_all_count"])
+    assert t["minObservedGenomicDist"] == int(g["ref_min_obs_dist"])
+    assert t["maxObservedGenomicDist"] == int(g["ref_max_obs_dist"])
+    assert t["maxPossibleGenomicDist"] == int(g["ref_max_possible_dist"])
+    assert t["possibleIntraInRangeCount"] == int(g["ref_possible_intra_in_range"])
+    assert t["possibleIntraAllCount"] == int(g["ref_possible_intra_all"])
+    assert t["possibleInterAllCount"] == int(g["ref_possible_inter_all"])
+    # K2b: bins, bit exact (same float64 operation order as the reference loop)
+    assert np.array_equal(out.x, g["ref_x"])
+    assert np.array_equal(out.y, g["ref_y"])
+    # K3: spline grid and antitonic values
+    assert np.array_equal(out.spline_x, g["ref_spline_x"])
+    assert np.allclose(out.spline_y, g["ref_spline_y"], rtol=1e-12, atol=0)
+    n_exact = int((out.spline_y == g["ref_spline_y"]).sum())
+    print("%s: spline_y bit-exact on %d of %d grid points; residual %r vs %r" %
+          (name, n_exact, len(out.spline_y), out.residual, float(g["ref_residual"])))
+    assert abs(out.residual - float(g["ref_residual"])) <= 1e-12 * abs(float(g["ref_residual"]))
+    # K4: the rows the reference emitted, in order, with its p-values
+    keep = out.keep
+    assert int(keep.sum()) == len(g["ref_out_p"])
+    assert np.array_equal(g["mid1"][keep], g["ref_out_mid1"])
+    assert np.array_equal(g["mid2"][keep], g["ref_out_mid2"])
+    assert np.array_equal(g["count"][keep], g["ref_out_count"])
+    ok, nbad = log10_close(out.p[keep], g["ref_out_p"], P_TOL_GOLDEN)
+    assert ok, "%d p-values differ by more than %g in log10" % (nbad, P_TOL_GOLDEN)
+
+
+@pytest.mark.parametrize("name", PASS_CASES)
+def test_bin_membership_bit_exact(name, torch_cuda):
+    from oracle import fithic_oracle as fo
+    g = load_golden(name)
+    out = _run_case(g)
+    _, _, _, bok = fo.calculate_probabilities(g["ref_possible"], g["ref_observed"], int(g["ref_S"]), int(g["n_bins"]),
+                                              int(g["resolution"]), int(g["ref_min_dist"]), int(g["ref_max_dist"]))
+    assert np.array_equal(out.bin_of_key, bok)
+
+
+def _score_table(torch, priors, counts, S, bias=None):
+    """Drive K4 directly: record i looks up priors[i] (mid1 = 0, mid2 = i, resolution 1)."""
+    from blueberry_b200 import _lib
+    from blueberry_b200.engine import PassEngine, Shard
+    n = len(priors)
+    eng = PassEngine(1, 100, 0, n, n, torch.device("cuda:0"))
+    eng.spline_y[:n] = torch.from_numpy(np.asarray(priors, dtype=np.float64)).cuda()
+    fr = _lib.FitResult(status=0, n_out=100, k0=0, L=n, n_knots=8, ier=0, S=int(S), min_x=0.0, max_x=float(n - 1),
+                        residual=0.0, fp=0.0, smoothing=0.0)
+    eng.fit_result.copy_(torch.frombuffer(bytearray(bytes(fr)), dtype=torch.uint8))
+    z = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    mid2 = torch.arange(n, dtype=torch.int32, device="cuda:0")
+    cnt = torch.from_numpy(np.asarray(counts, dtype=np.int32)).cuda()
+    p = torch.empty((n + 1) & ~1, dtype=torch.float64, device="cuda:0")[:n]
+    eng.pvalues(Shard(z, mid2, cnt), p)
+    torch.cuda.synchronize()
+    return p.cpu().numpy()
+
+
+def _random_tail_cases(rng, n, S):
+    mu = 10 ** rng.uniform(-4, 3.3, n)
+    mu = np.minimum(mu, S * 0.4)
+    q = mu / S
+    sd = np.sqrt(mu)
+    c = np.maximum(0, mu + rng.uniform(-6, 12, n) * sd + rng.integers(0, 4, n)).astype(np.int64)
+    small = rng.random(n) < 0.3
+    c[small] = rng.integers(0, 12, int(small.sum()))
+    c = np.minimum(c, min(S, 2**31 - 1))
+    return q, c
+
+
+@pytest.mark.parametrize("S", [1000, 213498, 50_000_000, 1_500_000_000, 2**31 - 1])
+def test_pvalue_kernel_against_scipy(S, torch_cuda):
+    import scipy.special as sc
+    rng = np.random.default_rng(S % 9973)
+    q, c = _random_tail_cases(rng, 200_001, S)      # odd length: exercises the scalar tail of the kernel
+    got = _score_table(torch_cuda, q, c, S)
+    with np.errstate(all="ignore"):
+        ref = sc.bdtrc((c - 1).astype(np.float64), np.int64(S), q)
+    assert not np.isnan(got).any() and not np.isnan(ref).any()
+    big = ref >= 1e-300                              # below that cephes is in its denormal / underflow regime
+    ok, nbad = log10_close(got[big], ref[big], P_TOL_SCIPY)
+    assert ok, "%d of %d differ by more than %g in log10" % (nbad, int(big.sum()), P_TOL_SCIPY)
+    assert (got[~big] <= 1e-299).all()
+    assert (got[c == 0] == 1.0).all()
+    err = np.abs(np.log10(got[big & (ref < 1)]) - np.log10(ref[big & (ref < 1)]))
+    print("S=%d: max |dlog10 p| vs scipy %.3g, p99 %.3g" % (S, err.max(), np.percentile(err, 99)))
+
+
+def test_pvalue_kernel_against_60_digit_truth(torch_cuda):
+    import mpmath as mp
+    mp.mp.dps = 60
+    rng = np.random.default_rng(77)
+    S = 1_234_567_891
+    q, c = _random_tail_cases(rng, 600, S)
+    c = np.maximum(c, 2)
+    got = _score_table(torch_cuda, q, c, S)
+
+    def truth(cc, n, qq):
+        qq = mp.mpf(float(qq))
+        lp = mp.loggamma(n + 1) - mp.loggamma(cc + 1) - mp.loggamma(n - cc + 1) + cc * mp.log(qq) + (n - cc) * mp.log(1 - qq)
+        qr = qq / (1 - qq)
+        if cc >= (n + 1) * qq:
+            term = mp.mpf(1); s = mp.mpf(1); j = cc
+            while j < n:
+                term *= mp.mpf(n - j) / (j + 1) * qr; s += term; j += 1
+                if term < mp.mpf(10) ** -45 * s:
+                    break
+            return mp.exp(lp) * s
+        term = mp.mpf(cc) / ((n - cc + 1) * qr); s = term; j = cc - 1
+        while j > 0:
+            term *= mp.mpf(j) / ((n - j + 1) * qr); s += term; j -= 1
+            if term < mp.mpf(10) ** -45 * s:
+                break
+        return 1 - mp.exp(lp) * s
+
+    worst = 0.0
+    for i in range(len(c)):
+        tv = truth(int(c[i]), S, q[i])
+        if tv < mp.mpf(10) ** -290:
+            continue
+        worst = max(worst, abs(float(mp.log10(tv)) - np.log10(got[i])))
+    print("max |dlog10 p| vs 60-digit truth: %.3g" % worst)
+    assert worst <= P_TOL_TRUTH
+
+
+def test_pvalue_edge_semantics_match_bdtrc(torch_cuda):
+    import scipy.special as sc
+    S = 100
+    priors = np.array([-0.5, 1.5, 0.5, 0.5, 0.5, 0.0, 1.0, 0.0, 1.0, np.nan, 0.02, 0.005, 0.3, 0.3, -0.1, 0.5])
+    counts = np.array([0, 0, 0, -3, 102, 1, 1, 2, 2, 3, 1, 1, 101, 100, 5, 7])
+    got = _score_table(torch_cuda, priors, counts, S)
+    with np.errstate(all="ignore"):
+        ref = sc.bdtrc((counts - 1).astype(np.float64), np.int64(S), priors)
+    ref = np.where(ref <= 1, ref, np.nan)             # fithic.py:434 drops the row
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    m = ~np.isnan(ref)
+    assert np.allclose(got[m], ref[m], rtol=1e-12, atol=0)
+    assert got[2] == 1.0 and got[3] == 1.0 and got[5] == 0.0 and got[6] == 1.0 and got[12] == 0.0
+
+
+def _bh_device(torch, p, n_tests, positional=False, want_rank=False):
+    from blueberry_b200 import _lib
+    lib = _lib.load()
+    m = len(p)
+    dp = torch.empty((m + 1) & ~1, dtype=torch.float64, device="cuda:0")[:m].copy_(torch.from_numpy(np.asarray(p, np.float64)))
+    dq = torch.full(((m + 1) & ~1,), -7.0, dtype=torch.float64, device="cuda:0")[:m]
+    dr = torch.full((m,), -7, dtype=torch.int64, device="cuda:0") if want_rank else None
+    ws = torch.empty(int(lib.bbk_bh_workspace_bytes(m)), dtype=torch.uint8, device="cuda:0")
+    _lib.check(lib.bbk_bh_qvalues(_lib.ptr(dp), m, int(n_tests), _lib.BH_POSITIONAL if positional else _lib.BH_UNSORTED,
+                                  None, _lib.ptr(dq), _lib.ptr(dr), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bh")
+    torch.cuda.synchronize()
+    return dq.cpu().numpy(), (dr.cpu().numpy() if want_rank else None)
+
+
+def test_bh_against_reference_golden(torch_cuda):
+    from blueberry_b200.blueberry import benjamini_hochberg, count_band_regions
+    from blueberry_b200.fithic import benjamini_hochberg_correction
+    g = load_golden("bh_band")
+    for tag in ("a", "b", "c", "doc"):
+        p, n = g["p_" + tag], int(g["n_" + tag])
+        q = benjamini_hochberg_correction(list(p), n)
+        assert isinstance(q, list)
+        assert np.array_equal(np.array(q), g["q_py_" + tag]), tag
+        qs = benjamini_hochberg(np.sort(p), n)
+        assert isinstance(qs, np.ndarray) and qs.dtype == np.float64
+        assert np.array_equal(qs, g["q_cy_sorted_" + tag]), tag
+    assert count_band_regions(g["regions_sorted"]) == int(g["band_sorted"])
+    assert count_band_regions(g["regions_shuffled"]) == int(g["band_shuffled"])
+
+
+@pytest.mark.parametrize("m,frac_ones,n_scale", [(1, 0.0, 1.0), (2, 0.5, 1.0), (4097, 0.0, 1.0), (300_001, 0.6, 1.0),
+                                                  (300_001, 0.0, 50.0), (300_001, 0.3, 0.01), (2_000_003, 0.8, 1.0)])
+def test_bh_random_bit_exact(m, frac_ones, n_scale, torch_cuda):
+    from oracle import fithic_oracle as fo
+    rng = np.random.default_rng(m + int(frac_ones * 10))
+    p = rng.random(m) ** 3
+    p[rng.random(m) < frac_ones] = 1.0
+    if m > 100:
+        p[rng.integers(0, m, m // 10)] = p[rng.integers(0, m, m // 10)]      # ties
+        p[rng.integers(0, m, 5)] = 0.0
+        p[rng.integers(0, m, 5)] = 5e-324
+        p[rng.integers(0, m, 50)] = 10.0 ** rng.uniform(-300, -5, 50)
+    n_tests = max(1, int(m * n_scale))
+    q, _ = _bh_device(torch_cuda, p, n_tests)
+    ref = fo.benjamini_hochberg_correction(p, n_tests)
+    assert np.array_equal(q, ref)
+    # with NaN rows (dropped by fithic.py:434): not ranked, q = NaN, others unchanged
+    if m > 100:
+        p2 = p.copy()
+        nan_at = rng.integers(0, m, m // 20)
+        p2[nan_at] = np.nan
+        q2, rk = _bh_device(torch_cuda, p2, n_tests, want_rank=True)
+        valid = ~np.isnan(p2)
+        ref2 = fo.benjamini_hochberg_correction(p2[valid], n_tests)
+        assert np.isnan(q2[~valid]).all() and np.array_equal(q2[valid], ref2)
+        srt = np.sort(p2[valid])
+        assert np.array_equal(rk[valid], 1 + np.searchsorted(srt, p2[valid], side="left"))
+        assert (rk[~valid] == 0).all()
+
+
+def test_bh_positional_matches_cython_semantics(torch_cuda):
+    from oracle import fithic_oracle as fo
+    rng = np.random.default_rng(4)
+    for m in (1, 7, 100_003):
+        p = np.sort(rng.random(m) ** 2)
+        q, _ = _bh_device(torch_cuda, p, 3 * m, positional=True)
+        assert np.array_equal(q, fo.benjamini_hochberg_sorted(p, 3 * m))
+        # not actually sorted: the reference does not care, it scans in the given order (blueberry.pyx:67-73)
+        p = rng.random(m)
+        q, _ = _bh_device(torch_cuda, p, m, positional=True)
+        assert np.array_equal(q, fo.benjamini_hochberg_sorted(p, m))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 257, 5000])
+def test_count_band_regions(n, torch_cuda):
+    from blueberry_b200.blueberry import count_band_regions
+    from oracle import fithic_oracle as fo
+    rng = np.random.default_rng(n)
+    reg = np.sort(rng.choice(60000, n, replace=False)).astype(np.float64) * 1000 + 500
+    assert count_band_regions(reg) == fo.count_band_regions(reg)
+    if n > 2:
+        shuf = reg[rng.permutation(n)]
+        assert count_band_regions(shuf) == fo.count_band_regions(shuf)
+        dup = np.sort(np.concatenate([reg, reg[: n // 3]]))
+        assert count_band_regions(dup) == fo.count_band_regions(dup)
+    with pytest.raises(TypeError):
+        count_band_regions(reg.astype(np.float32))
+
+
+def test_fit_stage_injection_against_scipy(torch_cuda):
+    """K3 alone on given (x, y): knots bit-exact against scipy's FITPACK, antitonic values against sklearn."""
+    import warnings
+    from scipy.interpolate import UnivariateSpline
+    from sklearn.isotonic import IsotonicRegression
+    from blueberry_b200 import _lib
+    torch = torch_cuda
+    lib = _lib.load()
+    rng = np.random.default_rng(12)
+    R, nkeys = 5000, 2001
+    exact_knots = 0
+    trials = 25
+    for trial in range(trials):
+        m = int(rng.integers(8, 140))
+        x = np.sort(rng.choice(np.arange(1, nkeys - 1), m, replace=False)).astype(np.float64) * R + rng.random(m) * 100
+        y = 1e-3 * (x / R + 1) ** -1.08 * np.exp(rng.normal(0, 0.08 if trial % 2 else 0.3, m))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ius = UnivariateSpline(x, y, s=float(min(y) ** 2))
+        keys = np.arange(nkeys) * R
+        sx = keys[(keys >= x.min()) & (keys <= x.max())]
+        raw = ius(sx)
+        ref = IsotonicRegression(increasing=False).fit_transform(sx, raw)
+        dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+        res = torch.zeros(ctypes.sizeof(_lib.FitResult), dtype=torch.uint8, device="cuda:0")
+        sy = torch.zeros(nkeys, dtype=torch.float64, device="cuda:0")
+        sraw = torch.zeros(nkeys, dtype=torch.float64, device="cuda:0")
+        kn = torch.zeros(m + 8, dtype=torch.float64, device="cuda:0")
+        co = torch.zeros(m + 8, dtype=torch.float64, device="cuda:0")
+        nb = int(lib.bbk_fit_workspace_bytes(max(m, 4), nkeys)) + 16 * m + 64
+        ws = torch.zeros(nb, dtype=torch.uint8, device="cuda:0")
+        _lib.check(lib.bbk_fit_from_bins(_lib.ptr(dx), _lib.ptr(dy), m, nkeys, R, _lib.ptr(res), _lib.ptr(sy), _lib.ptr(sraw),
+                                         _lib.ptr(kn), _lib.ptr(co), _lib.ptr(ws), nb, _lib.stream_ptr()), "fit_from_bins")
+        torch.cuda.synchronize()
+        fr = _lib.FitResult.from_buffer_copy(res.cpu().numpy().tobytes())
+        assert fr.status == 0
+        t_ref = ius._data[8][:ius._data[7]]
+        assert fr.n_knots == len(t_ref)
+        assert np.array_equal(kn.cpu().numpy()[:fr.n_knots], t_ref)
+        exact_knots += 1
+        assert fr.L == len(sx) and fr.k0 * R == sx[0]
+        assert np.array_equal(co.cpu().numpy()[:fr.n_knots - 4], ius._data[9][:fr.n_knots - 4])
+        assert np.array_equal(sraw.cpu().numpy()[:fr.L], raw)
+        assert np.array_equal(sy.cpu().numpy()[:fr.L], ref)
+    assert exact_knots == trials
+
+
+def test_error_behaviour_matches_reference(torch_cuda):
+    from blueberry_b200.fithic import FitHiC
+    from blueberry_b200 import synth
+    R = 10000
+    fc, fm = synth.make_fragments([50], R)
+    c = synth.make_contacts([50], R, 200000, 5.0, 3)
+    model = FitHiC("x", R, n_bins=20, max_dist=200000)
+    # no in-range contacts at all -> the reference divides by observedIntraInRangeSum == 0 (fithic.py:216)
+    with pytest.raises(ZeroDivisionError):
+        model.fit_transform_arrays(None, c["mid1"], None, c["mid2"], np.zeros_like(c["count"]), fc, fm)
+    # too few bins for a cubic spline -> scipy's "m > k must hold"
+    with pytest.raises(ValueError):
+        FitHiC("x", R, n_bins=2, max_dist=200000).fit_transform_arrays(None, c["mid1"], None, c["mid2"], c["count"], fc, fm)
