@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py - Fit-Hi-C contact pairs/sec on B200 (BASELINE.json's metric), one JSON line on stdout.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
+
+Workload (config.workload): BASELINE config 2 - chr1 at 5 kb (49,851 bins), every pair within 10 Mb
+(97,750,851 records, zeros kept), ICE-style biases, synthetic counts generated on the device.
+At N > 1 every rank holds one such chromosome-sized shard (weak scaling): the per-distance table and
+totals are all-reduced over NCCL (S, the bins and the spline are genome-wide, identical on all ranks),
+p-values and q-values are per shard (per-chromosome q, as the authors' per-chromosome result files).
+A "step" is one whole pass over the resident records: K1 histogram -> [allreduce] -> K2/K3 fit ->
+K4 p-values (+ coarse p histogram) -> K5 Benjamini-Hochberg q-values.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RESOLUTION = 5000
+CHR1_BINS = 49851            # ceil(249,250,621 / 5000)
+MAX_DIST = 10_000_000
+N_BINS = 100
+DEPTH = 600.0                # Poisson mean of a d=0 pair with unit bias -> S ~ 2e8 per shard (8 shards stay < 2^31)
+DECAY = 1.08
+SEED = 20161108
+BYTES_PER_PAIR = 48          # 12 (K1 read) + 20 (K4 read+write) + 16 (K5 read+write), BASELINE.md section 2
+K4_BYTES_PER_PAIR = 20
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.tmp.name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# =================================================================================================
+# CPU arm: the oracle port of the reference path on the host cores
+# =================================================================================================
+def _cpu_block(args):
+    """One bounded sample: a chromosome-shaped block (nb bins, all pairs within max_dist) through the whole
+    reference path restated in oracle/fithic_oracle.py: histogram, binning, spline, scoring, BH."""
+    nb, seed, repeat = args
+    import numpy as np
+    from blueberry_b200 import synth
+    from oracle import fithic_oracle as fo
+    bias = synth.make_bias([nb], seed)
+    fc, fm = synth.make_fragments([nb], RESOLUTION)
+    c = synth.make_contacts([nb], RESOLUTION, MAX_DIST, DEPTH, seed, bias)
+    bd, _ = fo.read_bias_arrays(np.zeros(nb, dtype=np.int64), fm, bias[0])
+    t0 = time.perf_counter()
+    for _ in range(repeat):
+        res = fo.fithic_arrays(fc, fm, None, c["mid1"], None, c["mid2"], c["count"], RESOLUTION, N_BINS, 0, MAX_DIST, bias=bd)
+        keep = res.keep
+        fo.benjamini_hochberg_correction(res.p[keep], int(keep.sum()))
+    return len(c["count"]) * repeat, time.perf_counter() - t0
+
+
+def cpu_baseline(cores, nb=3000, repeat=1):
+    """pairs/s of the oracle port on `cores` host processes (each gets its own block)."""
+    import multiprocessing as mp
+    jobs = [(nb, SEED + 101 * i, repeat) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_block(jobs[0])]
+        wall = res[0][1]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_block, jobs)
+        wall = max(r[1] for r in res)              # slowest worker's compute time (generation excluded)
+    pairs = sum(r[0] for r in res)
+    return pairs / wall, pairs, wall, time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cores = min(cores, 64)
+    nb = 2600
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(cores, nb=nb)
+    vals, per_step = [], []
+    for _ in range(args.steps):
+        v, pairs, wall, _ = cpu_baseline(cores, nb=nb)
+        vals.append(v); per_step.append(wall)
+    value = statistics.mean(vals)
+    sample = "%d blocks/step of %d bins (all pairs within 10 Mb at 5 kb, ~%.1fM records each), one per core" % (
+        cores, nb, (2001 * nb - 2000 * 2001 // 2) / 1e6)
+    line = {
+        "impl": "reference", "metric": "fithic_contact_pairs_per_sec", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(per_step),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2 chr1@5kb pairs within 10Mb (bounded sample per step)", "resolution": RESOLUTION,
+                   "n_bins": N_BINS, "max_dist": MAX_DIST},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# =================================================================================================
+# GPU arm
+# =================================================================================================
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from blueberry_b200 import _lib
+    from blueberry_b200.engine import BiasTables, PassEngine, Shard
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    R, nb, K = RESOLUTION, args.bins, MAX_DIST // RESOLUTION
+    P = int(lib.bbk_synth_n_pairs(nb, K))
+    # ---- synthetic shard, generated on the device (not timed)
+    rng = np.random.default_rng(SEED + 7919 * rank)
+    bias_host = np.exp(rng.normal(0.0, 0.25, size=nb))
+    bias_dev = torch.from_numpy(bias_host).to(dev)
+    mid1 = torch.empty(P, dtype=torch.int32, device=dev)
+    mid2 = torch.empty(P, dtype=torch.int32, device=dev)
+    count = torch.empty(P, dtype=torch.int32, device=dev)
+    _lib.check(lib.bbk_synth_contacts(nb, K, R, DEPTH, DECAY, SEED + rank, _lib.ptr(bias_dev), _lib.ptr(mid1), _lib.ptr(mid2),
+                                      _lib.ptr(count), _lib.stream_ptr()), "bbk_synth_contacts")
+    shard = Shard(mid1, mid2, count, chrom=rank)
+    # ---- the genome: `world` chromosomes of nb bins each (fragment mid = i*R + R/2)
+    nkeys = (nb - 1) * R // R + 1
+    eng = PassEngine(R, N_BINS, 0, MAX_DIST, nkeys, dev)
+    eng.set_fragments([nb] * world, [(nb - 1) * R] * world)
+    tab = np.where((bias_host < 0.5) | (bias_host > 2), -1.0, bias_host)      # read_bias_file, fithic.py:147-149
+    values = [np.zeros(0)] * world
+    values[rank] = tab
+    eng.set_bias(BiasTables(values, [R // 2] * world, dev))
+    p = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
+    q = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
+    group = None
+
+    def step():
+        eng.hist([shard])
+        eng.allreduce_stats(group)
+        eng.fit()
+        eng.p_hist.zero_()
+        eng.pvalues(shard, p, with_hist=True)
+        eng.qvalues(p, q, n_tests=-1, use_hist=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    fit = eng.read_fit()
+    eng.launches = 0
+    step()
+    launches_per_step = eng.launches + 1            # + the p_hist memset
+    barrier()
+
+    # ---- timed region: exactly K steps, device events, max over ranks
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    value = world * P / (ms_per_step * 1e-3)
+
+    # ---- per-stage device times (separate instrumented steps; same stream, CUDA events)
+    names = ["hist", "allreduce", "fit", "pvalues", "bh"]
+    acc = dict((n, 0.0) for n in names)
+    reps = min(args.steps, 5)
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record(); eng.hist([shard])
+        ev[1].record(); eng.allreduce_stats(group)
+        ev[2].record(); eng.fit()
+        ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True)
+        ev[4].record(); eng.qvalues(p, q, n_tests=-1, use_hist=True)
+        ev[5].record()
+        torch.cuda.synchronize()
+        for i, n in enumerate(names):
+            acc[n] += ev[i].elapsed_time(ev[i + 1]) / reps
+    peak, peak_src = _peaks()
+    k4_gbs = K4_BYTES_PER_PAIR * P / (acc["pvalues"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "pvalues_kernel (K4)", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
+                "frac": k4_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * P,
+                "whole_pass_frac": BYTES_PER_PAIR * P / (ms_per_step * 1e-3) / 1e9 / peak,
+                "stage_gbs": {"hist": 12 * P / (acc["hist"] * 1e-3) / 1e9, "pvalues": k4_gbs,
+                              "bh": 16 * P / (acc["bh"] * 1e-3) / 1e9}}
+
+    # ---- end to end: host (pinned) buffers in, p and q back to the host, every step
+    h_in = [torch.empty(P, dtype=torch.int32).pin_memory() for _ in range(3)]
+    for h, d in zip(h_in, (mid1, mid2, count)):
+        h.copy_(d)
+    h_p = torch.empty(P, dtype=torch.float64).pin_memory()
+    h_q = torch.empty(P, dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        mid1.copy_(h_in[0], non_blocking=True)
+        mid2.copy_(h_in[1], non_blocking=True)
+        count.copy_(h_in[2], non_blocking=True)
+        step()
+        h_p.copy_(p, non_blocking=True)
+        h_q.copy_(q, non_blocking=True)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    tms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_value = world * P / (float(tms.item()) / e2e_steps * 1e-3)
+    kept = int((h_p <= 1).sum().item())
+    sig = int((h_q <= 0.01).sum().item())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, pairs, wall_c, _ = cpu_baseline(1, nb=4500)
+        cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": "one %d-bin block of the same workload (%.1fM records): histogram, binning, spline, bdtrc scoring, BH; "
+                         "oracle/fithic_oracle.py on 1 of %d host cores, %.1f s" % (4500, pairs / 1e6, os.cpu_count() or 1, wall_c)}
+
+    if rank == 0:
+        t = eng.totals.cpu().numpy()
+        line = {
+            "metric": "fithic_contact_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: chr1@5kb, all pairs within 10 Mb, one chromosome-sized shard per GPU",
+                       "pairs_per_gpu": P, "bins_per_gpu": nb, "resolution": R, "max_dist": MAX_DIST, "n_bins": N_BINS,
+                       "biases": True, "q_values": "per shard", "l2": "inputs (%.2f GB/GPU) exceed the 126 MB L2" % (12 * P / 1e9),
+                       "bytes_per_pair": BYTES_PER_PAIR, "S": int(t[0]), "spline_knots": int(fit.n_knots),
+                       "emitted_rows_rank0": kept, "q_le_0.01_rank0": sig},
+            "stages_ms": acc,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 12 * P, "d2h_bytes_per_step": 16 * P,
+                    "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bins", type=int, default=CHR1_BINS, help="bins of the per-GPU chromosome (default chr1 @ 5 kb)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
