@@ -321,6 +321,9 @@ def run_ours(args):
                        "bytes_per_pair": BYTES_PER_PAIR, "S": int(t[0]), "spline_knots": int(fit.n_knots),
                        "emitted_rows_rank0": kept, "q_le_0.01_rank0": sig},
             "stages_ms": acc,
+            "fit_phase_cycles": dict(zip(["stage+boundaries", "bin_stats", "spline_search", "grid_eval", "pava+residual", "total"],
+                                         [int(v) for v in eng.read_fit().phase_cycles])),
+            "spline_diag": [int(v) for v in eng.read_fit().spline_diag],
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 12 * P, "d2h_bytes_per_step": 16 * P,

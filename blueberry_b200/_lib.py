@@ -31,7 +31,8 @@ class FitResult(ctypes.Structure):
         ("status", ctypes.c_int32), ("n_out", ctypes.c_int32), ("k0", ctypes.c_int32), ("L", ctypes.c_int32),
         ("n_knots", ctypes.c_int32), ("ier", ctypes.c_int32), ("S", ctypes.c_int64),
         ("min_x", ctypes.c_double), ("max_x", ctypes.c_double), ("residual", ctypes.c_double),
-        ("fp", ctypes.c_double), ("smoothing", ctypes.c_double),
+        ("fp", ctypes.c_double), ("smoothing", ctypes.c_double), ("phase_cycles", ctypes.c_int64 * 6),
+        ("spline_diag", ctypes.c_int64 * 8),
     ]
 
 

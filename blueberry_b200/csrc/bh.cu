@@ -115,32 +115,48 @@ __global__ void __launch_bounds__(BH_THREADS) bh_hist_kernel(const double* p, lo
     }
 }
 
-// one CTA: totals, N, and the saturation bucket
-__global__ void bh_threshold_kernel(BhState* st, const long long* phist, int prune) {
-    __shared__ long long cum[BBK_PHIST_BINS + 1];
-    if (threadIdx.x == 0) {
-        long long run = 0;
-        for (int b = 0; b < BBK_PHIST_BINS; ++b) { cum[b] = run; run += phist[b]; }
-        cum[BBK_PHIST_BINS] = run;
-        long long ones = phist[BBK_PHIST_BINS];
+// one CTA of 1024 threads (4 buckets each): totals, N, and the saturation bucket
+__global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const long long* phist, int prune) {
+    __shared__ long long part[1024];
+    __shared__ int first_bucket;
+    const int t = threadIdx.x;
+    long long h[4], loc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = phist[4 * t + i]; loc += h[i]; }
+    part[t] = loc;
+    if (t == 0) first_bucket = BBK_PHIST_BINS;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        long long v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const long long total = part[1023];
+    const long long ones = phist[BBK_PHIST_BINS];
+    long long n_tests = st->n_tests;
+    if (n_tests < 0) n_tests = total + ones;                 // default N: the number of ranked p-values
+    if (prune) {
+        const double N = (double)n_tests;
+        long long cum = part[t] - loc;                       // elements in buckets below 4t
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int b = 4 * t + i;
+            if (b > 0 && h[i] != 0) {                        // bucket 0 also holds negatives: never a threshold
+                double v_lo = __longlong_as_double((long long)b << 51);
+                // first element of the bucket: p >= v_lo, rank <= cum + 1.  Margin 2^-40 covers both roundings.
+                if (v_lo * N >= (double)(cum + 1) * (1.0 + 9.1e-13)) atomicMin(&first_bucket, b);
+            }
+            cum += h[i];
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
         st->n_ones = (unsigned long long)ones;
         st->n_nan = (unsigned long long)phist[BBK_PHIST_BINS + 1];
-        st->n_valid = (unsigned long long)(run + ones);
-        if (st->n_tests < 0) st->n_tests = run + ones;      // default N: the number of ranked p-values
-        unsigned long long tau = ~0ull;
-        if (prune) {
-            double N = (double)st->n_tests;
-            for (int b = 1; b < BBK_PHIST_BINS; ++b) {       // bucket 0 also holds negatives: never a threshold
-                if (phist[b] == 0) continue;
-                double v_lo = __longlong_as_double((long long)b << 51);
-                // first element of the bucket: p >= v_lo, rank == cum[b] + 1.  Margin 2^-40 covers both roundings.
-                if (v_lo * N >= (double)(cum[b] + 1) * (1.0 + 9.1e-13)) {
-                    tau = ((unsigned long long)b << 51) | 0x8000000000000000ull;     // key_of(v_lo)
-                    break;
-                }
-            }
-        }
-        st->tau_key = tau;
+        st->n_valid = (unsigned long long)(total + ones);
+        st->n_tests = n_tests;
+        st->tau_key = first_bucket < BBK_PHIST_BINS ? (((unsigned long long)first_bucket << 51) | 0x8000000000000000ull) : ~0ull;
     }
 }
 
@@ -208,35 +224,51 @@ __global__ void __launch_bounds__(BH_THREADS) sort_hist_kernel(BhLayout L, int p
     L.block_hist[(size_t)threadIdx.x * L.G + blockIdx.x] = sh[threadIdx.x];
 }
 
-// one CTA of 1024 threads: exclusive scan of the digit-major table, skip detection
+// one CTA of 1024 threads: exclusive scan of the digit-major table [256][G], skip detection.
+// Warp w owns digits 8w..8w+7 and walks each digit's G block counts with coalesced loads.
 __global__ void __launch_bounds__(1024) sort_scan_kernel(BhLayout L, int pass) {
-    __shared__ unsigned part[1024];
-    __shared__ int uniform;
-    const int total = 256 * L.G;
-    const int per = (total + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(lo + per, total);
-    unsigned s = 0;
-    for (int i = lo; i < hi; ++i) s += L.block_hist[i];
-    part[threadIdx.x] = s;
-    if (threadIdx.x == 0) uniform = 0;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {                    // Hillis-Steele inclusive scan
-        unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    unsigned run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-    for (int i = lo; i < hi; ++i) { unsigned v = L.block_hist[i]; L.block_hist[i] = run; run += v; }
-    __syncthreads();
-    const unsigned n = (unsigned)L.st->n_cand;
-    if (threadIdx.x < 256) {
-        unsigned start = L.block_hist[(size_t)threadIdx.x * L.G];
-        unsigned end = threadIdx.x == 255 ? n : L.block_hist[(size_t)(threadIdx.x + 1) * L.G];
-        if (end - start == n && n > 0) uniform = 1;
+    __shared__ unsigned tot[256];
+    __shared__ unsigned dbase[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = L.G;
+    for (int dd = 0; dd < 8; ++dd) {
+        const int d = warp * 8 + dd;
+        unsigned* row = L.block_hist + (size_t)d * G;
+        unsigned carry = 0;
+        for (int b0 = 0; b0 < G; b0 += 32) {
+            int b = b0 + lane;
+            unsigned v = b < G ? row[b] : 0, x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (b < G) row[b] = carry + x - v;               // exclusive, relative to the digit's start
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) tot[d] = carry;
     }
     __syncthreads();
-    if (threadIdx.x == 0) L.st->skip[pass] = (uniform || n == 0) ? 1 : 0;
+    if (threadIdx.x < 32) {                                  // exclusive scan of the 256 digit totals
+        unsigned carry = 0;
+        for (int d0 = 0; d0 < 256; d0 += 32) {
+            unsigned v = tot[d0 + lane], x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            dbase[d0 + lane] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    __syncthreads();
+    for (int dd = 0; dd < 8; ++dd) {
+        const int d = warp * 8 + dd;
+        unsigned* row = L.block_hist + (size_t)d * G;
+        const unsigned add = dbase[d];
+        if (add) for (int b = lane; b < G; b += 32) row[b] += add;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned n = (unsigned)L.st->n_cand;
+        int uniform = 0;
+        for (int d = 0; d < 256; ++d) uniform |= (tot[d] == n);
+        L.st->skip[pass] = (uniform || n == 0) ? 1 : 0;
+    }
 }
 
 __global__ void __launch_bounds__(BH_THREADS) sort_scatter_kernel(BhLayout L, int pass) {
@@ -373,23 +405,50 @@ __global__ void __launch_bounds__(BH_THREADS) scan_partial_kernel(ScanParams S) 
     }
 }
 
-__global__ void scan_prefix_kernel(ScanParams S) {           // one thread: G partials
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ MaxSeg seg_shfl_up(const MaxSeg& a, int o) {
+    MaxSeg r;
+    r.v = __shfl_up_sync(0xffffffffu, a.v, o);
+    r.h = __shfl_up_sync(0xffffffffu, a.h, o);
+    r.reset = __shfl_up_sync(0xffffffffu, a.reset, o);
+    return r;
+}
+
+__global__ void scan_prefix_kernel(ScanParams S) {           // one warp: exclusive prefix over the G block partials
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     BhState* st = S.L.st;
-    MaxSeg run = {-INFINITY, -1, 0};
-    for (int b = 0; b < S.L.G; ++b) {
+    const int lane = threadIdx.x, G = S.L.G;
+    const int per = (G + 31) / 32, lo = lane * per, hi = min(lo + per, G);
+    const MaxSeg ident = {-INFINITY, -1, 0};
+    MaxSeg loc = ident;
+    for (int b = lo; b < hi; ++b) {
+        MaxSeg e = {S.L.part_max[b], S.L.part_head[b] >> 1, (int)(S.L.part_head[b] & 1)};
+        loc = seg_combine(loc, e);
+    }
+    MaxSeg inc = loc;                                        // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        MaxSeg up = seg_shfl_up(inc, o);
+        if (lane >= o) inc = seg_combine(up, inc);
+    }
+    MaxSeg run = seg_shfl_up(inc, 1);
+    if (lane == 0) run = ident;
+    for (int b = lo; b < hi; ++b) {
         MaxSeg e = {S.L.part_max[b], S.L.part_head[b] >> 1, (int)(S.L.part_head[b] & 1)};
         S.L.part_max[b] = run.v;                             // exclusive prefix
         S.L.part_head[b] = run.h;
         run = seg_combine(run, e);
     }
-    if (!S.positional) {
-        st->total_max = run.v;
+    MaxSeg all;
+    all.v = __shfl_sync(0xffffffffu, inc.v, 31);
+    all.h = __shfl_sync(0xffffffffu, inc.h, 31);
+    all.reset = __shfl_sync(0xffffffffu, inc.reset, 31);
+    if (lane == 0 && !S.positional) {
+        st->total_max = all.v;
         // the p == 1.0 group: one tie group after every candidate (when nothing saturated before it)
         double N = (double)st->n_tests;
         double bh = (1.0 * N) / (double)(st->n_cand + 1);
         bh = (1.0 < bh) ? 1.0 : bh;
-        double qo = (run.v > bh) ? run.v : bh;
+        double qo = (all.v > bh) ? all.v : bh;
         if (st->tau_key != ~0ull) qo = 1.0;                  // saturated before the ones
         st->q_ones = qo;
         st->need_ones_fix = (qo != 1.0 && st->n_ones > 0) ? 1 : 0;
@@ -492,7 +551,7 @@ extern "C" int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int
             BBK_CHECK_LAUNCH("bh_hist_kernel");
         }
         const int want_rank = d_rank != nullptr;
-        bh_threshold_kernel<<<1, 32, 0, st>>>(L.st, L.phist, want_rank ? 0 : 1);
+        bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, want_rank ? 0 : 1);
         BBK_CHECK_LAUNCH("bh_threshold_kernel");
         bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, L.keys[0], L.idx[0], want_rank, (long long*)d_rank);
         BBK_CHECK_LAUNCH("bh_compact_kernel");

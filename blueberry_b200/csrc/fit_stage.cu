@@ -45,6 +45,7 @@ struct FitShared {
     int status, n_out, k0, L, nk_eff;
     long long S;
     double s, min_x, max_x;
+    long long t[7];
 };
 
 __device__ __forceinline__ double* pick(double* pool, size_t pool_doubles, size_t need, double* global_fallback) {
@@ -58,6 +59,8 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
     const bool injected = P.x_in != nullptr;
 
     if (tid == 0) {
+        for (int i = 0; i < 7; ++i) sh.t[i] = 0;
+        sh.t[0] = clock64();
         sh.status = BBK_FIT_OK;
         sh.n_out = 0; sh.k0 = 0; sh.L = 0;
         sh.S = injected ? 0 : P.totals[0];
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         if (P.max_dist > -1) { long long lim = P.max_dist / P.R + 1; if (lim < eff) eff = lim; }
         sh.nk_eff = (int)eff;
         sh.st.n = 0; sh.st.fp = 0.0; sh.st.ier = 0;
+        for (int i = 0; i < 8; ++i) sh.st.diag[i] = 0;
     }
     for (int k = tid; k < P.nkeys; k += FIT_THREADS) if (P.bin_of_key) P.bin_of_key[k] = -1;
     __syncthreads();
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         }
         __syncthreads();
         m = sh.n_out;
+        if (tid == 0) sh.t[1] = clock64();
         if (sh.status == BBK_FIT_OK) {
             for (int j = tid; j < m; j += FIT_THREADS) {
                 double xv = 0.0, yv = 0.0;
@@ -118,6 +123,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
     }
 
     // ---------------- smoothing spline UnivariateSpline(x, y, s=min(y)**2)   (fithic.py:340-343)
+    if (tid == 0) sh.t[2] = clock64();
     if (sh.status == BBK_FIT_OK && m < 4 && tid == 0) sh.status = BBK_FIT_TOO_FEW_BINS;
     __syncthreads();
     if (sh.status == BBK_FIT_OK) {
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
     }
 
     // ---------------- splineX = keys within [min(x), max(x)], splineY = ius(splineX)   (fithic.py:350-359)
+    if (tid == 0) sh.t[3] = clock64();
     if (sh.status == BBK_FIT_OK) {
         if (tid == 0) {
             // first key k with k*R >= min_x and last key with k*R <= max_x (keys are ints, x are doubles)
@@ -196,6 +203,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         __syncthreads();
         // ---------------- antitonic regression (fithic.py:361-362) and the residual (fithic.py:374)
         if (tid == 0) {
+            sh.t[4] = clock64();
             bbk_antitonic_pava(P.spline_raw, L, P.spline_y, wmean, wcount, wstart);
             double res = 0.0;
             int cur = 4;
@@ -221,6 +229,10 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         r->max_x = sh.max_x;
         r->fp = sh.st.fp;
         r->smoothing = sh.s;
+        sh.t[5] = clock64();
+        for (int i = 0; i < 5; ++i) r->phase_cycles[i] = (sh.t[i + 1] && sh.t[i]) ? sh.t[i + 1] - sh.t[i] : 0;
+        r->phase_cycles[5] = sh.t[5] - sh.t[0];
+        for (int i = 0; i < 8; ++i) r->spline_diag[i] = sh.st.diag[i];
         if (sh.status != BBK_FIT_OK) r->residual = 0.0;
     }
 }

@@ -5,21 +5,55 @@
 //   load (128-bit, streaming) -> distance -> spline index (closed form of the reference's bisect)
 //   -> bias gathers (L2-resident tables) -> prior -> log-space binomial tail -> store (128-bit).
 //
+// The FP64 special-function work is what threatens the HBM roofline here, and it is very uneven:
+// most records have count 0 (p = 1, no arithmetic), some have count 1 (closed form), the rest need a
+// tail sum whose length grows towards the diagonal (hundreds of terms at d ~ 0).  Evaluated in place,
+// every warp would pay for the union of all branches.  So every WARP works on tiles of 256 records
+// in phases, with no CTA barrier:
+//   1. classify: each lane resolves the priors of its records; trivial results go straight to the
+//      tile's result slots in shared memory, records that need arithmetic are appended to two dense
+//      warp-private work lists (count == 1 from the front, count >= 2 from the back; ballot + popc);
+//   2. solve: the warp runs down each list with all lanes on the same branch.  A tail sum is a small
+//      resumable state: a lane advances it 16 terms at a time while at least 8 lanes of the round
+//      are still going (neighbouring records have similar lengths, so rounds are homogeneous);
+//      the stragglers are then finished by groups of 8 lanes that take 8 consecutive terms each
+//      per step and combine them with a prefix product;
+//   3. each lane reads its 8 results back and issues coalesced 128-bit streaming stores.
+// The hot loop is kept small (tables and rare branches live in separate functions/kernels): with
+// autonomous warps the instruction cache is the first thing to overflow.
+//
 // The tail P(X >= c), X ~ Binomial(S, q), is the regularised incomplete beta I_q(c, S-c+1) that
-// cephes' bdtrc evaluates.  Here it is computed as  pmf(c) * (1 + r_c + r_c r_{c+1} + ...)  from the
-// mode outwards (upper tail when c >= (S+1)q, else 1 - lower tail), with pmf(c) in log space by the
-// saddle-point form (Stirling error + deviance terms; C. Loader, "Fast and accurate computation of
-// binomial probabilities", 2000) so nothing cancels even at S ~ 2^31.  Against 60-digit arithmetic
-// this is good to ~3e-13 in log10 p; cephes itself is only good to ~3e-6 there, which is
-// what bounds the parity tolerance.
+// cephes' bdtrc evaluates.  Here: pmf(c) * (1 + r_c + r_c r_{c+1} + ...) from the mode outwards (upper
+// tail when c >= (S+1)q, else 1 - lower tail).  ln pmf(c) = c ln(Sq) - ln c! + sum_{i<c} ln(1-i/S)
+// + (S-c) ln(1-q), with the two small logarithms expanded in series (exact to < 1e-12 for the c/S the
+// fast path admits) and ln c!, 1/j from shared-memory tables; outside that range the saddle-point
+// form (Stirling error + deviance terms; C. Loader, "Fast and accurate computation of binomial
+// probabilities", 2000) takes over.  Against 60-digit arithmetic this is good to ~1e-12 in log10 p;
+// cephes itself is only good to ~3e-6 at S ~ 1e9, which is what bounds the parity tolerance.
 // bdtrc's edge semantics are kept exactly: NaN for a prior outside [0,1] or NaN (checked BEFORE the
 // count, so a count of 0 with a negative prior is dropped too), 1.0 for count <= 0, NaN for
 // count-1 > S, 0.0 for count-1 == S, the count == 1 closed form, 0 / 1 at q == 0 / 1.
+#include <mutex>
 #include "common.cuh"
 
 namespace {
 
 constexpr int PV_THREADS = 256;
+constexpr int PV_WARPS = PV_THREADS / 32;
+constexpr int RCP_TAB = 1024;        // 1/j for j < RCP_TAB
+constexpr int LF_TAB = 256;          // ln j! for j < LF_TAB
+constexpr double TAIL_EPS = 1e-12;
+constexpr double LN_2PI = 1.8378770664093454836;
+
+// mathematical constants, filled once per device (pv_tables_kernel): 1/j and ln j!
+__device__ double g_rcp[RCP_TAB];
+__device__ double g_lfact[LF_TAB];
+
+__global__ void pv_tables_kernel() {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < RCP_TAB) g_rcp[j] = j ? 1.0 / (double)j : 0.0;
+    if (j < LF_TAB) g_lfact[j] = lgamma((double)j + 1.0);
+}
 
 __device__ __constant__ double c_stirl[16] = {
     0.0, 0.08106146679532726, 0.04134069595540929, 0.02767792568499834, 0.02079067210376509,
@@ -27,7 +61,7 @@ __device__ __constant__ double c_stirl[16] = {
     0.009255462182712733, 0.008330563433362871, 0.007573675487951841, 0.006942840107209530,
     0.006408994188004207, 0.005951370112758848, 0.005554733551962801};
 
-// log(n!) - [n log n - n + 0.5 log(2 pi n)]
+// ln(n!) - [n ln n - n + 0.5 ln(2 pi n)]
 __device__ __forceinline__ double stirlerr(double n) {
     if (n <= 15.0) return c_stirl[(int)n];
     const double S0 = 1.0 / 12.0, S1 = 1.0 / 360.0, S2 = 1.0 / 1260.0, S3 = 1.0 / 1680.0, S4 = 1.0 / 1188.0;
@@ -38,7 +72,7 @@ __device__ __forceinline__ double stirlerr(double n) {
     return (S0 - (S1 - (S2 - (S3 - S4 * rnn) * rnn) * rnn) * rnn) * rn;
 }
 
-// x log(x/M) + M - x, without cancellation when x ~ M
+// x ln(x/M) + M - x, without cancellation when x ~ M
 __device__ __forceinline__ double bd0(double x, double M) {
     double diff = x - M;
     if (fabs(diff) < 0.1 * (x + M)) {
@@ -57,25 +91,18 @@ __device__ __forceinline__ double bd0(double x, double M) {
     return x * log(x / M) + M - x;
 }
 
-struct TailConst {      // per-launch constants of the binomial tail (functions of S only)
-    double dn;          // (double) S
-    double inv_n;       // 1 / S
-    double stirl_n;     // stirlerr(S)
-};
-
-// P(X >= c) for 2 <= c <= S - 1 ... and c == S handled by the caller; 0 < q < 1
-__device__ double binom_upper_tail(int c, long long S, double q, const TailConst& K) {
-    const double dn = K.dn;
-    const double dc = (double)c;
-    const double mu = dn * q;
-    const double nmc = dn - dc;
-    double lc = K.stirl_n - stirlerr(dc) - stirlerr(nmc) - bd0(dc, mu) - bd0(nmc, dn * (1.0 - q));
-    double lf = 1.8378770664093454836 /* log(2 pi) */ + log(dc) + log1p(-dc * K.inv_n);
-    double lp = lc - 0.5 * lf;                       // log pmf(c)
+// General path (any S, any 2 <= c <= S, 0 < q < 1): saddle-point pmf + serial tail sum.  Rare: counts
+// beyond the fast path's range, or small S.  Kept out of line so it costs the hot loop one call.
+__device__ __noinline__ double tail_general(int c, long long S, double q) {
+    const double dn = (double)S, dc = (double)c;
+    if ((long long)c == S) return exp(dn * log(q));              // I_q(S, 1) = q^S
+    const double mu = dn * q, nmc = dn - dc;
+    double lc = stirlerr(dn) - stirlerr(dc) - stirlerr(nmc) - bd0(dc, mu) - bd0(nmc, dn * (1.0 - q));
+    double lf = LN_2PI + log(dc) + log1p(-dc / dn);
+    double lp = lc - 0.5 * lf;                                   // ln pmf(c)
     const double qr = q / (1.0 - q);
-    const double eps = 5.7e-14;                      // 2^-44: far inside the 1e-9 budget
+    const double eps = 5.7e-14;
     if (dc >= (dn + 1.0) * q) {
-        // upper tail: pmf(j+1)/pmf(j) = (n-j)/(j+1) * q/(1-q), decreasing from j = c
         double term = 1.0, sum = 1.0, dj = dc, rem = nmc;
         while (rem > 0.0) {
             term *= rem * qr / (dj + 1.0);
@@ -84,10 +111,9 @@ __device__ double binom_upper_tail(int c, long long S, double q, const TailConst
             rem -= 1.0;
             if (term < eps * sum) break;
         }
-        if (lp < -690.0) return exp(lp + log(sum));  // keep the denormal range reachable
+        if (lp < -690.0) return exp(lp + log(sum));              // keep the denormal range reachable
         return exp(lp) * sum;
     }
-    // lower tail: pmf(j-1)/pmf(j) = j / ((n-j+1) * q/(1-q)), decreasing from j = c-1 downwards
     const double iqr = (1.0 - q) / q;
     double term = dc * iqr / (nmc + 1.0), sum = term, dj = dc - 1.0;
     while (dj > 0.0) {
@@ -99,22 +125,157 @@ __device__ double binom_upper_tail(int c, long long S, double q, const TailConst
     return 1.0 - exp(lp) * sum;
 }
 
-// scipy.special.bdtrc(c - 1, S, q) semantics
-__device__ __forceinline__ double bdtrc_like(int c, long long S, double q, const TailConst& K) {
-    if (isnan(q)) return q;
-    if (q < 0.0 || q > 1.0) return __longlong_as_double(0x7ff8000000000000ll);
-    long long k = (long long)c - 1;
-    if (k < 0) return 1.0;
-    if (S < k) return __longlong_as_double(0x7ff8000000000000ll);
-    if (k == S) return 0.0;
-    if (k == 0) {
-        if (q < 0.01) return -expm1(K.dn * log1p(-q));
-        return 1.0 - pow(1.0 - q, K.dn);
+// rare branches of the fast path, out of line
+__device__ __noinline__ double log1m_big(double q) { return log1p(-q); }
+__device__ __noinline__ double lnfact_big(double dc) { return dc * log(dc) - dc + 0.5 * (LN_2PI + log(dc)) + stirlerr(dc); }
+__device__ __noinline__ double exp_deep(double lp, double sum) { return exp(lp + log(sum)); }
+
+// ln(1 - q)
+__device__ __forceinline__ double log1m(double q) {
+    if (q < 9.765625e-4)
+        return -q * (1.0 + q * (0.5 + q * (1.0 / 3.0 + q * (0.25 + q * (0.2 + q * (1.0 / 6.0))))));
+    return log1m_big(q);
+}
+
+struct TailConst {      // per-launch constants (functions of S only)
+    double dn;          // (double) S
+    double inv_n;       // 1 / S
+    double c_max;       // the series form of ln pmf needs c < c_max (= 1e-4 S: 1/(S-j) expands) ...
+    double c5_max;      // ... and c^5 < c5_max (= 2e-11 S^4: sum ln(1-i/S) truncated after the cubic term)
+};
+
+// The tail sum as a resumable state.
+struct TailState {
+    double lp;      // ln pmf(c)
+    double term;    // last term added, relative to pmf(c)
+    double sum;     // sum of the terms so far, relative to pmf(c)
+    double a;       // upper: (S - j + 1) q/(1-q) for the next index j;  lower: j (1-q)/q / S for the next index j
+    double step;    // upper: q/(1-q);  lower: (1-q)/q / S          (a moves by -step per term)
+    double e;       // lower only: (j - 1) / S for the next index j  (moves by -1/S per term)
+    int j;          // next index: upper j = c+1, c+2, ...; lower j = c, c-1, ... (ratio pmf(j-1)/pmf(j))
+    int upper;      // 1 upper tail, 0 lower tail
+};
+
+__device__ __forceinline__ bool fast_ok(int c, const TailConst& K) {
+    double dc = (double)c, c2 = dc * dc;
+    return dc < K.c_max && c2 * c2 * dc < K.c5_max;
+}
+
+__device__ __forceinline__ void tail_setup(int c, double q, const TailConst& K, const double* __restrict__ lfact, TailState& T) {
+    const double dc = (double)c, dn = K.dn, inv_n = K.inv_n;
+    const double mu = dn * q;
+    const double s1 = 0.5 * dc * (dc - 1.0) * inv_n;
+    const double A = -s1 * (1.0 + inv_n * ((2.0 * dc - 1.0) * (1.0 / 6.0) + s1 * (1.0 / 3.0)));   // sum_{i<c} ln(1 - i/S)
+    const double lnfact = c < LF_TAB ? lfact[c] : lnfact_big(dc);
+    T.lp = dc * log(mu) - lnfact + A + (dn - dc) * log1m(q);
+    T.upper = dc >= (dn + 1.0) * q;
+    const double qr = q / (1.0 - q);
+    T.term = 1.0;
+    if (T.upper) {
+        T.step = qr;
+        T.a = (dn - dc) * qr;
+        T.j = c + 1;
+        T.sum = 1.0;
+        T.e = 0.0;
+    } else {
+        // pmf(j-1)/pmf(j) = j (1-q)/q / (S-j+1);  1/(S-j+1) = (1/S)(1 + e + e^2 + e^3 ...), e = (j-1)/S < 1e-4
+        T.step = inv_n / qr;
+        T.a = dc * T.step;
+        T.e = (dc - 1.0) * inv_n;
+        T.j = c;
+        T.sum = 0.0;
     }
-    if (q == 0.0) return 0.0;
-    if (q == 1.0) return 1.0;
-    if ((long long)c == S) return exp(K.dn * log(q));          // I_q(S, 1) = q^S
-    return binom_upper_tail(c, S, q, K);
+}
+
+// one term of the state's own series
+__device__ __forceinline__ void tail_term(TailState& T, const TailConst& K, const double* __restrict__ rcp) {
+    double f;
+    if (T.upper) {
+        double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
+        f = T.a > 0.0 ? T.a * r : 0.0;
+        T.j += 1;
+    } else {
+        f = T.j > 0 ? T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e))) : 0.0;
+        T.e -= K.inv_n;
+        T.j -= 1;
+    }
+    T.term *= f;
+    T.sum += T.term;
+    T.a -= T.step;
+}
+
+// 8-lane group: every lane of the group holds the SAME state; each takes 8 consecutive terms per step and
+// the group combines them with a prefix product.  All 32 lanes run the same number of steps (shuffles
+// inside); groups that are done or idle pass through.  Returns the finished sum.
+__device__ __noinline__ double tail_group_finish(TailState T, double inv_n, const double* __restrict__ rcp, int sl, bool valid) {
+    constexpr int U = 8;
+    bool done = !valid;
+    while (!__all_sync(0xffffffffu, done)) {
+        double p = 1.0, s = 0.0;
+        if (!done) {
+            double a = T.a - (double)(sl * U) * T.step;
+            if (T.upper) {
+                int j = T.j + sl * U;
+#pragma unroll 2
+                for (int u = 0; u < U; ++u) {
+                    double r = j < RCP_TAB ? rcp[j] : 1.0 / (double)j;
+                    double f = a > 0.0 ? a * r : 0.0;
+                    p *= f; s += p; a -= T.step; j += 1;
+                }
+            } else {
+                double e = T.e - (double)(sl * U) * inv_n;
+                int j = T.j - sl * U;
+#pragma unroll 2
+                for (int u = 0; u < U; ++u) {
+                    double f = j > 0 ? a * (1.0 + e * (1.0 + e * (1.0 + e))) : 0.0;
+                    p *= f; s += p; a -= T.step; e -= inv_n; j -= 1;
+                }
+            }
+        }
+        double incl = p;                                         // inclusive prefix product over the group
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            double up = __shfl_up_sync(0xffffffffu, incl, o, 8);
+            if (sl >= o) incl *= up;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1, 8);
+        if (sl == 0) excl = 1.0;
+        double contrib = excl * s;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o, 8);
+        double prod = __shfl_sync(0xffffffffu, incl, 7, 8);
+        if (!done) {
+            T.sum += T.term * contrib;
+            T.term *= prod;
+            T.a -= (double)(8 * U) * T.step;
+            if (T.upper) T.j += 8 * U;
+            else { T.j -= 8 * U; T.e -= (double)(8 * U) * inv_n; }
+            done = (T.term < TAIL_EPS * T.sum) || (T.upper ? T.a <= 0.0 : T.j <= 0);
+        }
+    }
+    return T.sum;
+}
+
+__device__ __forceinline__ double tail_finish(double lp, double sum, int upper) {
+    if (upper && lp < -690.0) return exp_deep(lp, sum);          // keep the denormal range reachable
+    double v = exp(lp) * sum;
+    return upper ? v : 1.0 - v;
+}
+
+// Everything bdtrc decides without arithmetic.  Returns 0 when *out is final, 1 for count == 1
+// (closed form), 2 for a tail sum (then 0 < q < 1 and 2 <= c <= S).
+__device__ __forceinline__ int bdtrc_class(int c, long long S, double q, double* out) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    *out = qnan;
+    if (!(q >= 0.0 && q <= 1.0)) return 0;                       // NaN or outside [0, 1]
+    long long k = (long long)c - 1;
+    if (k < 0) { *out = 1.0; return 0; }
+    if (S < k) return 0;
+    if (k == S) { *out = 0.0; return 0; }
+    if (k == 0) return 1;
+    if (q == 0.0) { *out = 0.0; return 0; }
+    if (q == 1.0) { *out = 1.0; return 0; }
+    return 2;
 }
 
 struct PvParams {
@@ -137,24 +298,33 @@ struct PvParams {
     long long* p_hist;
 };
 
-__device__ __forceinline__ double bias_lookup(const PvParams& P, int chrom, int mid) {
+struct BiasRow { long long base, nloc, mid0; };
+
+__device__ __forceinline__ BiasRow bias_row(const PvParams& P, int chrom) {
+    BiasRow r = {0, 0, 0};
+    if (chrom < 0 || chrom >= P.n_chrom) return r;
+    r.base = __ldg(&P.chrom_base[chrom]);
+    r.nloc = __ldg(&P.chrom_base[chrom + 1]) - r.base;
+    r.mid0 = __ldg(&P.mid0[chrom]);
+    return r;
+}
+
+__device__ __forceinline__ double bias_lookup(const PvParams& P, const BiasRow& row, int mid) {
     // biasDic[chr][mid] with default 1.0 (fithic.py:418-425) on a dense per-chromosome grid
-    if (chrom < 0 || chrom >= P.n_chrom) return 1.0;
-    long long base = __ldg(&P.chrom_base[chrom]);
-    long long nloc = __ldg(&P.chrom_base[chrom + 1]) - base;
-    long long off = (long long)mid - __ldg(&P.mid0[chrom]);
+    long long off = (long long)mid - row.mid0;
     if (off < 0 || off >= (1ll << 32)) return 1.0;
     unsigned idx = fastdiv((unsigned)off, P.div);
-    if ((long long)idx * P.div.R != off || (long long)idx >= nloc) return 1.0;
-    double v = __ldg(&P.bias[base + idx]);
+    if ((long long)idx * P.div.R != off || (long long)idx >= row.nloc) return 1.0;
+    double v = __ldg(&P.bias[row.base + idx]);
     return isnan(v) ? 1.0 : v;
 }
 
+// prior of one record; returns false when the reference does not score it (fithic.py:427)
 template <bool HAS_CHR, bool HAS_BIAS>
-__device__ __forceinline__ double score_record(const PvParams& P, int m1, int m2, int c, int c1, int c2,
-                                               long long S, int k0, int L, const TailConst& K) {
+__device__ __forceinline__ bool record_prior(const PvParams& P, int m1, int m2, int c1, int c2, int k0, int L,
+                                             const BiasRow& shard_row, double* prior_out) {
     long long d = (long long)m2 - (long long)m1;                         // fithic.py:416
-    if (!(P.min_dist <= d && d <= P.max_dist)) return __longlong_as_double(0x7ff8000000000000ll);   // :427 not scored
+    if (!(P.min_dist <= d && d <= P.max_dist)) return false;
     // i = min(bisect_left(splineX, clamp(d, min_x, max_x)), L-1) == clamp(ceil((d - splineX[0]) / R), 0, L-1)
     long long t = d - (long long)k0 * P.R;
     int i = 0;
@@ -165,91 +335,267 @@ __device__ __forceinline__ double score_record(const PvParams& P, int m1, int m2
     }
     double prior = __ldg(&P.spline_y[i]);
     if (HAS_BIAS) {
-        double b1 = bias_lookup(P, HAS_CHR ? c1 : P.shard_chrom, m1);
-        double b2 = bias_lookup(P, HAS_CHR ? c2 : P.shard_chrom, m2);
+        double b1, b2;
+        if (HAS_CHR) {
+            b1 = bias_lookup(P, bias_row(P, c1), m1);
+            b2 = bias_lookup(P, bias_row(P, c2), m2);
+        } else {
+            b1 = bias_lookup(P, shard_row, m1);
+            b2 = bias_lookup(P, shard_row, m2);
+        }
         prior = prior * (b1 * b2);                                        // :431
     }
-    double pv = bdtrc_like(c, S, prior, K);                              // :432
-    if (!(pv <= 1.0)) pv = __longlong_as_double(0x7ff8000000000000ll);   // :434 row dropped
-    return pv;
+    *prior_out = prior;
+    return true;
+}
+
+__device__ __forceinline__ double finish_p(double pv) {                  // fithic.py:434: rows with !(p <= 1) are dropped
+    return (pv <= 1.0) ? pv : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 __device__ __forceinline__ void hist_p(unsigned* sh_hist, double pv, unsigned& ones, unsigned& nans) {
     if (isnan(pv)) { nans += 1; return; }
     if (pv == 1.0) { ones += 1; return; }
-    unsigned b = (unsigned)((unsigned long long)__double_as_longlong(pv) >> 51) & (BBK_PHIST_BINS - 1);
-    atomicAdd(&sh_hist[b], 1u);
+    atomicAdd(&sh_hist[(unsigned)((unsigned long long)__double_as_longlong(pv) >> 51) & (BBK_PHIST_BINS - 1)], 1u);
 }
+
+constexpr int WT_ITERS = 2;                         // int4 groups per lane per warp tile
+constexpr int WT_PAIRS = 32 * 4 * WT_ITERS;         // 256 records per warp tile
+
+struct WarpTile {                                   // warp-private
+    double res[WT_PAIRS];                           // result slot of every record of the tile (slot = it*128 + lane*4 + e)
+    double q[WT_PAIRS];                             // work lists: prior (count == 1 from the front, tails from the back)
+    int c[WT_PAIRS];
+    unsigned char slot[WT_PAIRS];
+};
+
+struct PvShared {
+    double rcp[RCP_TAB];
+    double lfact[LF_TAB];
+    WarpTile w[PV_WARPS];
+};
 
 template <bool HAS_CHR, bool HAS_BIAS, bool HIST>
 __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
-    __shared__ unsigned sh_hist[HIST ? BBK_PHIST_BINS : 1];
-    if (HIST) {
-        for (int i = threadIdx.x; i < BBK_PHIST_BINS; i += blockDim.x) sh_hist[i] = 0;
-        __syncthreads();
-    }
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PvShared& sh = *reinterpret_cast<PvShared*>(smem_raw);
+    unsigned* sh_hist = reinterpret_cast<unsigned*>(smem_raw + sizeof(PvShared));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long S = P.fit->S;
     const int k0 = P.fit->k0, L = P.fit->L;
     const bool fit_ok = P.fit->status == BBK_FIT_OK && L > 0;
+
+    for (int j = tid; j < RCP_TAB; j += PV_THREADS) sh.rcp[j] = g_rcp[j];
+    for (int j = tid; j < LF_TAB; j += PV_THREADS) sh.lfact[j] = g_lfact[j];
+    if (HIST) for (int i = tid; i < BBK_PHIST_BINS; i += PV_THREADS) sh_hist[i] = 0;
+    __syncthreads();
     TailConst K;
     K.dn = (double)S;
     K.inv_n = S > 0 ? 1.0 / K.dn : 0.0;
-    K.stirl_n = S > 0 ? stirlerr(K.dn) : 0.0;
+    K.c_max = 1e-4 * K.dn;
+    K.c5_max = 2e-11 * (K.dn * K.dn) * (K.dn * K.dn);
+    WarpTile& W = sh.w[warp];
+    BiasRow shard_row = {0, 0, 0};
+    if (HAS_BIAS && !HAS_CHR) shard_row = bias_row(P, P.shard_chrom);
     unsigned ones = 0, nans = 0;
 
     const long long n_groups = P.n_pairs >> 2;
+    const long long groups_per_tile = 32 * WT_ITERS;
+    const long long n_wtiles = (n_groups + groups_per_tile - 1) / groups_per_tile;
     const int4* m1v = reinterpret_cast<const int4*>(P.mid1);
     const int4* m2v = reinterpret_cast<const int4*>(P.mid2);
     const int4* cv = reinterpret_cast<const int4*>(P.count);
     const int4* c1v = reinterpret_cast<const int4*>(P.chr1);
     const int4* c2v = reinterpret_cast<const int4*>(P.chr2);
     double2* pv2 = reinterpret_cast<double2*>(P.p);
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (long long)gridDim.x * blockDim.x) {
-        int4 a1 = ld_stream_int4(m1v + g), a2 = ld_stream_int4(m2v + g), ac = ld_stream_int4(cv + g);
-        int4 x1 = make_int4(0, 0, 0, 0), x2 = x1;
-        if (HAS_CHR) { x1 = ld_stream_int4(c1v + g); x2 = ld_stream_int4(c2v + g); }
-        double r0 = qnan, r1 = qnan, r2 = qnan, r3 = qnan;
-        if (fit_ok) {
-            r0 = score_record<HAS_CHR, HAS_BIAS>(P, a1.x, a2.x, ac.x, x1.x, x2.x, S, k0, L, K);
-            r1 = score_record<HAS_CHR, HAS_BIAS>(P, a1.y, a2.y, ac.y, x1.y, x2.y, S, k0, L, K);
-            r2 = score_record<HAS_CHR, HAS_BIAS>(P, a1.z, a2.z, ac.z, x1.z, x2.z, S, k0, L, K);
-            r3 = score_record<HAS_CHR, HAS_BIAS>(P, a1.w, a2.w, ac.w, x1.w, x2.w, S, k0, L, K);
+    const unsigned lt = (1u << lane) - 1;
+
+    // warps are autonomous: no CTA barrier inside the loop
+    for (long long wt = (long long)blockIdx.x * PV_WARPS + warp; wt < n_wtiles; wt += (long long)gridDim.x * PV_WARPS) {
+        int n1 = 0, n2 = 0;                          // warp-uniform list lengths
+        // ---- phase 1: classify; trivial results to their slots, the rest into the two dense lists
+#pragma unroll 1
+        for (int it = 0; it < WT_ITERS; ++it) {
+            const long long g = wt * groups_per_tile + it * 32 + lane;
+            const bool live = g < n_groups;
+            int4 z4 = make_int4(0, 0, 0, 0);
+            int4 a1 = z4, a2 = z4, ac = z4, x1 = z4, x2 = z4;
+            if (live) {
+                a1 = ld_stream_int4(m1v + g); a2 = ld_stream_int4(m2v + g); ac = ld_stream_int4(cv + g);
+                if (HAS_CHR) { x1 = ld_stream_int4(c1v + g); x2 = ld_stream_int4(c2v + g); }
+            }
+            const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
+            const int c1s[4] = {x1.x, x1.y, x1.z, x1.w}, c2s[4] = {x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int cls = 0;                               // 0 final, 1 count == 1, 2 tail sum
+                double prior = 0.0, out = __longlong_as_double(0x7ff8000000000000ll);
+                if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, &prior))
+                    cls = bdtrc_class(cs[e], S, prior, &out);
+                const int slot = it * 128 + lane * 4 + e;
+                unsigned b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
+                if (cls) {
+                    int pos = cls == 1 ? n1 + __popc(b1 & lt) : WT_PAIRS - 1 - (n2 + __popc(b2 & lt));
+                    W.q[pos] = prior;
+                    W.c[pos] = cs[e];
+                    W.slot[pos] = (unsigned char)slot;
+                } else {
+                    W.res[slot] = out;
+                }
+                n1 += __popc(b1);
+                n2 += __popc(b2);
+            }
         }
-        st_stream_double2(pv2 + 2 * g, make_double2(r0, r1));
-        st_stream_double2(pv2 + 2 * g + 1, make_double2(r2, r3));
-        if (HIST) { hist_p(sh_hist, r0, ones, nans); hist_p(sh_hist, r1, ones, nans); hist_p(sh_hist, r2, ones, nans); hist_p(sh_hist, r3, ones, nans); }
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (P.n_pairs & 3)) {
-        long long i = (n_groups << 2) + threadIdx.x;
-        int c1 = 0, c2 = 0;
-        if (HAS_CHR) { c1 = P.chr1[i]; c2 = P.chr2[i]; }
-        double r = fit_ok ? score_record<HAS_CHR, HAS_BIAS>(P, P.mid1[i], P.mid2[i], P.count[i], c1, c2, S, k0, L, K) : qnan;
-        P.p[i] = r;
-        if (HIST) hist_p(sh_hist, r, ones, nans);
+        __syncwarp();
+        // ---- phase 2a: count == 1 (bdtrc's closed form; -expm1(S ln(1-q)) also covers its q >= 0.01 branch)
+        for (int k = lane; k < n1; k += 32) W.res[W.slot[k]] = -expm1(K.dn * log1m(W.q[k]));
+        // ---- phase 2b: tail sums
+        for (int kb = 0; kb < n2; kb += 32) {
+            const int k = kb + lane;
+            const bool active = k < n2;
+            const int pos = WT_PAIRS - 1 - (active ? k : 0);
+            TailState T;
+            T.lp = 0.0; T.term = 0.0; T.sum = 1.0; T.a = 0.0; T.step = 0.0; T.e = 0.0; T.j = 0; T.upper = 1;
+            bool running = false;                    // this lane's sum is set up and not yet converged
+            bool fast = false;
+            if (active) {
+                const int c = W.c[pos];
+                const double q = W.q[pos];
+                fast = fast_ok(c, K);
+                if (fast) { tail_setup(c, q, K, sh.lfact, T); running = true; }
+                else W.res[W.slot[pos]] = tail_general(c, S, q);
+            }
+            // lanes advance their own sums while the round is still mostly busy ...
+            unsigned rmask = __ballot_sync(0xffffffffu, running);
+            while (__popc(rmask) >= 8) {
+                if (running) {
+#pragma unroll 1
+                    for (int u = 0; u < 16; ++u) tail_term(T, K, sh.rcp);
+                    running = !(T.term < TAIL_EPS * T.sum);
+                }
+                rmask = __ballot_sync(0xffffffffu, running);
+            }
+            // ... and groups of 8 lanes finish the stragglers, four at a time
+            const int sub = lane >> 3, sl = lane & 7;
+            while (rmask) {
+                const unsigned src = __fns(rmask, 0, sub + 1);
+                const bool valid = src < 32u;
+                const int from = valid ? (int)src : lane;
+                TailState G;
+                G.lp = 0.0;
+                G.term = __shfl_sync(0xffffffffu, T.term, from);
+                G.sum = __shfl_sync(0xffffffffu, T.sum, from);
+                G.a = __shfl_sync(0xffffffffu, T.a, from);
+                G.step = __shfl_sync(0xffffffffu, T.step, from);
+                G.e = __shfl_sync(0xffffffffu, T.e, from);
+                G.j = __shfl_sync(0xffffffffu, T.j, from);
+                G.upper = __shfl_sync(0xffffffffu, T.upper, from);
+                double gsum = tail_group_finish(G, K.inv_n, sh.rcp, sl, valid);
+                // every lane of group g now holds the finished sum of the g-th straggler: hand it to its owner lane
+#pragma unroll
+                for (int gsel = 0; gsel < 4; ++gsel) {
+                    unsigned owner = __fns(rmask, 0, gsel + 1);
+                    double v = __shfl_sync(0xffffffffu, gsum, gsel * 8);
+                    if (owner == (unsigned)lane) { T.sum = v; running = false; }
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) rmask &= rmask - 1;      // drop the (up to) 4 lowest set bits
+            }
+            if (active && fast) W.res[W.slot[pos]] = tail_finish(T.lp, T.sum, T.upper);
+        }
+        __syncwarp();
+        // ---- results back to their owners, coalesced 128-bit stores
+#pragma unroll 1
+        for (int it = 0; it < WT_ITERS; ++it) {
+            const long long g = wt * groups_per_tile + it * 32 + lane;
+            const double2* rs = reinterpret_cast<const double2*>(&W.res[it * 128 + lane * 4]);
+            double2 r01 = rs[0], r23 = rs[1];
+            r01.x = finish_p(r01.x); r01.y = finish_p(r01.y); r23.x = finish_p(r23.x); r23.y = finish_p(r23.y);
+            if (g < n_groups) {
+                st_stream_double2(pv2 + 2 * g, r01);
+                st_stream_double2(pv2 + 2 * g + 1, r23);
+                if (HIST) { hist_p(sh_hist, r01.x, ones, nans); hist_p(sh_hist, r01.y, ones, nans);
+                            hist_p(sh_hist, r23.x, ones, nans); hist_p(sh_hist, r23.y, ones, nans); }
+            }
+        }
+        __syncwarp();      // the tile buffers are reused by the next warp tile
     }
     if (HIST) {
         __syncthreads();
-        for (int i = threadIdx.x; i < BBK_PHIST_BINS; i += blockDim.x) {
+        for (int i = tid; i < BBK_PHIST_BINS; i += PV_THREADS) {
             unsigned v = sh_hist[i];
             if (v) atomicAdd((unsigned long long*)&P.p_hist[i], (unsigned long long)v);
         }
-        unsigned o = __reduce_add_sync(0xffffffffu, ones), z = __reduce_add_sync(0xffffffffu, nans);
-        if ((threadIdx.x & 31) == 0) {
+        unsigned o = __reduce_add_sync(0xffffffffu, ones), zn = __reduce_add_sync(0xffffffffu, nans);
+        if (lane == 0) {
             if (o) atomicAdd((unsigned long long*)&P.p_hist[BBK_PHIST_BINS], (unsigned long long)o);
-            if (z) atomicAdd((unsigned long long*)&P.p_hist[BBK_PHIST_BINS + 1], (unsigned long long)z);
+            if (zn) atomicAdd((unsigned long long*)&P.p_hist[BBK_PHIST_BINS + 1], (unsigned long long)zn);
         }
     }
+}
+
+// the last n_pairs % 4 records (at most 3): one thread each, evaluated in place
+template <bool HAS_CHR, bool HAS_BIAS>
+__global__ void pvalues_tail_kernel(PvParams P) {
+    const long long i = ((P.n_pairs >> 2) << 2) + threadIdx.x;
+    if (i >= P.n_pairs) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const long long S = P.fit->S;
+    const int k0 = P.fit->k0, L = P.fit->L;
+    const bool fit_ok = P.fit->status == BBK_FIT_OK && L > 0;
+    BiasRow shard_row = {0, 0, 0};
+    if (HAS_BIAS && !HAS_CHR) shard_row = bias_row(P, P.shard_chrom);
+    int c1 = 0, c2 = 0;
+    if (HAS_CHR) { c1 = P.chr1[i]; c2 = P.chr2[i]; }
+    double pv = qnan, prior = 0.0;
+    const int c = P.count[i];
+    if (fit_ok && record_prior<HAS_CHR, HAS_BIAS>(P, P.mid1[i], P.mid2[i], c1, c2, k0, L, shard_row, &prior)) {
+        double out;
+        int cls = bdtrc_class(c, S, prior, &out);
+        if (cls == 0) pv = out;
+        else if (cls == 1) pv = -expm1((double)S * log1m(prior));
+        else pv = tail_general(c, S, prior);
+    }
+    pv = finish_p(pv);
+    P.p[i] = pv;
+    if (P.p_hist) {
+        if (isnan(pv)) atomicAdd((unsigned long long*)&P.p_hist[BBK_PHIST_BINS + 1], 1ull);
+        else if (pv == 1.0) atomicAdd((unsigned long long*)&P.p_hist[BBK_PHIST_BINS], 1ull);
+        else atomicAdd((unsigned long long*)&P.p_hist[(unsigned)((unsigned long long)__double_as_longlong(pv) >> 51) & (BBK_PHIST_BINS - 1)], 1ull);
+    }
+}
+
+int ensure_tables(cudaStream_t st) {
+    // 1/j and ln j! are constants; fill them once per device (same values whoever wins a race)
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    BBK_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return BBK_OK;
+    pv_tables_kernel<<<(RCP_TAB + 255) / 256, 256, 0, st>>>();
+    BBK_CHECK_LAUNCH("pv_tables_kernel");
+    BBK_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return BBK_OK;
 }
 
 template <bool HAS_CHR, bool HAS_BIAS, bool HIST>
 int launch_pv(const PvParams& P, cudaStream_t st) {
     long long groups = P.n_pairs >> 2;
-    long long need = (groups + PV_THREADS - 1) / PV_THREADS;
-    long long grid = (long long)bbk_num_sms() * 3 * 4;     // 4 waves of 3 CTAs/SM: evens out the divergent tails
-    if (need < grid) grid = need > 0 ? need : 1;
-    pvalues_kernel<HAS_CHR, HAS_BIAS, HIST><<<(unsigned)grid, PV_THREADS, 0, st>>>(P);
-    BBK_CHECK_LAUNCH("pvalues_kernel");
+    if (groups > 0) {
+        long long need = (groups + PV_WARPS * 32 * WT_ITERS - 1) / (PV_WARPS * 32 * WT_ITERS);
+        long long grid = (long long)bbk_num_sms() * 3;
+        if (need < grid) grid = need;
+        size_t smem = sizeof(PvShared) + (HIST ? BBK_PHIST_BINS * sizeof(unsigned) : 0);
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(pvalues_kernel<HAS_CHR, HAS_BIAS, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pvalues_kernel<HAS_CHR, HAS_BIAS, HIST><<<(unsigned)grid, PV_THREADS, smem, st>>>(P);
+        BBK_CHECK_LAUNCH("pvalues_kernel");
+    }
+    if (P.n_pairs & 3) {
+        pvalues_tail_kernel<HAS_CHR, HAS_BIAS><<<1, 32, 0, st>>>(P);
+        BBK_CHECK_LAUNCH("pvalues_tail_kernel");
+    }
     return BBK_OK;
 }
 
@@ -279,6 +625,8 @@ extern "C" int bbk_pvalues(const int32_t* d_chr1, const int32_t* d_chr2, const i
         P.n_chrom = bias->n_chrom;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_tables(st);
+    if (rc != BBK_OK) return rc;
     bool chr = d_chr1 != nullptr, hist = d_p_hist != nullptr;
 #define BBK_PV_CASE(C, B, H) if (chr == C && has_bias == B && hist == H) return launch_pv<C, B, H>(P, st);
     BBK_PV_CASE(false, false, false) BBK_PV_CASE(false, false, true)

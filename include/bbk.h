@@ -94,6 +94,10 @@ typedef struct BbkFitResult {
     double residual;     /* sum((y - ius(x))**2), fithic.py:374 */
     double fp;           /* weighted sum of squared residuals of the smoothing spline */
     double smoothing;    /* s = min(y)**2 */
+    int64_t phase_cycles[6]; /* SM clock cycles: staging+binning, bin stats, spline search, grid evaluation,
+                                antitonic regression + residual, total */
+    int64_t spline_diag[8];  /* LSQ fits, smoothing iterations, then SM cycles: B-spline rows, row QR + back
+                                substitution, residuals + knot insertion, Givens sweep, f(p) evaluation */
 } BbkFitResult;
 
 /* bytes of scratch bbk_fit needs for up to max_bins bins and nkeys distances */
