@@ -46,6 +46,8 @@ struct FitShared {
     long long S;
     double s, min_x, max_x;
     long long t[7];
+    long long slice_tot[FIT_THREADS];
+    int n_blocks;
 };
 
 __device__ __forceinline__ double* pick(double* pool, size_t pool_doubles, size_t need, double* global_fallback) {
@@ -79,27 +81,76 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         const int nk = sh.nk_eff;
         const long long S = sh.S;
         // stage observed[0..nk) (and possible) in shared memory when they fit; bin bounds after them
-        size_t need = (size_t)2 * nk + (size_t)P.max_bins + 2;    // 2 int64 tables + 2 int32 bound arrays
+        size_t need = (size_t)3 * nk + (size_t)P.max_bins + 2;    // 3 int64 tables + 2 int32 bound arrays
         double* base = pick(pool, P.pool_doubles, need, P.gws);
         long long* obs_s = (long long*)base;
         long long* pos_s = obs_s + nk;
-        int* bstart = (int*)(pos_s + nk);
+        long long* pre_s = pos_s + nk;
+        int* bstart = (int*)(pre_s + nk);
         int* bend = bstart + P.max_bins;
         for (int k = tid; k < nk; k += FIT_THREADS) { obs_s[k] = P.observed[k]; pos_s[k] = P.possible[k]; }
         __syncthreads();
-        if (tid == 0) {
-            int nout = 0;
-            int stc = BBK_FIT_OK;
+        // inclusive prefix sums of observed (the reference's totalInteractionCountSoFar, fithic.py:183):
+        // every thread scans a contiguous slice, thread 0 chains the slice totals
+        {
+            const int per = (nk + FIT_THREADS - 1) / FIT_THREADS;
+            const int lo = tid * per, hi = min(lo + per, nk);
+            long long run = 0;
+            for (int k = lo; k < hi; ++k) { run += obs_s[k]; pre_s[k] = run; }
+            sh.slice_tot[tid] = run;
+            __syncthreads();
+            if (tid == 0) { long long c = 0; for (int t = 0; t < FIT_THREADS; ++t) { long long v = sh.slice_tot[t]; sh.slice_tot[t] = c; c += v; } }
+            __syncthreads();
+            const long long add = sh.slice_tot[tid];
+            for (int k = lo; k < hi; ++k) pre_s[k] += add;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // Bin boundaries by warp 0.  A bin that starts at key s closes at the first key k >= s with
+            //   observed[k] >= desired  or  (sum of observed[s..k]) >= desired        (fithic.py:188-197)
+            // which 32 lanes test for 32 consecutive keys at a time.  `desired` is an int floor for the first
+            // bin (:167) and a double afterwards (:209); for an integer v, v >= d  <=>  v >= ceil(d).
+            const int lane = tid;
+            int stc = BBK_FIT_OK, nout = 0;
             if (S == 0) {
                 bool any = false;
-                for (int k = 0; k < nk && !any; ++k) any = bbk_in_range((long long)k * P.R, P.min_dist, P.max_dist);
-                stc = any ? BBK_FIT_S_ZERO : BBK_FIT_OK;
+                for (int k = lane; k < nk; k += 32) any |= bbk_in_range((long long)k * P.R, P.min_dist, P.max_dist);
+                stc = __any_sync(0xffffffffu, any) ? BBK_FIT_S_ZERO : BBK_FIT_OK;
             } else {
-                stc = bbk_eo_boundaries((const int64_t*)obs_s, nk, S, P.n_bins, P.R, P.min_dist, P.max_dist,
-                                        bstart, bend, P.max_bins, &nout);
+                // the in-range keys form one interval [klo, khi]
+                int klo = nk, khi = -1;
+                for (int k = lane; k < nk; k += 32)
+                    if (bbk_in_range((long long)k * P.R, P.min_dist, P.max_dist)) { klo = min(klo, k); khi = max(khi, k); }
+                for (int o = 16; o > 0; o >>= 1) {
+                    klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+                    khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
+                }
+                long long D = 0;
+                if (P.n_bins != 0) D = (S >= 0 || S % P.n_bins == 0) ? S / P.n_bins : S / P.n_bins - 1;   // floor (:167)
+                int n = 0, s0 = klo;
+                while (s0 <= khi) {
+                    const long long base = s0 > 0 ? pre_s[s0 - 1] : 0;
+                    int kk = -1;
+                    for (int k0w = s0; k0w <= khi; k0w += 32) {
+                        const int k = k0w + lane;
+                        bool hit = k <= khi && (obs_s[k] >= D || pre_s[k] - base >= D);
+                        unsigned bal = __ballot_sync(0xffffffffu, hit);
+                        if (bal) { kk = k0w + __ffs(bal) - 1; break; }
+                    }
+                    if (kk < 0) break;                               // the trailing, unfilled bin is dropped
+                    if (nout >= P.max_bins) { stc = BBK_FIT_TOO_MANY_BINS; break; }
+                    if (lane == 0) { bstart[nout] = s0; bend[nout] = kk; }
+                    nout += 1;
+                    n += 1;                                          // :206
+                    if (n < P.n_bins) {                              // :208-209
+                        double dd = 1.0 * (double)(S - pre_s[kk]) / (double)(P.n_bins - n);
+                        double cd = ceil(dd);
+                        D = cd >= 9.2e18 ? 0x7fffffffffffffffll : (cd <= -9.2e18 ? -0x7fffffffffffffffll : (long long)cd);
+                    }
+                    s0 = kk + 1;
+                }
             }
-            sh.status = stc;
-            sh.n_out = nout;
+            if (lane == 0) { sh.status = stc; sh.n_out = stc == BBK_FIT_OK ? nout : 0; }
         }
         __syncthreads();
         m = sh.n_out;
@@ -186,11 +237,13 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
     if (sh.status == BBK_FIT_OK) {
         const int L = sh.L, n = sh.st.n;
         // knots / coefficients back into shared memory for the evaluation
-        size_t need = (size_t)2 * (m + 4) + (size_t)3 * L + 8;
+        size_t need = (size_t)3 * (m + 4) + (size_t)4 * L + 8;
         double* base = pick(pool, P.pool_doubles, need, P.gws);
         double* tk = base;
         double* ck = base + (m + 4);
-        double* wmean = ck + (m + 4);
+        double* rterm = ck + (m + 4);
+        double* vraw = rterm + (m + 4);
+        double* wmean = vraw + L;
         double* wcount = wmean + L;
         int* wstart = (int*)(wcount + L);
         for (int i = tid; i < n; i += FIT_THREADS) { tk[i] = P.knots[i]; ck[i] = P.coefs[i]; }
@@ -202,16 +255,29 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         }
         __syncthreads();
         // ---------------- antitonic regression (fithic.py:361-362) and the residual (fithic.py:374)
+        // residual terms in parallel (summed in order by thread 0 below)
+        for (int j = tid; j < m; j += FIT_THREADS) {
+            int cur = 4;
+            double dv = P.y[j] - bbk_spline_eval(tk, n, ck, P.x[j], &cur);
+            rterm[j] = dv * dv;
+        }
+        for (int i = tid; i < L; i += FIT_THREADS) vraw[i] = P.spline_raw[i];
+        __syncthreads();
         if (tid == 0) {
             sh.t[4] = clock64();
-            bbk_antitonic_pava(P.spline_raw, L, P.spline_y, wmean, wcount, wstart);
+            sh.n_blocks = bbk_antitonic_pava_blocks(vraw, L, wmean, wcount, wstart);
             double res = 0.0;
-            int cur = 4;
-            for (int j = 0; j < m; ++j) {
-                double dv = P.y[j] - bbk_spline_eval(tk, n, ck, P.x[j], &cur);
-                res = res + dv * dv;
-            }
+            for (int j = 0; j < m; ++j) res = res + rterm[j];
             P.result->residual = res;
+        }
+        __syncthreads();
+        {   // expand the blocks: element i of the reversed view belongs to the last block with start <= i
+            const int nb = sh.n_blocks;
+            for (int i = tid; i < L; i += FIT_THREADS) {
+                int lo = 0, hi = nb - 1;
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (wstart[mid] <= i) lo = mid; else hi = mid - 1; }
+                P.spline_y[L - 1 - i] = wmean[lo];
+            }
         }
         for (int i = L + tid; i < P.nkeys; i += FIT_THREADS) { P.spline_y[i] = 0.0; P.spline_raw[i] = 0.0; }
     }
@@ -267,9 +333,9 @@ int launch_fit(FitParams& P, size_t workspace_bytes, cudaStream_t st) {
 
 extern "C" size_t bbk_fit_workspace_bytes(int32_t max_bins, int32_t nkeys) {
     size_t m = max_bins > 4 ? (size_t)max_bins : 4;
-    size_t a = (size_t)2 * nkeys + m + 2;
+    size_t a = (size_t)3 * nkeys + m + 2;
     size_t b = bbk_coop_ws_doubles((int)m) + 2 * m;
-    size_t c = 2 * (m + 4) + (size_t)3 * nkeys + 8;
+    size_t c = 3 * (m + 4) + (size_t)4 * nkeys + 8;
     size_t mx = a > b ? a : b;
     mx = mx > c ? mx : c;
     return (mx + 16) * sizeof(double);

@@ -529,47 +529,48 @@ BBK_HD double bbk_spline_eval(const double* t, int n, const double* c, double ar
 // (sklearn/isotonic.py isotonic_regression(..., increasing=False) -> y[::-1]); block means are
 // kept as (weighted-mean) running values, merged backwards, exactly in that order.
 // v[L] in, out[L]; work arrays wmean[L], wcount[L] (doubles), start[L+1] (int32).
-BBK_HD void bbk_antitonic_pava(const double* v, int L, double* out, double* wmean, double* wcount, int32_t* start) {
-    // reversed view: u[i] = v[L-1-i]; solve non-decreasing on u
-    int b = 0;   // number of blocks - 1
-    if (L <= 0) return;
-    wmean[0] = v[L - 1];
+BBK_HD int bbk_antitonic_pava_blocks(const double* v, int L, double* wmean, double* wcount, int32_t* start) {
+    // Pool-adjacent-violators on the reversed view u[i] = v[L-1-i] (non-decreasing fit), the current block
+    // carried in registers.  Returns the number of blocks; block b covers u[start[b] .. start[b+1]-1].
+    if (L <= 0) return 0;
+    int b = 0;
+    double xb_prev = v[L - 1], wb_prev = 1.0;
+    wmean[0] = xb_prev;
     wcount[0] = 1.0;
     start[0] = 0;
     start[1] = 1;
-    int i = 1;
-    while (i < L) {
+    for (int i = 1; i < L; ++i) {
         b += 1;
-        double xb_prev = wmean[b - 1];
-        double wb_prev = wcount[b - 1];
-        wmean[b] = v[L - 1 - i];
-        wcount[b] = 1.0;
-        i += 1;
-        start[b + 1] = i;
-        if (xb_prev >= wmean[b]) {
+        double xb = v[L - 1 - i], wb = 1.0;
+        if (xb_prev >= xb) {
             // violation (or tie): pool with the previous block, then look ahead and behind
             b -= 1;
-            double sb = wb_prev * xb_prev + wcount[b + 1] * wmean[b + 1];
-            wb_prev += wcount[b + 1];
-            xb_prev = sb / wb_prev;
-            while (i < L && v[L - 1 - i] <= xb_prev) {
-                sb += v[L - 1 - i];
-                wb_prev += 1.0;
-                xb_prev = sb / wb_prev;
+            double sb = wb_prev * xb_prev + wb * xb;
+            wb += wb_prev;
+            xb = sb / wb;
+            while (i < L - 1 && xb >= v[L - 2 - i]) {
                 i += 1;
+                sb += v[L - 1 - i];
+                wb += 1.0;
+                xb = sb / wb;
             }
-            while (b > 0 && wmean[b - 1] >= xb_prev) {
+            while (b > 0 && wmean[b - 1] >= xb) {
                 b -= 1;
                 sb += wcount[b] * wmean[b];
-                wb_prev += wcount[b];
-                xb_prev = sb / wb_prev;
+                wb += wcount[b];
+                xb = sb / wb;
             }
-            wmean[b] = xb_prev;
-            wcount[b] = wb_prev;
-            start[b + 1] = i;
         }
+        wmean[b] = xb_prev = xb;
+        wcount[b] = wb_prev = wb;
+        start[b + 1] = i + 1;
     }
-    for (int blk = 0; blk <= b; ++blk)
+    return b + 1;
+}
+
+BBK_HD void bbk_antitonic_pava(const double* v, int L, double* out, double* wmean, double* wcount, int32_t* start) {
+    int nb = bbk_antitonic_pava_blocks(v, L, wmean, wcount, start);
+    for (int blk = 0; blk < nb; ++blk)
         for (int j = start[blk]; j < start[blk + 1]; ++j) out[L - 1 - j] = wmean[blk];
 }
 

@@ -15,6 +15,26 @@ import torch
 from . import _lib
 
 
+def reduce_distance_stats(obs_sum, totals, group=None):
+    """All-reduce K1's outputs across ranks, in place: per-distance sums and the six sum-type totals are
+    added, minObservedGenomicDist / maxObservedGenomicDist take min / max (fithic.py:258-259).  Integer
+    reductions are independent of the reduction order, so every rank ends with bit-identical tables and
+    the fit that follows is replicated deterministically.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(obs_sum, op=dist.ReduceOp.SUM, group=group)
+    sums = totals[:6].clone()
+    mn = totals[6:7].clone()
+    mx = totals[7:8].clone()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    totals[:6] = sums
+    totals[6:7] = mn
+    totals[7:8] = mx
+
+
 class Shard(object):
     """Contact records of one shard (a chromosome or a diagonal band), as int32 CUDA tensors.
 
@@ -115,19 +135,7 @@ class PassEngine(object):
 
     def allreduce_stats(self, group=None):
         """Sum the distance table and totals over ranks (integers: order-free, bit-exact)."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return
-        dist.all_reduce(self.obs_sum, op=dist.ReduceOp.SUM, group=group)
-        sums = self.totals[:6].clone()
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        mn = self.totals[6:7].clone()
-        mx = self.totals[7:8].clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-        self.totals[:6] = sums
-        self.totals[6:7] = mn
-        self.totals[7:8] = mx
+        reduce_distance_stats(self.obs_sum, self.totals, group)
 
     def fit(self):
         _lib.check(self.lib.bbk_fit(_lib.ptr(self.possible), _lib.ptr(self.obs_sum), self.nkeys, _lib.ptr(self.totals),

@@ -1,0 +1,158 @@
+"""GPU tests: (1) the path-based drop-in (gzip text in, significances.txt.gz out, stage functions) against the
+golden outputs of the reference; (2) size-independent properties at BASELINE's full config-2 size."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, log10_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_inputs(tmp, g):
+    def name(c):
+        return "chr%d" % (int(c) + 1)
+    inter = os.path.join(tmp, "interactions.gz")
+    frags = os.path.join(tmp, "fragments.gz")
+    with gzip.open(inter, "wt") as fh:
+        for a, b, c, d, e in zip(g["chr1"], g["mid1"], g["chr2"], g["mid2"], g["count"]):
+            fh.write("%s\t%d\t%s\t%d\t%d\n" % (name(a), b, name(c), d, e))
+    with gzip.open(frags, "wt") as fh:
+        for c, m in zip(g["frag_chrom"], g["frag_mid"]):
+            fh.write("%s\t%d\t0\t0\t0\n" % (name(c), m))
+    bias = "none"
+    if bool(g["has_bias"]):
+        bias = os.path.join(tmp, "biases.gz")
+        with gzip.open(bias, "wt") as fh:
+            for c, m, b in zip(g["bias_chrom"], g["bias_mid"], g["bias_val"]):
+                fh.write("%s\t%d\t%r\n" % (name(c), m, float(b)))
+    return inter, frags, bias
+
+
+def _parse(path):
+    rows = []
+    with gzip.open(path, "rt") as fh:
+        header = fh.readline()
+        for line in fh:
+            rows.append(line.rstrip("\n").split("\t"))
+    return header, rows
+
+
+@pytest.mark.parametrize("name", ["pass_bias_dense", "pass_messy"])
+def test_fit_transform_files_match_reference_output(name, tmp_path):
+    from blueberry_b200.fithic import FitHiC
+    g = load_golden(name)
+    inter, frags, bias = _write_inputs(str(tmp_path), g)
+    R = int(g["resolution"])
+    lib = os.path.join(str(tmp_path), "lib")
+    model = FitHiC(lib, R, n_bins=int(g["n_bins"]), max_dist=int(g["max_dist_arg"]), min_dist=int(g["min_dist_arg"]))
+    assert model.fit_transform(inter, frags, bias) is None                    # fithic.py:85-108 returns None
+    assert os.path.exists("%s.fithic_pass1.res%d.txt" % (lib, R))             # opened, never written (fithic.py:164)
+    header, rows = _parse("%s.spline_pass1.res%d.significances.txt.gz" % (lib, R))
+    assert header == "chr1\tfragmentMid1\tchr2\tfragmentMid2\tcontactCount\tp-value\tq-value\n"   # fithic.py:411
+    assert len(rows) == len(g["ref_out_p"])
+    assert [int(r[1]) for r in rows] == g["ref_out_mid1"].tolist()
+    assert [int(r[3]) for r in rows] == g["ref_out_mid2"].tolist()
+    assert [int(r[4]) for r in rows] == g["ref_out_count"].tolist()
+    assert [r[0] for r in rows] == ["chr%d" % (c + 1) for c in g["ref_out_chr1"]]
+    assert all(r[6] == "-1" for r in rows)                                     # fithic.py:435
+    ok, nbad = log10_close(np.array([float(r[5]) for r in rows]), g["ref_out_p"], 1e-6)
+    assert ok, nbad
+
+
+def test_stage_functions_drop_in(tmp_path):
+    """generate_FragPairs -> read_interactions -> calculate_probabilities -> fit_spline, as fithic() chains them."""
+    from blueberry_b200 import fithic as f
+    g = load_golden("pass_bias_dense")
+    inter, frags, bias = _write_inputs(str(tmp_path), g)
+    R, lo, hi = int(g["resolution"]), int(g["ref_min_dist"]), int(g["ref_max_dist"])
+    main = f.generate_FragPairs(frags, R, lo, hi, False)
+    assert sorted(main) == [k * R for k in range(len(g["ref_possible"]))]
+    assert [main[k][0] for k in sorted(main)] == g["ref_possible"].tolist()
+    assert f.possibleIntraInRangeCount == int(g["ref_possible_intra_in_range"])
+    bias_dic = f.read_bias_file(bias, False)
+    main = f.read_interactions(main, inter, lo, hi, False)
+    assert [main[k][1] for k in sorted(main)] == g["ref_observed"].tolist()
+    assert f.observedIntraInRangeSum == int(g["ref_S"])
+    x, y, yerr = f.calculate_probabilities(main, int(g["n_bins"]), R, lo, hi, os.path.join(str(tmp_path), "l.fithic_pass1"), False)
+    assert x == g["ref_x"].tolist() and y == g["ref_y"].tolist() and yerr == [0.0] * len(x)
+    sx, sy, residual = f.fit_spline(main, x, y, yerr, inter, os.path.join(str(tmp_path), "l.spline_pass1"), bias_dic, R, lo, hi, False)
+    assert sx == g["ref_spline_x"].tolist()
+    assert np.allclose(sy, g["ref_spline_y"], rtol=1e-12, atol=0)
+    header, rows = _parse(os.path.join(str(tmp_path), "l.spline_pass1.res%d.significances.txt.gz" % R))
+    assert len(rows) == len(g["ref_out_p"])
+    ok, nbad = log10_close(np.array([float(r[5]) for r in rows]), g["ref_out_p"], 1e-6)
+    assert ok, nbad
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 (chr1 @ 5 kb, 97,750,851 records) generated on the device: properties that need no oracle."""
+    import torch
+    from blueberry_b200 import _lib
+    from blueberry_b200.engine import BiasTables, PassEngine, Shard
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    R, nb, K, max_dist = 5000, 49851, 2000, 10_000_000
+    P = int(lib.bbk_synth_n_pairs(nb, K))
+    assert P == 97750851
+    rng = np.random.default_rng(5)
+    bias_host = np.exp(rng.normal(0.0, 0.25, size=nb))
+    bias_dev = torch.from_numpy(bias_host).to(dev)
+    mid1 = torch.empty(P, dtype=torch.int32, device=dev)
+    mid2 = torch.empty(P, dtype=torch.int32, device=dev)
+    count = torch.empty(P, dtype=torch.int32, device=dev)
+    _lib.check(lib.bbk_synth_contacts(nb, K, R, 600.0, 1.08, 99, _lib.ptr(bias_dev), _lib.ptr(mid1), _lib.ptr(mid2),
+                                      _lib.ptr(count), _lib.stream_ptr()), "synth")
+    eng = PassEngine(R, 100, 0, max_dist, nb, dev)
+    eng.set_fragments([nb], [(nb - 1) * R])
+    eng.set_bias(BiasTables([np.where((bias_host < 0.5) | (bias_host > 2), -1.0, bias_host)], [R // 2], dev))
+    p = torch.empty(P + 1, dtype=torch.float64, device=dev)[:P]
+    q = torch.empty(P + 1, dtype=torch.float64, device=dev)[:P]
+    eng.run([Shard(mid1, mid2, count)], [p], [q])
+    fit = eng.read_fit()
+    d = (mid2 - mid1).long()
+    # K1: a checksum of checksums - the table must hold exactly the in-range counts, distance by distance
+    in_range = (d > 0) & (d <= max_dist)
+    S = int(count[in_range].long().sum().item())
+    assert int(eng.totals[0].item()) == S == fit.S
+    assert int(eng.obs_sum.sum().item()) == S
+    ref_hist = torch.zeros(nb, dtype=torch.int64, device=dev).index_add_(0, (d[in_range] // R), count[in_range].long())
+    assert torch.equal(ref_hist, eng.obs_sum)
+    assert int(eng.totals[1].item()) == int(in_range.sum().item())
+    assert int(eng.totals[3].item()) == P and int(eng.totals[2].item()) == int(count.long().sum().item())
+    assert (int(eng.totals[6].item()), int(eng.totals[7].item())) == (R, max_dist)
+    # K2a: closed form
+    k = torch.arange(nb, device=dev)
+    assert torch.equal(eng.possible, nb - k)
+    # K3: the fitted prior is positive and non-increasing over the grid
+    sy = eng.spline_y[:fit.L]
+    assert bool((sy > 0).all()) and bool((sy[1:] <= sy[:-1]).all())
+    # K4: zero counts -> exactly 1 (or NaN when a bias is discarded); everything else in (0, 1]; more contacts
+    # at the same prior never give a larger p
+    ok_bias = torch.from_numpy((bias_host >= 0.5) & (bias_host <= 2)).to(dev)
+    i1 = (mid1 - R // 2) // R
+    i2 = (mid2 - R // 2) // R
+    valid = ok_bias[i1] & ok_bias[i2]
+    assert bool(torch.isnan(p[~valid]).all()) and not bool(torch.isnan(p[valid]).any())
+    assert bool((p[valid & (count == 0)] == 1.0).all())
+    pv = p[valid]
+    assert bool(((pv >= 0) & (pv <= 1)).all())
+    # K5: q is NaN exactly where p is, q >= p, and sorting by p sorts q (forward running max)
+    assert torch.equal(torch.isnan(q), torch.isnan(p))
+    qv = q[valid]
+    assert bool((qv >= pv).all()) and bool((qv <= 1).all())
+    n_valid = int(valid.sum().item())
+    cand = pv < 1e-3
+    ps, order = torch.sort(pv[cand])
+    qs = qv[cand][order]
+    assert bool((qs[1:] >= qs[:-1]).all())
+    # exact BH on the smallest 10^5 p-values (ranks below any saturation point are exact ranks)
+    top = min(100000, ps.numel())
+    ps_h, qs_h = ps[:top].cpu().numpy(), qs[:top].cpu().numpy()
+    bh = np.maximum.accumulate(np.minimum(ps_h * n_valid / np.arange(1, top + 1), 1))
+    # ties share the first tie's value: compare through the oracle's tie-aware formulation
+    first = np.searchsorted(ps_h, ps_h, side="left")
+    bh_t = np.maximum.accumulate(np.minimum(ps_h * n_valid / (first + 1), 1))
+    assert np.array_equal(qs_h, bh_t) or np.array_equal(qs_h, bh)
