@@ -134,7 +134,9 @@ def test_full_size_properties_config2():
     ok_bias = torch.from_numpy((bias_host >= 0.5) & (bias_host <= 2)).to(dev)
     i1 = (mid1 - R // 2) // R
     i2 = (mid2 - R // 2) // R
-    valid = ok_bias[i1] & ok_bias[i2]
+    # a discarded bias is -1 (fithic.py:147-149): exactly one of the two makes the prior negative and the row is
+    # dropped (:434); two of them multiply to +1 and the row is scored - as in the reference
+    valid = ok_bias[i1] == ok_bias[i2]
     assert bool(torch.isnan(p[~valid]).all()) and not bool(torch.isnan(p[valid]).any())
     assert bool((p[valid & (count == 0)] == 1.0).all())
     pv = p[valid]
