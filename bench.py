@@ -46,23 +46,33 @@ def _peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons; started before the warm-up (nvidia-smi takes ~100 ms to come up),
+    reduced over the samples whose timestamp falls inside the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -70,25 +80,26 @@ class ClockSampler(object):
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.tmp.read().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.tmp.name)
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.005 <= r[0] <= self.t1 + 0.005]
+        use = inside if inside else rows[-20:]
+        if use:
+            out["sm_mhz"] = statistics.median(r[1] for r in use)
+            out["sm_max_mhz"] = max(r[2] for r in use)
+            out["reasons"] = sorted(set(x for r in use for x in r[3]))
+            out["samples"] = len(use)
+            out["window"] = "timed region" if inside else "last samples under load (timed region shorter than the sampling period)"
         return out
 
 
@@ -130,7 +141,7 @@ def cpu_baseline(cores, nb=3000, repeat=1):
     return pairs / wall, pairs, wall, time.perf_counter() - t0
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,13 +167,13 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(out_fd, line)
 
 
 # =================================================================================================
 # GPU arm
 # =================================================================================================
-def run_ours(args):
+def run_ours(args, out_fd):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -218,6 +229,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -228,14 +240,17 @@ def run_ours(args):
     barrier()
 
     # ---- timed region: exactly K steps, device events, max over ranks
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark_start()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -331,9 +346,22 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner there) get stderr instead."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -345,10 +373,11 @@ def main():
     ap.add_argument("--bins", type=int, default=CHR1_BINS, help="bins of the per-GPU chromosome (default chr1 @ 5 kb)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    out_fd = _claim_stdout()
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out_fd)
     else:
-        run_ours(args)
+        run_ours(args, out_fd)
 
 
 if __name__ == "__main__":
