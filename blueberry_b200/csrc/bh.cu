@@ -198,7 +198,15 @@ __device__ __forceinline__ int sort_parity(const BhState* st, int pass) {
 }
 
 struct Chunk { long long lo, hi; };
+// block columns actually used for n elements: at least one tile per block, at most G
+__device__ __forceinline__ int eff_blocks(long long n, int G) {
+    long long g = (n + SORT_TILE - 1) / SORT_TILE;
+    if (g < 1) g = 1;
+    return g < G ? (int)g : G;
+}
 __device__ __forceinline__ Chunk chunk_of(long long n, int G, int b) {
+    G = eff_blocks(n, G);
+    if (b >= G) { Chunk e; e.lo = e.hi = n; return e; }
     long long per = (n + G - 1) / G;
     per = (per + SORT_TILE - 1) / SORT_TILE * SORT_TILE;     // whole tiles per block
     Chunk c;
@@ -216,12 +224,14 @@ __global__ void __launch_bounds__(BH_THREADS) sort_hist_kernel(BhLayout L, int p
     const BhState* st = L.st;
     const long long n = (long long)st->n_cand;
     const unsigned long long* keys = L.keys[sort_parity(st, pass)];
+    const int Ge = eff_blocks(n, L.G);
+    if ((int)blockIdx.x >= Ge) return;
     Chunk c = chunk_of(n, L.G, blockIdx.x);
     const int shift = 8 * pass;
     for (long long i = c.lo + threadIdx.x; i < c.hi; i += blockDim.x)
         atomicAdd(&sh[(unsigned)(keys[i] >> shift) & 255u], 1u);
     __syncthreads();
-    L.block_hist[(size_t)threadIdx.x * L.G + blockIdx.x] = sh[threadIdx.x];
+    L.block_hist[(size_t)threadIdx.x * Ge + blockIdx.x] = sh[threadIdx.x];
 }
 
 // one CTA of 1024 threads: exclusive scan of the digit-major table [256][G], skip detection.
@@ -230,18 +240,29 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(BhLayout L, int pass) {
     __shared__ unsigned tot[256];
     __shared__ unsigned dbase[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = L.G;
+    const int G = eff_blocks((long long)L.st->n_cand, L.G);
+    constexpr int MAX_IT = 32;                               // G <= 1024 block columns
     for (int dd = 0; dd < 8; ++dd) {
         const int d = warp * 8 + dd;
         unsigned* row = L.block_hist + (size_t)d * G;
-        unsigned carry = 0;
-        for (int b0 = 0; b0 < G; b0 += 32) {
-            int b = b0 + lane;
-            unsigned v = b < G ? row[b] : 0, x = v;
+        unsigned v[MAX_IT];
+        const int n_it = (G + 31) >> 5;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (b < G) row[b] = carry + x - v;               // exclusive, relative to the digit's start
-            carry += __shfl_sync(0xffffffffu, x, 31);
+        for (int k = 0; k < MAX_IT; ++k) {                   // all loads of the row in flight at once
+            int b = k * 32 + lane;
+            v[k] = (k < n_it && b < G) ? row[b] : 0u;
+        }
+        unsigned carry = 0;
+#pragma unroll
+        for (int k = 0; k < MAX_IT; ++k) {
+            if (k < n_it) {
+                unsigned x = v[k];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                int b = k * 32 + lane;
+                if (b < G) row[b] = carry + x - v[k];        // exclusive, relative to the digit's start
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
         }
         if (lane == 0) tot[d] = carry;
     }
@@ -263,11 +284,12 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(BhLayout L, int pass) {
         const unsigned add = dbase[d];
         if (add) for (int b = lane; b < G; b += 32) row[b] += add;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         const unsigned n = (unsigned)L.st->n_cand;
         int uniform = 0;
-        for (int d = 0; d < 256; ++d) uniform |= (tot[d] == n);
-        L.st->skip[pass] = (uniform || n == 0) ? 1 : 0;
+        for (int d = lane; d < 256; d += 32) uniform |= (tot[d] == n);
+        uniform = __any_sync(0xffffffffu, uniform);
+        if (lane == 0) L.st->skip[pass] = (uniform || n == 0) ? 1 : 0;
     }
 }
 
@@ -284,7 +306,9 @@ __global__ void __launch_bounds__(BH_THREADS) sort_scatter_kernel(BhLayout L, in
     unsigned* iout = L.idx[par ^ 1];
     const int shift = 8 * pass;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = L.block_hist[(size_t)threadIdx.x * L.G + blockIdx.x];
+    const int Ge = eff_blocks(n, L.G);
+    if ((int)blockIdx.x >= Ge) return;
+    base[threadIdx.x] = L.block_hist[(size_t)threadIdx.x * Ge + blockIdx.x];
     Chunk c = chunk_of(n, L.G, blockIdx.x);
     for (long long tile = c.lo; tile < c.hi; tile += SORT_TILE) {
         for (int d = lane; d < 256; d += 32) whist[warp][d] = 0;
@@ -513,7 +537,7 @@ __global__ void __launch_bounds__(BH_THREADS) ones_fix_kernel(const double* p, l
         if (p[i] == 1.0) q[i] = qo;
 }
 
-int sort_blocks() { return bbk_num_sms() * 4; }
+int sort_blocks() { int g = bbk_num_sms() * 4; return g > 1024 ? 1024 : g; }
 
 }  // namespace
 

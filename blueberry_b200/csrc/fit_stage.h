@@ -539,20 +539,23 @@ BBK_HD int bbk_antitonic_pava_blocks(const double* v, int L, double* wmean, doub
     wcount[0] = 1.0;
     start[0] = 0;
     start[1] = 1;
+    double nxt = L > 1 ? v[L - 2] : 0.0;          // element i of the reversed view, loaded one step ahead
     for (int i = 1; i < L; ++i) {
         b += 1;
-        double xb = v[L - 1 - i], wb = 1.0;
+        double xb = nxt, wb = 1.0;
+        if (i + 1 < L) nxt = v[L - 2 - i];
         if (xb_prev >= xb) {
             // violation (or tie): pool with the previous block, then look ahead and behind
             b -= 1;
             double sb = wb_prev * xb_prev + wb * xb;
             wb += wb_prev;
             xb = sb / wb;
-            while (i < L - 1 && xb >= v[L - 2 - i]) {
+            while (i < L - 1 && xb >= nxt) {
                 i += 1;
-                sb += v[L - 1 - i];
+                sb += nxt;
                 wb += 1.0;
                 xb = sb / wb;
+                if (i + 1 < L) nxt = v[L - 2 - i];
             }
             while (b > 0 && wmean[b - 1] >= xb) {
                 b -= 1;

@@ -42,7 +42,7 @@ constexpr int PV_THREADS = 256;
 constexpr int PV_WARPS = PV_THREADS / 32;
 constexpr int RCP_TAB = 1024;        // 1/j for j < RCP_TAB
 constexpr int LF_TAB = 256;          // ln j! for j < LF_TAB
-constexpr double TAIL_EPS = 1e-12;
+constexpr double TAIL_EPS = 2e-12;
 constexpr double LN_2PI = 1.8378770664093454836;
 
 // mathematical constants, filled once per device (pv_tables_kernel): 1/j and ln j!
@@ -187,21 +187,50 @@ __device__ __forceinline__ void tail_setup(int c, double q, const TailConst& K, 
     }
 }
 
-// one term of the state's own series
-__device__ __forceinline__ void tail_term(TailState& T, const TailConst& K, const double* __restrict__ rcp) {
-    double f;
+// 16 terms of the state's own series.  The per-term work is kept to the recurrence itself: the table bound
+// and the end of the support are checked once per block (the slow variant handles blocks that cross them).
+__device__ __forceinline__ void tail_terms16(TailState& T, const TailConst& K, const double* __restrict__ rcp) {
     if (T.upper) {
-        double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
-        f = T.a > 0.0 ? T.a * r : 0.0;
-        T.j += 1;
+        if (T.j + 16 <= RCP_TAB && T.a > 16.0 * T.step) {
+            const double* r = rcp + T.j;
+#pragma unroll 4
+            for (int u = 0; u < 16; ++u) {
+                T.term *= T.a * r[u];
+                T.sum += T.term;
+                T.a -= T.step;
+            }
+            T.j += 16;
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < 16; ++u) {
+                double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
+                T.term *= T.a > 0.0 ? T.a * r : 0.0;
+                T.sum += T.term;
+                T.a -= T.step;
+                T.j += 1;
+            }
+        }
     } else {
-        f = T.j > 0 ? T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e))) : 0.0;
-        T.e -= K.inv_n;
-        T.j -= 1;
+        if (T.j > 16) {
+#pragma unroll 4
+            for (int u = 0; u < 16; ++u) {
+                T.term *= T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e)));
+                T.sum += T.term;
+                T.a -= T.step;
+                T.e -= K.inv_n;
+            }
+            T.j -= 16;
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < 16; ++u) {
+                T.term *= T.j > 0 ? T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e))) : 0.0;
+                T.sum += T.term;
+                T.a -= T.step;
+                T.e -= K.inv_n;
+                T.j -= 1;
+            }
+        }
     }
-    T.term *= f;
-    T.sum += T.term;
-    T.a -= T.step;
 }
 
 // 8-lane group: every lane of the group holds the SAME state; each takes 8 consecutive terms per step and
@@ -469,8 +498,7 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
             unsigned rmask = __ballot_sync(0xffffffffu, running);
             while (__popc(rmask) >= 8) {
                 if (running) {
-#pragma unroll 1
-                    for (int u = 0; u < 16; ++u) tail_term(T, K, sh.rcp);
+                    tail_terms16(T, K, sh.rcp);
                     running = !(T.term < TAIL_EPS * T.sum);
                 }
                 rmask = __ballot_sync(0xffffffffu, running);
