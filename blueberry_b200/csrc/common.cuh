@@ -66,19 +66,35 @@ __device__ __forceinline__ void st_stream_double(double* p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 
-// exact unsigned division of a < 2^32 by an invariant divisor R < 2^32: q = hi64(a * ceil(2^64 / R))
+// exact unsigned division by an invariant divisor R < 2^32:
+//   fastdiv   : any a < 2^32        q = hi64(a * ceil(2^64 / R))
+//   fastdiv31 : a < 2^31 (cheaper)  q = hi32(a * ceil(2^(31+l) / R)) >> (l-1),  l = ceil(log2 R)
 struct FastDiv {
     uint64_t magic;   // ceil(2^64 / R), 0 when R == 1
     uint32_t R;
+    uint32_t mul31;   // ceil(2^(31+l) / R), 0 when R == 1
+    uint32_t sh31;    // l - 1
 };
 static inline FastDiv make_fastdiv(uint64_t R) {
     FastDiv f;
     f.R = (uint32_t)R;
     f.magic = (R <= 1) ? 0 : (~0ull / R + 1);   // floor((2^64-1)/R)+1 == ceil(2^64/R) for R not a power of two; exact otherwise too
+    f.mul31 = 0;
+    f.sh31 = 0;
+    if (R > 1) {
+        uint32_t l = 0;
+        while ((1ull << l) < R) ++l;
+        unsigned __int128 num = (unsigned __int128)1 << (31 + l);
+        f.mul31 = (uint32_t)((num + R - 1) / R);
+        f.sh31 = l - 1;
+    }
     return f;
 }
 __device__ __forceinline__ uint32_t fastdiv(uint32_t a, const FastDiv& f) {
     return f.magic ? (uint32_t)__umul64hi((uint64_t)a, f.magic) : a;
+}
+__device__ __forceinline__ uint32_t fastdiv31(uint32_t a, const FastDiv& f) {
+    return f.mul31 ? (__umulhi(a, f.mul31) >> f.sh31) : a;
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {

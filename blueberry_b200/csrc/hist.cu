@@ -27,6 +27,7 @@ struct HistParams {
     const int32_t* count;
     long long n_pairs;
     long long min_dist, max_dist;
+    long long lo_excl, hi_incl;   // in range  <=>  lo_excl < d <= hi_incl   (the -1 sentinels folded in)
     FastDiv div;
     int nkeys;        // len(mainDic)
     int nkeys_s;      // bins kept in shared memory (prefix of the table), 0 = none
@@ -89,6 +90,65 @@ __device__ __forceinline__ void process_record(const HistParams& P, unsigned* sh
     }
 }
 
+// FAST path (0 <= d <= max_dist < 2^31 for every in-range record, no chromosome columns): one int4 group = 4
+// consecutive records of a lane.  32-bit arithmetic throughout; the warp-uniform test (diagonal-major input:
+// all 128 records of the warp step on one distance) is made once per group, otherwise plain shared atomics.
+struct FastAcc {
+    long long S, intra_sum;
+    int in_range, intra_cnt, dmin, dmax;
+};
+
+__device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, bool live, FastAcc& a) {
+    const int m1s[4] = {m1.x, m1.y, m1.z, m1.w}, m2s[4] = {m2.x, m2.y, m2.z, m2.w}, cs[4] = {c.x, c.y, c.z, c.w};
+    unsigned key[4];
+    bool ok[4];
+    int csum = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const long long d64 = (long long)m2s[e] - (long long)m1s[e];                 // fithic.py:247
+        const bool in_range = live && d64 > P.lo_excl && d64 <= P.hi_incl;            // fithic.py:256-257
+        const int d = (int)d64;                                                       // valid when in_range
+        a.intra_sum += live ? cs[e] : 0;
+        a.intra_cnt += live ? 1 : 0;
+        if (in_range) {
+            a.dmin = min(a.dmin, d);                                                  // fithic.py:258-259
+            a.dmax = max(a.dmax, d);
+            a.S += cs[e];                                                             // fithic.py:262
+            a.in_range += 1;                                                          // fithic.py:263
+        }
+        const unsigned k = fastdiv31((unsigned)d, P.div);
+        key[e] = k;
+        ok[e] = in_range && cs[e] != 0 && k * P.div.R == (unsigned)d && k < (unsigned)P.nkeys;   // "distance in mainDic" (:260)
+        csum += ok[e] ? cs[e] : 0;
+    }
+    // big counts / keys beyond the shared table go straight to the global table
+    bool small[4];
+    bool any_small = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        small[e] = ok[e] && (unsigned)cs[e] < (unsigned)SMALL_COUNT_LIMIT && key[e] < (unsigned)P.nkeys_s;
+        if (ok[e] && !small[e]) atomicAdd((unsigned long long*)&P.obs_sum[key[e]], (unsigned long long)(long long)cs[e]);
+        any_small |= small[e];
+    }
+    // warp-uniform distance?  (every lane's 4 keys equal lane 0's first key, all of them "small" or zero-count)
+    const unsigned kref = __shfl_sync(0xffffffffu, key[0], 0);
+    bool mine_uniform = true;
+    int ssum = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        mine_uniform = mine_uniform && (!ok[e] || (small[e] && key[e] == kref));
+        ssum += small[e] ? cs[e] : 0;
+    }
+    if (__all_sync(0xffffffffu, mine_uniform)) {
+        unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)ssum);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&sh[phys_bin((int)kref, P.quarter)], tot);
+    } else if (any_small) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (small[e]) atomicAdd(&sh[phys_bin((int)key[e], P.quarter)], (unsigned)cs[e]);
+    }
+}
+
 __device__ __forceinline__ void flush_hist(const HistParams& P, unsigned* sh) {
     __syncthreads();
     for (int k = threadIdx.x; k < P.nkeys_s; k += blockDim.x) {
@@ -102,14 +162,15 @@ __device__ __forceinline__ void flush_hist(const HistParams& P, unsigned* sh) {
     __syncthreads();
 }
 
-template <bool HAS_CHR>
-__global__ void __launch_bounds__(HIST_THREADS, 2) hist_pairs_kernel(HistParams P) {
+template <bool HAS_CHR, bool FAST>
+__global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kernel(HistParams P) {
     extern __shared__ unsigned sh[];
     __shared__ long long red[8][HIST_THREADS / 32];
     for (int i = threadIdx.x; i < 4 * P.quarter; i += blockDim.x) sh[i] = 0;
     __syncthreads();
 
     Acc a = {0, 0, 0, 0, 0, 0, 500000000ll, 0ll};                      // fithic.py:40-41 initial min / max
+    FastAcc fa = {0, 0, 0, 0, 500000000, 0};
     const long long n_groups = P.n_pairs >> 2;                         // groups of 4 records (one int4 per column)
     const int4* m1v = reinterpret_cast<const int4*>(P.mid1);
     const int4* m2v = reinterpret_cast<const int4*>(P.mid2);
@@ -133,14 +194,19 @@ __global__ void __launch_bounds__(HIST_THREADS, 2) hist_pairs_kernel(HistParams 
             if (l0) { ax = ld_stream_int4(c1v + g0); ay = ld_stream_int4(c2v + g0); }
             if (l1) { bx = ld_stream_int4(c1v + g1); by = ld_stream_int4(c2v + g1); }
         }
-        process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0, a);
-        process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0, a);
-        process_record<HAS_CHR>(P, sh, a1.z, a2.z, ac.z, ax.z, ay.z, l0, a);
-        process_record<HAS_CHR>(P, sh, a1.w, a2.w, ac.w, ax.w, ay.w, l0, a);
-        process_record<HAS_CHR>(P, sh, b1.x, b2.x, bc.x, bx.x, by.x, l1, a);
-        process_record<HAS_CHR>(P, sh, b1.y, b2.y, bc.y, bx.y, by.y, l1, a);
-        process_record<HAS_CHR>(P, sh, b1.z, b2.z, bc.z, bx.z, by.z, l1, a);
-        process_record<HAS_CHR>(P, sh, b1.w, b2.w, bc.w, bx.w, by.w, l1, a);
+        if (FAST && !HAS_CHR) {
+            process_group_fast(P, sh, a1, a2, ac, l0, fa);
+            process_group_fast(P, sh, b1, b2, bc, l1, fa);
+        } else {
+            process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0, a);
+            process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0, a);
+            process_record<HAS_CHR>(P, sh, a1.z, a2.z, ac.z, ax.z, ay.z, l0, a);
+            process_record<HAS_CHR>(P, sh, a1.w, a2.w, ac.w, ax.w, ay.w, l0, a);
+            process_record<HAS_CHR>(P, sh, b1.x, b2.x, bc.x, bx.x, by.x, l1, a);
+            process_record<HAS_CHR>(P, sh, b1.y, b2.y, bc.y, bx.y, by.y, l1, a);
+            process_record<HAS_CHR>(P, sh, b1.z, b2.z, bc.z, bx.z, by.z, l1, a);
+            process_record<HAS_CHR>(P, sh, b1.w, b2.w, bc.w, bx.w, by.w, l1, a);
+        }
         since_flush += 4 * tile_groups;
         if (since_flush >= FLUSH_PAIRS) {      // uniform across the CTA
             flush_hist(P, sh);
@@ -157,6 +223,11 @@ __global__ void __launch_bounds__(HIST_THREADS, 2) hist_pairs_kernel(HistParams 
         process_record<HAS_CHR>(P, sh, m1, m2, c, c1, c2, live, a);
     }
     flush_hist(P, sh);
+    if (FAST && !HAS_CHR) {
+        a.S += fa.S; a.in_range += fa.in_range; a.intra_sum += fa.intra_sum; a.intra_cnt += fa.intra_cnt;
+        a.dmin = fa.dmin < a.dmin ? fa.dmin : a.dmin;
+        a.dmax = fa.dmax > a.dmax ? fa.dmax : a.dmax;
+    }
 
     // scalar totals: warp shuffle -> shared -> one global atomic per CTA and quantity
     long long v[8] = {a.S, a.in_range, a.intra_sum, a.intra_cnt, a.inter_sum, a.inter_cnt, a.dmin, a.dmax};
@@ -212,6 +283,10 @@ extern "C" int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, cons
     P.chr1 = d_chr1; P.chr2 = d_chr2; P.mid1 = d_mid1; P.mid2 = d_mid2; P.count = d_count;
     P.n_pairs = n_pairs; P.min_dist = min_dist; P.max_dist = max_dist;
     P.div = make_fastdiv((uint64_t)resolution);
+    P.lo_excl = (min_dist == -1) ? (-0x7fffffffffffffffll - 1) : (min_dist > -1 ? min_dist : 0x7fffffffffffffffll);
+    P.hi_incl = (max_dist == -1) ? 0x7fffffffffffffffll : (max_dist > -1 ? max_dist : (-0x7fffffffffffffffll - 1));
+    // 31-bit fast path: every in-range distance is in [0, 2^31)
+    const bool fast = d_chr1 == nullptr && min_dist >= -1 && max_dist >= 0 && max_dist < (1ll << 31) && P.lo_excl >= -1;
     P.nkeys = nkeys;
     // only keys that can be in range need a shared bin: k*R <= max_dist
     long long want = nkeys;
@@ -231,11 +306,14 @@ extern "C" int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, cons
     if (need < grid) grid = need > 0 ? need : 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (d_chr1) {
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hist_pairs_kernel<true><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hist_pairs_kernel<true, false><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
+    } else if (fast) {
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hist_pairs_kernel<false, true><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
     } else {
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hist_pairs_kernel<false><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hist_pairs_kernel<false, false><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
     }
     BBK_CHECK_LAUNCH("hist_pairs_kernel");
     return BBK_OK;

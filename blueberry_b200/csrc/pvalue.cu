@@ -292,15 +292,15 @@ __device__ __forceinline__ double tail_finish(double lp, double sum, int upper) 
 }
 
 // Everything bdtrc decides without arithmetic.  Returns 0 when *out is final, 1 for count == 1
-// (closed form), 2 for a tail sum (then 0 < q < 1 and 2 <= c <= S).
-__device__ __forceinline__ int bdtrc_class(int c, long long S, double q, double* out) {
+// (closed form), 2 for a tail sum (then 0 < q < 1 and 2 <= c <= S).  s_cap = min(S, INT_MAX).
+__device__ __forceinline__ int bdtrc_class(int c, int s_cap, bool s_fits, double q, double* out) {
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     *out = qnan;
     if (!(q >= 0.0 && q <= 1.0)) return 0;                       // NaN or outside [0, 1]
-    long long k = (long long)c - 1;
-    if (k < 0) { *out = 1.0; return 0; }
-    if (S < k) return 0;
-    if (k == S) { *out = 0.0; return 0; }
+    if (c <= 0) { *out = 1.0; return 0; }                        // k = c - 1 < 0
+    const int k = c - 1;
+    if (s_fits && k > s_cap) return 0;                           // n < k: NaN
+    if (s_fits && k == s_cap) { *out = 0.0; return 0; }
     if (k == 0) return 1;
     if (q == 0.0) { *out = 0.0; return 0; }
     if (q == 1.0) { *out = 1.0; return 0; }
@@ -327,50 +327,68 @@ struct PvParams {
     long long* p_hist;
 };
 
-struct BiasRow { long long base, nloc, mid0; };
+struct BiasRow { long long base, nloc, mid0; unsigned long long span; };     // span = nloc * R
 
 __device__ __forceinline__ BiasRow bias_row(const PvParams& P, int chrom) {
-    BiasRow r = {0, 0, 0};
+    BiasRow r = {0, 0, 0, 0};
     if (chrom < 0 || chrom >= P.n_chrom) return r;
     r.base = __ldg(&P.chrom_base[chrom]);
     r.nloc = __ldg(&P.chrom_base[chrom + 1]) - r.base;
     r.mid0 = __ldg(&P.mid0[chrom]);
+    r.span = (unsigned long long)r.nloc * (unsigned long long)P.div.R;
     return r;
 }
 
+// biasDic[chr][mid] with default 1.0 (fithic.py:418-425) on a dense per-chromosome grid
+template <bool FAST>
 __device__ __forceinline__ double bias_lookup(const PvParams& P, const BiasRow& row, int mid) {
-    // biasDic[chr][mid] with default 1.0 (fithic.py:418-425) on a dense per-chromosome grid
-    long long off = (long long)mid - row.mid0;
-    if (off < 0 || off >= (1ll << 32)) return 1.0;
-    unsigned idx = fastdiv((unsigned)off, P.div);
-    if ((long long)idx * P.div.R != off || (long long)idx >= row.nloc) return 1.0;
+    const long long off = (long long)mid - row.mid0;
+    if ((unsigned long long)off >= row.span) return 1.0;          // before the table, or past its end
+    unsigned idx;
+    if (FAST) {
+        if (off >= (1ll << 31)) return 1.0;                      // (cannot happen with int32 coordinates >= 0)
+        idx = fastdiv31((unsigned)off, P.div);
+    } else {
+        if (off >= (1ll << 32)) return 1.0;
+        idx = fastdiv((unsigned)off, P.div);
+    }
+    if (idx * P.div.R != (unsigned)off) return 1.0;
     double v = __ldg(&P.bias[row.base + idx]);
     return isnan(v) ? 1.0 : v;
 }
 
-// prior of one record; returns false when the reference does not score it (fithic.py:427)
-template <bool HAS_CHR, bool HAS_BIAS>
+// prior of one record; returns false when the reference does not score it (fithic.py:427).
+// FAST: 0 <= min_dist, max_dist + R < 2^31, so every in-range quantity fits 31 bits.
+template <bool HAS_CHR, bool HAS_BIAS, bool FAST>
 __device__ __forceinline__ bool record_prior(const PvParams& P, int m1, int m2, int c1, int c2, int k0, int L,
                                              const BiasRow& shard_row, double* prior_out) {
-    long long d = (long long)m2 - (long long)m1;                         // fithic.py:416
+    const long long d = (long long)m2 - (long long)m1;                   // fithic.py:416
     if (!(P.min_dist <= d && d <= P.max_dist)) return false;
     // i = min(bisect_left(splineX, clamp(d, min_x, max_x)), L-1) == clamp(ceil((d - splineX[0]) / R), 0, L-1)
-    long long t = d - (long long)k0 * P.R;
     int i = 0;
-    if (t > 0) {
-        long long tt = t + P.R - 1;
-        long long qd = tt < (1ll << 32) ? (long long)fastdiv((unsigned)tt, P.div) : tt / P.R;
-        i = qd > (long long)(L - 1) ? L - 1 : (int)qd;
+    if (FAST) {
+        const int t = (int)d - k0 * (int)P.div.R;                        // k0 * R <= max_dist
+        if (t > 0) {
+            unsigned qd = fastdiv31((unsigned)t + P.div.R - 1u, P.div);
+            i = qd > (unsigned)(L - 1) ? L - 1 : (int)qd;
+        }
+    } else {
+        const long long t = d - (long long)k0 * P.R;
+        if (t > 0) {
+            long long tt = t + P.R - 1;
+            long long qd = tt < (1ll << 32) ? (long long)fastdiv((unsigned)tt, P.div) : tt / P.R;
+            i = qd > (long long)(L - 1) ? L - 1 : (int)qd;
+        }
     }
     double prior = __ldg(&P.spline_y[i]);
     if (HAS_BIAS) {
         double b1, b2;
         if (HAS_CHR) {
-            b1 = bias_lookup(P, bias_row(P, c1), m1);
-            b2 = bias_lookup(P, bias_row(P, c2), m2);
+            b1 = bias_lookup<FAST>(P, bias_row(P, c1), m1);
+            b2 = bias_lookup<FAST>(P, bias_row(P, c2), m2);
         } else {
-            b1 = bias_lookup(P, shard_row, m1);
-            b2 = bias_lookup(P, shard_row, m2);
+            b1 = bias_lookup<FAST>(P, shard_row, m1);
+            b2 = bias_lookup<FAST>(P, shard_row, m2);
         }
         prior = prior * (b1 * b2);                                        // :431
     }
@@ -404,7 +422,7 @@ struct PvShared {
     WarpTile w[PV_WARPS];
 };
 
-template <bool HAS_CHR, bool HAS_BIAS, bool HIST>
+template <bool HAS_CHR, bool HAS_BIAS, bool HIST, bool FAST>
 __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PvShared& sh = *reinterpret_cast<PvShared*>(smem_raw);
@@ -424,9 +442,11 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
     K.c_max = 1e-4 * K.dn;
     K.c5_max = 2e-11 * (K.dn * K.dn) * (K.dn * K.dn);
     WarpTile& W = sh.w[warp];
-    BiasRow shard_row = {0, 0, 0};
+    BiasRow shard_row = {0, 0, 0, 0};
     if (HAS_BIAS && !HAS_CHR) shard_row = bias_row(P, P.shard_chrom);
     unsigned ones = 0, nans = 0;
+    const bool s_fits = S <= 0x7fffffffll;
+    const int s_cap = s_fits ? (int)S : 0x7fffffff;
 
     const long long n_groups = P.n_pairs >> 2;
     const long long groups_per_tile = 32 * WT_ITERS;
@@ -459,8 +479,8 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
             for (int e = 0; e < 4; ++e) {
                 int cls = 0;                               // 0 final, 1 count == 1, 2 tail sum
                 double prior = 0.0, out = __longlong_as_double(0x7ff8000000000000ll);
-                if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, &prior))
-                    cls = bdtrc_class(cs[e], S, prior, &out);
+                if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS, FAST>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, &prior))
+                    cls = bdtrc_class(cs[e], s_cap, s_fits, prior, &out);
                 const int slot = it * 128 + lane * 4 + e;
                 unsigned b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
                 if (cls) {
@@ -571,15 +591,17 @@ __global__ void pvalues_tail_kernel(PvParams P) {
     const long long S = P.fit->S;
     const int k0 = P.fit->k0, L = P.fit->L;
     const bool fit_ok = P.fit->status == BBK_FIT_OK && L > 0;
-    BiasRow shard_row = {0, 0, 0};
+    BiasRow shard_row = {0, 0, 0, 0};
     if (HAS_BIAS && !HAS_CHR) shard_row = bias_row(P, P.shard_chrom);
+    const bool s_fits = S <= 0x7fffffffll;
+    const int s_cap = s_fits ? (int)S : 0x7fffffff;
     int c1 = 0, c2 = 0;
     if (HAS_CHR) { c1 = P.chr1[i]; c2 = P.chr2[i]; }
     double pv = qnan, prior = 0.0;
     const int c = P.count[i];
-    if (fit_ok && record_prior<HAS_CHR, HAS_BIAS>(P, P.mid1[i], P.mid2[i], c1, c2, k0, L, shard_row, &prior)) {
+    if (fit_ok && record_prior<HAS_CHR, HAS_BIAS, false>(P, P.mid1[i], P.mid2[i], c1, c2, k0, L, shard_row, &prior)) {
         double out;
-        int cls = bdtrc_class(c, S, prior, &out);
+        int cls = bdtrc_class(c, s_cap, s_fits, prior, &out);
         if (cls == 0) pv = out;
         else if (cls == 1) pv = -expm1((double)S * log1m(prior));
         else pv = tail_general(c, S, prior);
@@ -608,7 +630,7 @@ int ensure_tables(cudaStream_t st) {
     return BBK_OK;
 }
 
-template <bool HAS_CHR, bool HAS_BIAS, bool HIST>
+template <bool HAS_CHR, bool HAS_BIAS, bool HIST, bool FAST>
 int launch_pv(const PvParams& P, cudaStream_t st) {
     long long groups = P.n_pairs >> 2;
     if (groups > 0) {
@@ -616,8 +638,8 @@ int launch_pv(const PvParams& P, cudaStream_t st) {
         long long grid = (long long)bbk_num_sms() * 3;
         if (need < grid) grid = need;
         size_t smem = sizeof(PvShared) + (HIST ? BBK_PHIST_BINS * sizeof(unsigned) : 0);
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(pvalues_kernel<HAS_CHR, HAS_BIAS, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pvalues_kernel<HAS_CHR, HAS_BIAS, HIST><<<(unsigned)grid, PV_THREADS, smem, st>>>(P);
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(pvalues_kernel<HAS_CHR, HAS_BIAS, HIST, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pvalues_kernel<HAS_CHR, HAS_BIAS, HIST, FAST><<<(unsigned)grid, PV_THREADS, smem, st>>>(P);
         BBK_CHECK_LAUNCH("pvalues_kernel");
     }
     if (P.n_pairs & 3) {
@@ -656,7 +678,10 @@ extern "C" int bbk_pvalues(const int32_t* d_chr1, const int32_t* d_chr2, const i
     int rc = ensure_tables(st);
     if (rc != BBK_OK) return rc;
     bool chr = d_chr1 != nullptr, hist = d_p_hist != nullptr;
-#define BBK_PV_CASE(C, B, H) if (chr == C && has_bias == B && hist == H) return launch_pv<C, B, H>(P, st);
+    // 31-bit fast path: every in-range distance, and distance + resolution, fits 31 bits
+    const bool fast = min_dist >= 0 && max_dist >= 0 && max_dist + resolution < (1ll << 31);
+#define BBK_PV_CASE(C, B, H) if (chr == C && has_bias == B && hist == H) \
+        return fast ? launch_pv<C, B, H, true>(P, st) : launch_pv<C, B, H, false>(P, st);
     BBK_PV_CASE(false, false, false) BBK_PV_CASE(false, false, true)
     BBK_PV_CASE(false, true, false)  BBK_PV_CASE(false, true, true)
     BBK_PV_CASE(true, false, false)  BBK_PV_CASE(true, false, true)
