@@ -158,3 +158,50 @@ def test_full_size_properties_config2():
     first = np.searchsorted(ps_h, ps_h, side="left")
     bh_t = np.maximum.accumulate(np.minimum(ps_h * n_valid / (first + 1), 1))
     assert np.array_equal(qs_h, bh_t) or np.array_equal(qs_h, bh)
+
+
+def test_config1_full_size_against_oracle():
+    """BASELINE config 1 in full (chr21 @ 10 kb, 4,813 bins, no effective distance cap, 11,584,891 records):
+    the device pass against the CPU oracle on identical records (generated on the device, copied to the host)."""
+    import torch
+    from blueberry_b200 import _lib
+    from blueberry_b200.fithic import FitHiC
+    from blueberry_b200 import synth
+    from oracle import fithic_oracle as fo
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    R, nb = 10000, 4813
+    K = nb - 1
+    max_dist = 48_130_000
+    P = int(lib.bbk_synth_n_pairs(nb, K))
+    assert P == 11584891
+    rng = np.random.default_rng(21)
+    bias_host = np.exp(rng.normal(0.0, 0.25, size=nb))
+    bias_dev = torch.from_numpy(bias_host).to(dev)
+    mid1 = torch.empty(P, dtype=torch.int32, device=dev)
+    mid2 = torch.empty(P, dtype=torch.int32, device=dev)
+    count = torch.empty(P, dtype=torch.int32, device=dev)
+    _lib.check(lib.bbk_synth_contacts(nb, K, R, 3000.0, 1.08, 2021, _lib.ptr(bias_dev), _lib.ptr(mid1), _lib.ptr(mid2),
+                                      _lib.ptr(count), _lib.stream_ptr()), "synth")
+    m1, m2, c = mid1.cpu().numpy(), mid2.cpu().numpy(), count.cpu().numpy()
+    fc, fm = synth.make_fragments([nb], R)
+    bc = np.zeros(nb, dtype=np.int32)
+    model = FitHiC("cfg1", R, n_bins=100, max_dist=max_dist)
+    out = model.fit_transform_arrays(None, m1, None, m2, c, fc, fm, bias=(bc, fm, bias_host), q_values=True)
+    bd, _ = fo.read_bias_arrays(bc, fm, bias_host)
+    ref = fo.fithic_arrays(fc, fm, None, m1, None, m2, c, R, 100, model.min_dist, model.max_dist, bias=bd)
+    assert np.array_equal(out.possible, ref.frag.possible)
+    assert np.array_equal(out.observed, ref.contacts.observed)
+    assert out.totals["observedIntraInRangeSum"] == ref.contacts.S < 2 ** 31
+    assert np.array_equal(out.bin_of_key, ref.bin_of_key)
+    assert np.array_equal(out.x, np.array(ref.x)) and np.array_equal(out.y, np.array(ref.y))
+    assert out.spline_x[0] == ref.k0 * R and len(out.spline_y) == len(ref.spline_y)
+    assert np.array_equal(out.spline_y, ref.spline_y)
+    assert np.array_equal(out.keep, ref.keep)
+    k = ref.keep & (ref.p >= 1e-300)
+    err = np.abs(np.log10(out.p[k]) - np.log10(ref.p[k]))
+    print("config 1: S=%d, %d rows kept, max |dlog10 p| vs oracle %.3g (p99 %.3g)" % (ref.contacts.S, int(ref.keep.sum()), err.max(), np.percentile(err, 99)))
+    assert err.max() <= 1e-5
+    assert (out.p[ref.keep & (ref.p < 1e-300)] <= 1e-299).all()
+    qref = fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum()))
+    assert np.array_equal(out.q[out.keep], qref)

@@ -71,3 +71,17 @@ def test_lpt_sharding_and_bands():
         sizes.append(int(np.minimum(2000, nb - 1 - rows).sum() + len(rows)))
     assert sum(sizes) == synth.n_pairs_of(nb, 2000) == 496750251   # BASELINE config 4
     assert max(sizes) / min(sizes) < 1.001
+
+
+def test_extract_contacts_from_map_follows_reference_steps():
+    from blueberry_b200 import utils
+    rng = np.random.default_rng(2)
+    n = 500
+    mid1 = rng.integers(0, 2000, n) * 5000 + 2500
+    mid2 = mid1 + rng.integers(0, 3000, n) * 5000
+    tab = np.column_stack([mid1, mid2, rng.integers(1, 50, n), rng.random(n), np.full(n, -1.0)]).astype(np.float64)
+    out = utils.extract_contacts_from_map(tab, 7, alpha=0.3)
+    keep = (tab[:, 3] <= 0.3) & (tab[:, 1] - tab[:, 0] >= 25000) & (tab[:, 1] - tab[:, 0] <= 10000000)
+    assert out.shape == (int(keep.sum()), 5)
+    assert (out[:, 0] == 7).all()
+    assert np.array_equal(out[:, 1:], tab[keep][:, :4])        # chromosome, mid1, mid2, contactCount, p (utils.py:85-86)
