@@ -537,6 +537,35 @@ __global__ void __launch_bounds__(BH_THREADS) ones_fix_kernel(const double* p, l
         if (p[i] == 1.0) q[i] = qo;
 }
 
+// ---- genome-wide (multi-GPU) variant: select locally, rank the gathered candidates, scatter back -----
+__global__ void export_state_kernel(const BhState* st, unsigned long long* out) {
+    out[0] = st->n_cand; out[1] = st->tau_key; out[2] = (unsigned long long)st->n_tests; out[3] = st->n_ones;
+}
+
+__global__ void import_state_kernel(BhState* st, const unsigned long long* in, unsigned long long n_all) {
+    st->n_cand = n_all; st->tau_key = in[1]; st->n_tests = (long long)in[2]; st->n_ones = in[3];
+    st->n_nan = 0; st->n_valid = 0; st->q_ones = 1.0; st->total_max = 0.0; st->need_ones_fix = 0;
+    for (int p = 0; p < NPASS; ++p) st->skip[p] = 0;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) load_keys_kernel(const unsigned long long* in, long long n, unsigned long long* keys, unsigned* idx) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { keys[i] = in[i]; idx[i] = (unsigned)i; }
+}
+
+__global__ void export_ones_kernel(const BhState* st, double* out) { out[0] = st->q_ones; out[1] = st->need_ones_fix ? 1.0 : 0.0; }
+
+__global__ void __launch_bounds__(BH_THREADS) scatter_q_kernel(const double* src, const unsigned* idx, long long n, double* dst) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[idx[i]] = src[i];
+}
+
+__global__ void __launch_bounds__(BH_THREADS) fix_ones_value_kernel(const double* p, long long m, double* q, double qo) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+        if (p[i] == 1.0) q[i] = qo;
+}
+
 int sort_blocks() { int g = bbk_num_sms() * 4; return g > 1024 ? 1024 : g; }
 
 }  // namespace
@@ -600,5 +629,113 @@ extern "C" int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int
         ones_fix_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st);
         BBK_CHECK_LAUNCH("ones_fix_kernel");
     }
+    return BBK_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Genome-wide q-values across ranks (collective 2), in three local steps around two
+// host-side collectives:
+//   all-reduce(p_hist)  ->  bbk_bh_select  ->  all-gather(candidate keys)  ->  bbk_bh_rank_gathered
+//   ->  bbk_bh_scatter (and bbk_bh_fix_ones in the rare case q(p == 1) < 1)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int bbk_bh_select(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                             uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
+                             void* stream) {
+    BBK_REQUIRE(m >= 0 && m < (1ll << 32), "bbk_bh_select: m must be in [0, 2^32)");
+    BBK_REQUIRE(d_p_hist_global && d_state && d_workspace, "bbk_bh_select: null pointer");
+    BBK_REQUIRE(m == 0 || (d_p && d_q && d_keys && d_idx), "bbk_bh_select: null array");
+    BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_select: workspace must be 256-byte aligned");
+    const int G = sort_blocks();
+    BhLayout L;
+    size_t need = bh_layout(d_workspace, 0, G, &L);
+    if (workspace_bytes < need) { bbk_set_error("bbk_bh_select: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return BBK_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist_global, n_tests);
+    BBK_CHECK_LAUNCH("bh_init_kernel");
+    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1);
+    BBK_CHECK_LAUNCH("bh_threshold_kernel");
+    if (m > 0) {
+        long long want = (m + BH_THREADS - 1) / BH_THREADS;
+        int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+        bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, (unsigned long long*)d_keys, d_idx, 0, nullptr);
+        BBK_CHECK_LAUNCH("bh_compact_kernel");
+    }
+    export_state_kernel<<<1, 1, 0, st>>>(L.st, (unsigned long long*)d_state);
+    BBK_CHECK_LAUNCH("export_state_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, const uint64_t* d_state, double* d_q_all,
+                                    double* d_q_ones, void* d_workspace, size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(n_all >= 0 && n_all < (1ll << 32), "bbk_bh_rank_gathered: n_all must be in [0, 2^32)");
+    BBK_REQUIRE(d_state && d_q_ones && d_workspace, "bbk_bh_rank_gathered: null pointer");
+    BBK_REQUIRE(n_all == 0 || (d_keys_all && d_q_all), "bbk_bh_rank_gathered: null array");
+    BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_rank_gathered: workspace must be 256-byte aligned");
+    const int G = sort_blocks();
+    BhLayout L;
+    size_t need = bh_layout(d_workspace, n_all, G, &L);
+    if (workspace_bytes < need) { bbk_set_error("bbk_bh_rank_gathered: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return BBK_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    import_state_kernel<<<1, 1, 0, st>>>(L.st, (const unsigned long long*)d_state, (unsigned long long)n_all);
+    BBK_CHECK_LAUNCH("import_state_kernel");
+    if (n_all > 0) {
+        long long want = (n_all + BH_THREADS - 1) / BH_THREADS;
+        int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+        load_keys_kernel<<<grid, BH_THREADS, 0, st>>>((const unsigned long long*)d_keys_all, n_all, L.keys[0], L.idx[0]);
+        BBK_CHECK_LAUNCH("load_keys_kernel");
+        for (int pass = 0; pass < NPASS; ++pass) {
+            sort_hist_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
+            BBK_CHECK_LAUNCH("sort_hist_kernel");
+            sort_scan_kernel<<<1, 1024, 0, st>>>(L, pass);
+            BBK_CHECK_LAUNCH("sort_scan_kernel");
+            sort_scatter_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
+            BBK_CHECK_LAUNCH("sort_scatter_kernel");
+        }
+    }
+    ScanParams S;
+    S.L = L; S.p_in = nullptr; S.m = n_all; S.q = d_q_all; S.rank = nullptr; S.positional = 0;
+    scan_partial_kernel<<<G, BH_THREADS, 0, st>>>(S);
+    BBK_CHECK_LAUNCH("scan_partial_kernel");
+    scan_prefix_kernel<<<1, 32, 0, st>>>(S);
+    BBK_CHECK_LAUNCH("scan_prefix_kernel");
+    scan_apply_kernel<<<G, BH_THREADS, 0, st>>>(S);
+    BBK_CHECK_LAUNCH("scan_apply_kernel");
+    export_ones_kernel<<<1, 1, 0, st>>>(L.st, d_q_ones);
+    BBK_CHECK_LAUNCH("export_ones_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_bh_scatter(const double* d_q_src, const uint32_t* d_idx, int64_t n, double* d_q_dst, void* stream) {
+    BBK_REQUIRE(n >= 0, "bbk_bh_scatter: negative size");
+    if (n == 0) return BBK_OK;
+    BBK_REQUIRE(d_q_src && d_idx && d_q_dst, "bbk_bh_scatter: null pointer");
+    long long want = (n + BH_THREADS - 1) / BH_THREADS;
+    int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+    scatter_q_kernel<<<grid, BH_THREADS, 0, (cudaStream_t)stream>>>(d_q_src, d_idx, n, d_q_dst);
+    BBK_CHECK_LAUNCH("scatter_q_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_bh_fix_ones(const double* d_p, int64_t m, double q_ones, double* d_q, void* stream) {
+    BBK_REQUIRE(m >= 0, "bbk_bh_fix_ones: negative size");
+    if (m == 0) return BBK_OK;
+    BBK_REQUIRE(d_p && d_q, "bbk_bh_fix_ones: null pointer");
+    long long want = (m + BH_THREADS - 1) / BH_THREADS;
+    int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+    fix_ones_value_kernel<<<grid, BH_THREADS, 0, (cudaStream_t)stream>>>(d_p, m, d_q, q_ones);
+    BBK_CHECK_LAUNCH("fix_ones_value_kernel");
+    return BBK_OK;
+}
+
+// coarse p histogram alone (what K4 fills when asked): needed before the all-reduce when p did not come from K4
+extern "C" int bbk_p_hist(const double* d_p, int64_t m, int64_t* d_p_hist, void* stream) {
+    BBK_REQUIRE(m >= 0 && d_p_hist, "bbk_p_hist: bad arguments");
+    if (m == 0) return BBK_OK;
+    BBK_REQUIRE(d_p, "bbk_p_hist: null p");
+    long long want = (m + BH_THREADS - 1) / BH_THREADS;
+    int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+    bh_hist_kernel<<<grid, BH_THREADS, 0, (cudaStream_t)stream>>>(d_p, m, (long long*)d_p_hist);
+    BBK_CHECK_LAUNCH("bh_hist_kernel");
     return BBK_OK;
 }

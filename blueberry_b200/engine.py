@@ -164,6 +164,65 @@ class PassEngine(object):
                                            _lib.stream_ptr()), "bbk_bh_qvalues")
         self.launches += (4 if mode == _lib.BH_POSITIONAL else 33 - (1 if use_hist else 0))
 
+    def qvalues_global(self, p, q, n_tests=-1, group=None, hist=None):
+        """Genome-wide Benjamini-Hochberg across the ranks of `group`: every rank passes its shard's p and gets
+        the q-values its rows would have if all shards had been ranked together (the reference's q-value step,
+        utils.py:31-90 -> blueberry.pyx:40).  Two collectives: all-reduce of the 4096-bucket p histogram and
+        all-gather of the candidate keys below the common saturation bucket.  `hist`: this shard's coarse
+        histogram when K4 already filled it (self.p_hist), else it is computed here.  Synchronises the host twice
+        (candidate counts).  With one rank the result equals qvalues() bit for bit."""
+        import torch.distributed as dist
+        lib, dev = self.lib, self.device
+        st = _lib.stream_ptr()
+        m = int(p.numel())
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        if hist is None:
+            hist = torch.zeros(_lib.PHIST_LEN, dtype=torch.int64, device=dev)
+            _lib.check(lib.bbk_p_hist(_lib.ptr(p), m, _lib.ptr(hist), st), "bbk_p_hist")
+        ghist = hist.clone()
+        if world > 1:
+            dist.all_reduce(ghist, op=dist.ReduceOp.SUM, group=group)
+        keys = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+        idx = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        state = torch.zeros(4, dtype=torch.int64, device=dev)
+        ws0 = torch.empty(int(lib.bbk_bh_workspace_bytes(0)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.bbk_bh_select(_lib.ptr(p), m, int(n_tests), _lib.ptr(ghist), _lib.ptr(q), _lib.ptr(keys), _lib.ptr(idx),
+                                     _lib.ptr(state), _lib.ptr(ws0), ws0.numel(), st), "bbk_bh_select")
+        n_local = int(state[0].item())
+        counts = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        if world > 1:
+            all_counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(all_counts, counts, group=group)
+            all_counts = [int(c.item()) for c in all_counts]
+        else:
+            all_counts = [n_local]
+        n_all = sum(all_counts)
+        if world > 1:
+            cap = max(max(all_counts), 1)
+            send = torch.zeros(cap, dtype=torch.int64, device=dev)
+            send[:n_local] = keys[:n_local]
+            recv = [torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(recv, send, group=group)
+            keys_all = torch.cat([r[:c] for r, c in zip(recv, all_counts)]) if n_all else torch.empty(0, dtype=torch.int64, device=dev)
+        else:
+            keys_all = keys[:n_local]
+        q_all = torch.empty(max(n_all, 1), dtype=torch.float64, device=dev)
+        q_ones = torch.zeros(2, dtype=torch.float64, device=dev)
+        need = int(lib.bbk_bh_workspace_bytes(n_all))
+        if self.bh_ws is None or self.bh_ws.numel() < need:
+            self.bh_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _lib.check(lib.bbk_bh_rank_gathered(_lib.ptr(keys_all), n_all, _lib.ptr(state), _lib.ptr(q_all), _lib.ptr(q_ones),
+                                            _lib.ptr(self.bh_ws), self.bh_ws.numel(), st), "bbk_bh_rank_gathered")
+        off = sum(all_counts[:rank])
+        if n_local:
+            _lib.check(lib.bbk_bh_scatter(_lib.ptr(q_all[off:off + n_local]), _lib.ptr(idx), n_local, _lib.ptr(q), st), "bbk_bh_scatter")
+        qo = q_ones.cpu().numpy()
+        if qo[1] != 0.0:
+            _lib.check(lib.bbk_bh_fix_ones(_lib.ptr(p), m, float(qo[0]), _lib.ptr(q), st), "bbk_bh_fix_ones")
+        self.launches += 40
+        return n_all
+
     # ------------------------------------------------------------------ results
     def read_fit(self):
         """Copy the fit status back (synchronises) and raise what the reference would raise."""

@@ -160,6 +160,31 @@ int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int32_t mode, 
                    double* d_q, int64_t* d_rank, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K5, genome-wide across ranks: the reference's q-value step ranks the p-values of ALL chromosomes
+ * together (utils.py:31-90 gathers them per chromosome for blueberry.pyx:40).  Shards live on different
+ * GPUs, so the ranking is split around two host-side collectives (NCCL through torch.distributed):
+ *   bbk_p_hist (or K4's d_p_hist)  ->  all-reduce(sum) of the histogram
+ *   bbk_bh_select        : common saturation bucket from the GLOBAL histogram; writes q = 1.0 / NaN for
+ *                          everything that is not a candidate, candidates' keys / row indices to d_keys /
+ *                          d_idx (capacity m), d_state[4] = {n_candidates, tau_key, N, n_ones}
+ *   all-gather of the candidate keys (order: rank 0's, rank 1's, ...)
+ *   bbk_bh_rank_gathered : sorts the gathered keys, forward running max; d_q_all[i] = q of gathered key i;
+ *                          d_q_ones[2] = {q of the p == 1.0 group, 1.0 if it is below 1}
+ *   bbk_bh_scatter       : d_q_dst[d_idx[i]] = d_q_src[i] for this rank's slice of d_q_all
+ *   bbk_bh_fix_ones      : only when d_q_ones[1] != 0: q = q_ones wherever p == 1.0
+ * Workspaces: bbk_bh_workspace_bytes(0) for select, bbk_bh_workspace_bytes(n_all) for rank_gathered.
+ * With one rank this reproduces bbk_bh_qvalues bit for bit.
+ * ------------------------------------------------------------------------------------------- */
+int bbk_p_hist(const double* d_p, int64_t m, int64_t* d_p_hist, void* stream);
+int bbk_bh_select(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                  uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
+                  void* stream);
+int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, const uint64_t* d_state, double* d_q_all,
+                         double* d_q_ones, void* d_workspace, size_t workspace_bytes, void* stream);
+int bbk_bh_scatter(const double* d_q_src, const uint32_t* d_idx, int64_t n, double* d_q_dst, void* stream);
+int bbk_bh_fix_ones(const double* d_p, int64_t m, double q_ones, double* d_q, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K6  count_band_regions                               replaces blueberry.pyx:77-91
  *     t = #{(i, j) : j < i, low <= regions[i] - regions[j] <= high}
  * d_result: TWO int64 (device): [0] the count, [1] scratch.  Exact for sorted and unsorted input.

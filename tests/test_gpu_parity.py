@@ -343,3 +343,26 @@ def test_error_behaviour_matches_reference(torch_cuda):
     # too few bins for a cubic spline -> scipy's "m > k must hold"
     with pytest.raises(ValueError):
         FitHiC("x", R, n_bins=2, max_dist=200000).fit_transform_arrays(None, c["mid1"], None, c["mid2"], c["count"], fc, fm)
+
+
+@pytest.mark.parametrize("m,frac_ones,n_scale", [(300_001, 0.6, 1.0), (300_001, 0.3, 0.01), (50_000, 0.0, 40.0)])
+def test_bh_genome_wide_path_single_rank_equals_local(m, frac_ones, n_scale, torch_cuda):
+    """The split select / gather / rank / scatter pipeline used across GPUs, run with one rank, against the oracle."""
+    from blueberry_b200.engine import PassEngine
+    from oracle import fithic_oracle as fo
+    torch = torch_cuda
+    rng = np.random.default_rng(m + 3)
+    p = rng.random(m) ** 3
+    p[rng.random(m) < frac_ones] = 1.0
+    p[rng.integers(0, m, m // 10)] = p[rng.integers(0, m, m // 10)]
+    p[rng.integers(0, m, m // 50)] = np.nan
+    n_tests = max(1, int(m * n_scale))
+    eng = PassEngine(1, 100, 0, 10, 16, torch.device("cuda:0"))
+    dp = torch.empty((m + 1) & ~1, dtype=torch.float64, device="cuda:0")[:m].copy_(torch.from_numpy(p))
+    dq = torch.full(((m + 1) & ~1,), -7.0, dtype=torch.float64, device="cuda:0")[:m]
+    eng.qvalues_global(dp, dq, n_tests=n_tests)
+    torch.cuda.synchronize()
+    q = dq.cpu().numpy()
+    valid = ~np.isnan(p)
+    assert np.isnan(q[~valid]).all()
+    assert np.array_equal(q[valid], fo.benjamini_hochberg_correction(p[valid], n_tests))
