@@ -9,7 +9,8 @@ Workload (config.workload): BASELINE config 2 - chr1 at 5 kb (49,851 bins), ever
 (97,750,851 records, zeros kept), ICE-style biases, synthetic counts generated on the device.
 At N > 1 every rank holds one such chromosome-sized shard (weak scaling): the per-distance table and
 totals are all-reduced over NCCL (S, the bins and the spline are genome-wide, identical on all ranks),
-p-values and q-values are per shard (per-chromosome q, as the authors' per-chromosome result files).
+p-values are per shard; q-values are ranked genome-wide across the ranks (all-reduce of the coarse p histogram
++ all-gather of the few candidate keys; `--q-scope shard` ranks per chromosome instead).
 A "step" is one whole pass over the resident records: K1 histogram -> [allreduce] -> K2/K3 fit ->
 K4 p-values (+ coarse p histogram) -> K5 Benjamini-Hochberg q-values.
 """
@@ -216,13 +217,21 @@ def run_ours(args, out_fd):
     q = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
     group = None
 
+    genome_q = world > 1 and args.q_scope == "genome"
+
+    def bh():
+        if genome_q:      # all-reduce of the p histogram + all-gather of the candidate keys (2 host syncs)
+            eng.qvalues_global(p, q, n_tests=-1, group=group, hist=eng.p_hist)
+        else:
+            eng.qvalues(p, q, n_tests=-1, use_hist=True)
+
     def step():
         eng.hist([shard])
         eng.allreduce_stats(group)
         eng.fit()
         eng.p_hist.zero_()
         eng.pvalues(shard, p, with_hist=True)
-        eng.qvalues(p, q, n_tests=-1, use_hist=True)
+        bh()
 
     def barrier():
         if world > 1:
@@ -270,7 +279,7 @@ def run_ours(args, out_fd):
         ev[1].record(); eng.allreduce_stats(group)
         ev[2].record(); eng.fit()
         ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True)
-        ev[4].record(); eng.qvalues(p, q, n_tests=-1, use_hist=True)
+        ev[4].record(); bh()
         ev[5].record()
         torch.cuda.synchronize()
         for i, n in enumerate(names):
@@ -333,7 +342,7 @@ def run_ours(args, out_fd):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg2: chr1@5kb, all pairs within 10 Mb, one chromosome-sized shard per GPU",
                        "pairs_per_gpu": P, "bins_per_gpu": nb, "resolution": R, "max_dist": MAX_DIST, "n_bins": N_BINS,
-                       "biases": True, "q_values": "per shard", "l2": "inputs (%.2f GB/GPU) exceed the 126 MB L2" % (12 * P / 1e9),
+                       "biases": True, "q_values": "genome-wide (histogram all-reduce + candidate all-gather)" if genome_q else "per shard", "l2": "inputs (%.2f GB/GPU) exceed the 126 MB L2" % (12 * P / 1e9),
                        "bytes_per_pair": BYTES_PER_PAIR, "S": int(t[0]), "spline_knots": int(fit.n_knots),
                        "emitted_rows_rank0": kept, "q_le_0.01_rank0": sig},
             "stages_ms": acc,
@@ -373,6 +382,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bins", type=int, default=CHR1_BINS, help="bins of the per-GPU chromosome (default chr1 @ 5 kb)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--q-scope", default="genome", choices=["genome", "shard"],
+                    help="N > 1: rank p-values across all ranks (default) or per shard")
     args = ap.parse_args()
     out_fd = _claim_stdout()
     if args.impl == "reference":
