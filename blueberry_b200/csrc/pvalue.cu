@@ -187,9 +187,10 @@ __device__ __forceinline__ void tail_setup(int c, double q, const TailConst& K, 
     }
 }
 
-// 16 terms of the state's own series.  The per-term work is kept to the recurrence itself: the table bound
-// and the end of the support are checked once per block (the slow variant handles blocks that cross them).
-__device__ __forceinline__ void tail_terms16(TailState& T, const TailConst& K, const double* __restrict__ rcp) {
+// Up to 16 terms of the state's own series; returns true when the support is exhausted (nothing left to add).
+// The per-term work is kept to the recurrence itself: the table bound and the end of the support are checked
+// once per block (the slow variants handle the blocks that cross them, and stop at the end of the support).
+__device__ __forceinline__ bool tail_terms16(TailState& T, const TailConst& K, const double* __restrict__ rcp) {
     if (T.upper) {
         if (T.j + 16 <= RCP_TAB && T.a > 16.0 * T.step) {
             const double* r = rcp + T.j;
@@ -200,37 +201,39 @@ __device__ __forceinline__ void tail_terms16(TailState& T, const TailConst& K, c
                 T.a -= T.step;
             }
             T.j += 16;
-        } else {
-#pragma unroll 1
-            for (int u = 0; u < 16; ++u) {
-                double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
-                T.term *= T.a > 0.0 ? T.a * r : 0.0;
-                T.sum += T.term;
-                T.a -= T.step;
-                T.j += 1;
-            }
+            return false;
         }
-    } else {
-        if (T.j > 16) {
-#pragma unroll 4
-            for (int u = 0; u < 16; ++u) {
-                T.term *= T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e)));
-                T.sum += T.term;
-                T.a -= T.step;
-                T.e -= K.inv_n;
-            }
-            T.j -= 16;
-        } else {
 #pragma unroll 1
-            for (int u = 0; u < 16; ++u) {
-                T.term *= T.j > 0 ? T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e))) : 0.0;
-                T.sum += T.term;
-                T.a -= T.step;
-                T.e -= K.inv_n;
-                T.j -= 1;
-            }
+        for (int u = 0; u < 16; ++u) {
+            if (!(T.a > 0.0)) return true;                       // j > S: pmf is zero from here on
+            double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
+            T.term *= T.a * r;
+            T.sum += T.term;
+            T.a -= T.step;
+            T.j += 1;
         }
+        return false;
     }
+    if (T.j > 16) {
+#pragma unroll 4
+        for (int u = 0; u < 16; ++u) {
+            T.term *= T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e)));
+            T.sum += T.term;
+            T.a -= T.step;
+            T.e -= K.inv_n;
+        }
+        T.j -= 16;
+        return false;
+    }
+#pragma unroll 1
+    while (T.j > 0) {                                            // the last (at most 16) terms down to j = 0
+        T.term *= T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e)));
+        T.sum += T.term;
+        T.a -= T.step;
+        T.e -= K.inv_n;
+        T.j -= 1;
+    }
+    return true;
 }
 
 // 8-lane group: every lane of the group holds the SAME state; each takes 8 consecutive terms per step and
@@ -518,8 +521,8 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
             unsigned rmask = __ballot_sync(0xffffffffu, running);
             while (__popc(rmask) >= 8) {
                 if (running) {
-                    tail_terms16(T, K, sh.rcp);
-                    running = !(T.term < TAIL_EPS * T.sum);
+                    const bool exhausted = tail_terms16(T, K, sh.rcp);
+                    running = !(exhausted || T.term < TAIL_EPS * T.sum);
                 }
                 rmask = __ballot_sync(0xffffffffu, running);
             }
