@@ -50,6 +50,7 @@ SIGNATURES = {
     "bbk_sm_count": (ctypes.c_int, []),
     "bbk_hist_init": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
     "bbk_hist_pairs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "bbk_hist_pairs_excluding": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "bbk_possible_pairs": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "bbk_fit_workspace_bytes": (_sz, [_i32, _i32]),
     "bbk_fit": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

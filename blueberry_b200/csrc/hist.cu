@@ -25,6 +25,8 @@ struct HistParams {
     const int32_t* mid1;
     const int32_t* mid2;
     const int32_t* count;
+    const double* p_excl;     // optional: records with p_excl[i] <= p_thr are skipped (second-pass outlier removal)
+    double p_thr;
     long long n_pairs;
     long long min_dist, max_dist;
     long long lo_excl, hi_incl;   // in range  <=>  lo_excl < d <= hi_incl   (the -1 sentinels folded in)
@@ -98,13 +100,14 @@ struct FastAcc {
     int in_range, intra_cnt, dmin, dmax;
 };
 
-__device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, bool live, FastAcc& a) {
+__device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, bool live_group, unsigned excl, FastAcc& a) {
     const int m1s[4] = {m1.x, m1.y, m1.z, m1.w}, m2s[4] = {m2.x, m2.y, m2.z, m2.w}, cs[4] = {c.x, c.y, c.z, c.w};
     unsigned key[4];
     bool ok[4];
     int csum = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+        const bool live = live_group && !((excl >> e) & 1u);
         const long long d64 = (long long)m2s[e] - (long long)m1s[e];                 // fithic.py:247
         const bool in_range = live && d64 > P.lo_excl && d64 <= P.hi_incl;            // fithic.py:256-257
         const int d = (int)d64;                                                       // valid when in_range
@@ -194,18 +197,27 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
             if (l0) { ax = ld_stream_int4(c1v + g0); ay = ld_stream_int4(c2v + g0); }
             if (l1) { bx = ld_stream_int4(c1v + g1); by = ld_stream_int4(c2v + g1); }
         }
+        // outlier mask: bit e set = record e of the group is excluded
+        unsigned xa = 0, xb = 0;
+        if (P.p_excl) {
+            const double2* pe = reinterpret_cast<const double2*>(P.p_excl);
+            if (l0) { double2 u = ld_stream_double2(pe + 2 * g0), v = ld_stream_double2(pe + 2 * g0 + 1);
+                      xa = (u.x <= P.p_thr ? 1u : 0u) | (u.y <= P.p_thr ? 2u : 0u) | (v.x <= P.p_thr ? 4u : 0u) | (v.y <= P.p_thr ? 8u : 0u); }
+            if (l1) { double2 u = ld_stream_double2(pe + 2 * g1), v = ld_stream_double2(pe + 2 * g1 + 1);
+                      xb = (u.x <= P.p_thr ? 1u : 0u) | (u.y <= P.p_thr ? 2u : 0u) | (v.x <= P.p_thr ? 4u : 0u) | (v.y <= P.p_thr ? 8u : 0u); }
+        }
         if (FAST && !HAS_CHR) {
-            process_group_fast(P, sh, a1, a2, ac, l0, fa);
-            process_group_fast(P, sh, b1, b2, bc, l1, fa);
+            process_group_fast(P, sh, a1, a2, ac, l0, xa, fa);
+            process_group_fast(P, sh, b1, b2, bc, l1, xb, fa);
         } else {
-            process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0, a);
-            process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0, a);
-            process_record<HAS_CHR>(P, sh, a1.z, a2.z, ac.z, ax.z, ay.z, l0, a);
-            process_record<HAS_CHR>(P, sh, a1.w, a2.w, ac.w, ax.w, ay.w, l0, a);
-            process_record<HAS_CHR>(P, sh, b1.x, b2.x, bc.x, bx.x, by.x, l1, a);
-            process_record<HAS_CHR>(P, sh, b1.y, b2.y, bc.y, bx.y, by.y, l1, a);
-            process_record<HAS_CHR>(P, sh, b1.z, b2.z, bc.z, bx.z, by.z, l1, a);
-            process_record<HAS_CHR>(P, sh, b1.w, b2.w, bc.w, bx.w, by.w, l1, a);
+            process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0 && !(xa & 1u), a);
+            process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0 && !(xa & 2u), a);
+            process_record<HAS_CHR>(P, sh, a1.z, a2.z, ac.z, ax.z, ay.z, l0 && !(xa & 4u), a);
+            process_record<HAS_CHR>(P, sh, a1.w, a2.w, ac.w, ax.w, ay.w, l0 && !(xa & 8u), a);
+            process_record<HAS_CHR>(P, sh, b1.x, b2.x, bc.x, bx.x, by.x, l1 && !(xb & 1u), a);
+            process_record<HAS_CHR>(P, sh, b1.y, b2.y, bc.y, bx.y, by.y, l1 && !(xb & 2u), a);
+            process_record<HAS_CHR>(P, sh, b1.z, b2.z, bc.z, bx.z, by.z, l1 && !(xb & 4u), a);
+            process_record<HAS_CHR>(P, sh, b1.w, b2.w, bc.w, bx.w, by.w, l1 && !(xb & 8u), a);
         }
         since_flush += 4 * tile_groups;
         if (since_flush >= FLUSH_PAIRS) {      // uniform across the CTA
@@ -217,6 +229,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         long long i = (n_groups << 2) + threadIdx.x;
         bool live = threadIdx.x < (P.n_pairs & 3);
+        if (live && P.p_excl && P.p_excl[i] <= P.p_thr) live = false;
         int m1 = live ? P.mid1[i] : 0, m2 = live ? P.mid2[i] : 0, c = live ? P.count[i] : 0;
         int c1 = 0, c2 = 0;
         if (HAS_CHR && live) { c1 = P.chr1[i]; c2 = P.chr2[i]; }
@@ -267,20 +280,21 @@ extern "C" int bbk_hist_init(int64_t* d_obs_sum, int32_t nkeys, int64_t* d_total
     return BBK_OK;
 }
 
-extern "C" int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
-                              const int32_t* d_count, int64_t n_pairs, int64_t resolution, int64_t min_dist,
-                              int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream) {
+static int hist_pairs_impl(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                           const int32_t* d_count, const double* d_p_excl, double p_thr, int64_t n_pairs, int64_t resolution,
+                           int64_t min_dist, int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream) {
     BBK_REQUIRE(n_pairs >= 0 && nkeys >= 0, "bbk_hist_pairs: negative size");
     BBK_REQUIRE(resolution > 0 && resolution < (1ll << 32), "bbk_hist_pairs: resolution must be in [1, 2^32)");
     BBK_REQUIRE((d_chr1 == nullptr) == (d_chr2 == nullptr), "bbk_hist_pairs: chr1/chr2 must both be given or both NULL");
     BBK_REQUIRE(d_obs_sum && d_totals, "bbk_hist_pairs: null output");
     if (n_pairs == 0) return BBK_OK;
     BBK_REQUIRE(d_mid1 && d_mid2 && d_count, "bbk_hist_pairs: null input column");
-    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_chr1 | (uintptr_t)d_chr2;
+    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_chr1 | (uintptr_t)d_chr2 | (uintptr_t)d_p_excl;
     BBK_REQUIRE((align & 15) == 0, "bbk_hist_pairs: columns must be 16-byte aligned");
 
     HistParams P;
     P.chr1 = d_chr1; P.chr2 = d_chr2; P.mid1 = d_mid1; P.mid2 = d_mid2; P.count = d_count;
+    P.p_excl = d_p_excl; P.p_thr = p_thr;
     P.n_pairs = n_pairs; P.min_dist = min_dist; P.max_dist = max_dist;
     P.div = make_fastdiv((uint64_t)resolution);
     P.lo_excl = (min_dist == -1) ? (-0x7fffffffffffffffll - 1) : (min_dist > -1 ? min_dist : 0x7fffffffffffffffll);
@@ -317,4 +331,20 @@ extern "C" int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, cons
     }
     BBK_CHECK_LAUNCH("hist_pairs_kernel");
     return BBK_OK;
+}
+
+extern "C" int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                              const int32_t* d_count, int64_t n_pairs, int64_t resolution, int64_t min_dist,
+                              int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream) {
+    return hist_pairs_impl(d_chr1, d_chr2, d_mid1, d_mid2, d_count, nullptr, 0.0, n_pairs, resolution, min_dist, max_dist,
+                           nkeys, d_obs_sum, d_totals, stream);
+}
+
+extern "C" int bbk_hist_pairs_excluding(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                                        const int32_t* d_count, const double* d_p, double p_outlier, int64_t n_pairs,
+                                        int64_t resolution, int64_t min_dist, int64_t max_dist, int32_t nkeys,
+                                        int64_t* d_obs_sum, int64_t* d_totals, void* stream) {
+    BBK_REQUIRE(d_p != nullptr || n_pairs == 0, "bbk_hist_pairs_excluding: null p");
+    return hist_pairs_impl(d_chr1, d_chr2, d_mid1, d_mid2, d_count, d_p, p_outlier, n_pairs, resolution, min_dist, max_dist,
+                           nkeys, d_obs_sum, d_totals, stream);
 }

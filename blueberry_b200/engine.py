@@ -133,6 +133,20 @@ class PassEngine(object):
                                                _lib.ptr(self.obs_sum), _lib.ptr(self.totals), st), "bbk_hist_pairs")
             self.launches += 1
 
+    def hist_excluding(self, shards, p_list, p_outlier):
+        """Second-pass histogram: K1 over the records whose first-pass p is NOT <= p_outlier."""
+        st = _lib.stream_ptr()
+        _lib.check(self.lib.bbk_hist_init(_lib.ptr(self.obs_sum), self.nkeys, _lib.ptr(self.totals), st), "bbk_hist_init")
+        self.launches += 1
+        for sh, p in zip(shards, p_list):
+            if sh.n == 0:
+                continue
+            _lib.check(self.lib.bbk_hist_pairs_excluding(_lib.ptr(sh.chr1), _lib.ptr(sh.chr2), _lib.ptr(sh.mid1), _lib.ptr(sh.mid2),
+                                                         _lib.ptr(sh.count), _lib.ptr(p), float(p_outlier), sh.n, self.R,
+                                                         self.min_dist, self.max_dist, self.nkeys, _lib.ptr(self.obs_sum),
+                                                         _lib.ptr(self.totals), st), "bbk_hist_pairs_excluding")
+            self.launches += 1
+
     def allreduce_stats(self, group=None):
         """Sum the distance table and totals over ranks (integers: order-free, bit-exact)."""
         reduce_distance_stats(self.obs_sum, self.totals, group)
@@ -232,6 +246,23 @@ class PassEngine(object):
         if err is not None:
             raise err[0](err[1])
         return res
+
+    def run_second_pass(self, shards, p_first, p_outs, p_outlier, q_outs=None, n_tests=-1, group=None):
+        """Refit after outlier removal (BASELINE config 4; definition in include/bbk.h): statistics from the records
+        with first-pass p > p_outlier, then ALL records are scored again with the refitted S and spline."""
+        self.hist_excluding(shards, p_first, p_outlier)
+        self.allreduce_stats(group)
+        self.fit()
+        fuse_hist = q_outs is not None and len(shards) == 1
+        if fuse_hist:
+            self.p_hist.zero_()
+        for sh, p in zip(shards, p_outs):
+            if sh.n:
+                self.pvalues(sh, p, with_hist=fuse_hist)
+        if q_outs is not None:
+            for p, q in zip(p_outs, q_outs):
+                if p.numel():
+                    self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist)
 
     def run(self, shards, p_outs, q_outs=None, n_tests=-1, group=None):
         """The whole pass over `shards`; p_outs[i] (float64, len shards[i].n) receives the p-values.

@@ -177,7 +177,7 @@ def _bias_tables(bias_dic, resolution, device, n_chrom_hint=0):
 class PassOutput(object):
     """Everything one pass produces, as numpy arrays / Python scalars."""
     __slots__ = ("p", "q", "keep", "x", "y", "spline_x", "spline_y", "spline_y_raw", "residual", "possible",
-                 "observed", "bin_of_key", "totals", "frag", "fit", "gpu_launches")
+                 "observed", "bin_of_key", "totals", "frag", "fit", "gpu_launches", "p_first")
 
 
 def _pad16(n):
@@ -185,7 +185,7 @@ def _pad16(n):
 
 
 def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count,
-              bias_dic=None, want_q=False, n_tests=None, keep_device=False):
+              bias_dic=None, want_q=False, n_tests=None, keep_device=False, refit=False):
     dev = _device()
     info = _frag_info(frag_chrom, frag_mid, resolution)
     eng = PassEngine(resolution, n_bins, min_dist, max_dist, info.nkeys, dev)
@@ -208,7 +208,20 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
     n = shard.n
     p = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n]
     q = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n] if want_q else None
-    eng.run([shard], [p], [q] if want_q else None, n_tests=-1 if n_tests is None else int(n_tests))
+    nt = -1 if n_tests is None else int(n_tests)
+    first = None
+    if not refit:
+        eng.run([shard], [p], [q] if want_q else None, n_tests=nt)
+    else:
+        # pass 1 without q-values, then the refit on the non-outliers scores every record again
+        eng.run([shard], [p], None)
+        eng.read_fit()
+        possible_host = eng.possible.cpu().numpy()
+        in_rng = sum(int(v) for k, v in enumerate(possible_host) if in_range_check(k * int(resolution), min_dist, max_dist))
+        if in_rng <= 0:
+            raise ZeroDivisionError("float division by zero (possibleIntraInRangeCount == 0)")
+        first = p.clone()
+        eng.run_second_pass([shard], [first], [p], 1.0 / in_rng, [q] if want_q else None, n_tests=nt)
     fit = eng.read_fit()                                        # raises what the reference would raise
 
     out = PassOutput()
@@ -238,6 +251,7 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
                                              if in_range_check(k * int(resolution), min_dist, max_dist))),
     }
     out.gpu_launches = eng.launches
+    out.p_first = first.cpu().numpy() if first is not None else None
     return out
 
 
@@ -258,19 +272,23 @@ class FitHiC(object):
                interactions, fragments, biases, verbose)
 
     def fit_transform_arrays(self, chr1, mid1, chr2, mid2, count, frag_chrom, frag_mid, bias=None,
-                             q_values=False, n_tests=None):
+                             q_values=False, n_tests=None, refit=False):
         """The same pass on in-memory records.
 
         chr1/chr2: integer chromosome ids per record (None: all records on one chromosome).
         bias: None or (bias_chrom, bias_mid, bias_value) arrays in file order (fithic.py:143).
         q_values: also compute Benjamini-Hochberg q-values over the emitted rows (the reference
         writes the literal -1, fithic.py:435); n_tests defaults to the number of emitted rows.
+        refit: second pass (BASELINE config 4).  The reference accepts n_passes and never uses it
+        (fithic.py:121-133); with refit=True the rows of pass 1 with p <= 1/possibleIntraInRangeCount are
+        left out of the statistics, the bins and spline are refitted with the reference's own stage
+        semantics and every record is scored again (p_first keeps the pass-1 values).
         """
         bias_dic = None
         if bias is not None:
             bias_dic = _bias_dict_from_arrays(*bias)
         return _run_pass(self.resolution, self.n_bins, self.min_dist, self.max_dist, frag_chrom, frag_mid,
-                         chr1, mid1, chr2, mid2, count, bias_dic, want_q=q_values, n_tests=n_tests)
+                         chr1, mid1, chr2, mid2, count, bias_dic, want_q=q_values, n_tests=n_tests, refit=refit)
 
 
 def _bias_dict_from_arrays(bias_chrom, bias_mid, bias_val):

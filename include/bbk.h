@@ -67,6 +67,16 @@ int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* 
                    const int32_t* d_count, int64_t n_pairs, int64_t resolution, int64_t min_dist,
                    int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream);
 
+/* Second pass (BASELINE config 4): the same histogram over the records that are NOT first-pass outliers,
+ * i.e. skipping record i when d_p[i] <= p_outlier (NaN never compares true: unscored rows stay in).  The
+ * reference has no second pass (n_passes is ignored, fithic.py:121-133); the definition follows SURVEY.md
+ * section 8c: outliers are rows with p <= 1 / possibleIntraInRangeCount, the refit uses the reference's own
+ * read_interactions / calculate_probabilities / fit_spline on the filtered records and scores ALL records. */
+int bbk_hist_pairs_excluding(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                             const int32_t* d_count, const double* d_p, double p_outlier, int64_t n_pairs,
+                             int64_t resolution, int64_t min_dist, int64_t max_dist, int32_t nkeys,
+                             int64_t* d_obs_sum, int64_t* d_totals, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2a possible pairs per distance                      replaces generate_FragPairs, fithic.py:302-311
  * d_n_frags[c] = number of distinct fragment mids of chromosome c, d_max_frag[c] = max(mid) - R/2.

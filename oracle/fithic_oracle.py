@@ -318,3 +318,34 @@ def fithic_arrays(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, resolutio
     res.p, res.scored, res.keep = score_pairs(mid1, mid2, count, res.contacts.S, res.k0, res.spline_y,
                                               resolution, min_dist, max_dist, b1, b2)
     return res
+
+
+def fithic_two_pass_arrays(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, resolution,
+                           n_bins=100, min_dist=0, max_dist=10000000, bias=None):
+    """Second pass (BASELINE config 4).  The reference has no pass-2 code (n_passes is ignored,
+    fithic.py:121-133); SURVEY.md section 8c composes it from the reference's own functions:
+    outliers = rows of pass 1 with p <= 1 / possibleIntraInRangeCount (fithic.py:320-322); the statistics
+    (read_interactions, calculate_probabilities, the spline) are recomputed on the records that are not
+    outliers, and fit_spline then scores ALL records with the refitted S and spline.
+    Returns (pass1 PassResult, pass2 PassResult, outlier mask, threshold)."""
+    r1 = fithic_arrays(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, resolution, n_bins, min_dist, max_dist, bias)
+    thr = 1.0 / r1.frag.possible_intra_in_range
+    with np.errstate(invalid="ignore"):
+        outlier = r1.keep & (r1.p <= thr)
+    sel = ~outlier
+    sub = lambda a: None if a is None else np.asarray(a)[sel]
+    r2 = PassResult()
+    r2.frag = r1.frag
+    nkeys = len(r1.frag.possible)
+    r2.contacts = read_interactions(nkeys, resolution, sub(chr1), sub(mid1), sub(chr2), sub(mid2), sub(count), min_dist, max_dist)
+    x, y, _, r2.bin_of_key = calculate_probabilities(r2.frag.possible, r2.contacts.observed, r2.contacts.S, n_bins,
+                                                     resolution, min_dist, max_dist)
+    r2.x, r2.y = x, y
+    r2.k0, r2.spline_y, r2.residual, r2.spline_y_raw, _ = fit_spline_tables(x, y, nkeys, resolution)
+    b1 = b2 = None
+    if bias:
+        b1 = bias_lookup(bias, chr1, mid1)
+        b2 = bias_lookup(bias, chr2, mid2)
+    r2.p, r2.scored, r2.keep = score_pairs(mid1, mid2, count, r2.contacts.S, r2.k0, r2.spline_y, resolution,
+                                           min_dist, max_dist, b1, b2)
+    return r1, r2, outlier, thr

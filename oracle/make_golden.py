@@ -99,6 +99,25 @@ def _bh_case():
     print("bh_band", {k: v.shape for k, v in cases.items() if k.startswith("q_py")}, cases["band_sorted"], cases["band_shuffled"])
 
 
+def _pass2_case():
+    """Second pass on the inputs of pass_bias_dense (outputs only; inputs are in pass_bias_dense.npz)."""
+    from oracle import fithic_oracle as fo
+    g = np.load(os.path.join(GOLDEN, "pass_bias_dense.npz"))
+    R = int(g["resolution"])
+    bd, _ = fo.read_bias_arrays(g["bias_chrom"], g["bias_mid"], g["bias_val"])
+    o = fo.fithic_arrays(g["frag_chrom"], g["frag_mid"], g["chr1"], g["mid1"], g["chr2"], g["mid2"], g["count"], R,
+                         int(g["n_bins"]), int(g["ref_min_dist"]), int(g["ref_max_dist"]), bias=bd)
+    ref2 = run_reference.run_reference_two_pass(g["frag_chrom"], g["frag_mid"], g["chr1"], g["mid1"], g["chr2"], g["mid2"], g["count"],
+                                                R, o.keep, n_bins=int(g["n_bins"]), min_dist=int(g["min_dist_arg"]),
+                                                max_dist=int(g["max_dist_arg"]), bias=(g["bias_chrom"], g["bias_mid"], g["bias_val"]))
+    out = ref2["out"]
+    np.savez_compressed(os.path.join(GOLDEN, "pass2_bias_dense.npz"), threshold=ref2["threshold"], n_outliers=ref2["n_outliers"],
+                        outlier_idx=ref2["outlier_idx"], ref2_observed=ref2["observed"], ref2_S=np.int64(ref2["S"]), ref2_x=ref2["x"],
+                        ref2_y=ref2["y"], ref2_spline_x=ref2["spline_x"], ref2_spline_y=ref2["spline_y"], ref2_out_mid1=out["mid1"],
+                        ref2_out_mid2=out["mid2"], ref2_out_count=out["count"], ref2_out_p=out["p"])
+    print("pass2_bias_dense outliers", ref2["n_outliers"], "S", ref2["S"], "rows", len(out["p"]))
+
+
 def main():
     if not ref_loader.reference_available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -111,6 +130,7 @@ def main():
     # min_dist > 0, bias file with a duplicate and a missing locus, n_bins != 100
     _pass_case("pass_messy", [300, 220, 90], 5000, 1000000, 20000, 60.0, 7, True, True, n_bins=40, messy=True)
     _bh_case()
+    _pass2_case()
 
 
 if __name__ == "__main__":

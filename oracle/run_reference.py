@@ -96,3 +96,44 @@ def run_reference_pass(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, reso
         "out": out,
         "ref_module": ref,
     }
+
+
+def run_reference_two_pass(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, resolution, keep_mask,
+                           n_bins=100, min_dist=-1, max_dist=-1, bias=None):
+    """Pass 2 composed from the reference's own functions: pass 1, drop the rows with
+    p <= 1/possibleIntraInRangeCount from the interactions file, recompute the statistics on the filtered
+    file in a FRESH module, then let fit_spline score the FULL file.  keep_mask: which input rows pass 1
+    emitted (validated against the oracle) - needed to map output rows back to input rows."""
+    import tempfile
+    ref1 = run_reference_pass(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, resolution, n_bins, min_dist, max_dist, bias)
+    thr = 1.0 / ref1["possible_intra_in_range"]
+    idx_kept = np.nonzero(keep_mask)[0]
+    assert len(idx_kept) == len(ref1["out"]["p"])
+    outlier_idx = idx_kept[ref1["out"]["p"] <= thr]
+    sel = np.ones(len(count), dtype=bool)
+    sel[outlier_idx] = False
+    ref = ref_loader.load_reference_fithic()
+    tmp = tempfile.mkdtemp(prefix="bbk_ref2_")
+    full = os.path.join(tmp, "interactions_full.gz")
+    filt = os.path.join(tmp, "interactions_filtered.gz")
+    frags = os.path.join(tmp, "fragments.gz")
+    write_interactions(full, chr1, mid1, chr2, mid2, count)
+    write_interactions(filt, np.asarray(chr1)[sel], np.asarray(mid1)[sel], np.asarray(chr2)[sel], np.asarray(mid2)[sel], np.asarray(count)[sel])
+    write_fragments(frags, frag_chrom, frag_mid)
+    bias_dic = {}
+    if bias is not None:
+        bf = os.path.join(tmp, "biases.gz")
+        write_biases(bf, *bias)
+        bias_dic = ref.read_bias_file(bf, False)
+    lo, hi = ref1["min_dist"], ref1["max_dist"]
+    main = ref.generate_FragPairs(frags, resolution, lo, hi, False)
+    main = ref.read_interactions(main, filt, lo, hi, False)
+    x, y, yerr = ref.calculate_probabilities(main, n_bins, resolution, lo, hi, os.path.join(tmp, "lib.fithic_pass2"), False)
+    spline_x, new_y, residual = ref.fit_spline(main, x, y, yerr, full, os.path.join(tmp, "lib.spline_pass2"), bias_dic,
+                                               resolution, lo, hi, False)
+    out = parse_significances(os.path.join(tmp, "lib.spline_pass2.res%d.significances.txt.gz" % resolution))
+    keys = sorted(main)
+    return {"threshold": thr, "n_outliers": int(len(outlier_idx)), "outlier_idx": outlier_idx,
+            "observed": np.array([main[k][1] for k in keys], np.int64), "S": int(ref.observedIntraInRangeSum),
+            "x": np.array(x), "y": np.array(y), "spline_x": np.array(spline_x, np.int64), "spline_y": np.array(new_y),
+            "out": out}

@@ -366,3 +366,25 @@ def test_bh_genome_wide_path_single_rank_equals_local(m, frac_ones, n_scale, tor
     valid = ~np.isnan(p)
     assert np.isnan(q[~valid]).all()
     assert np.array_equal(q[valid], fo.benjamini_hochberg_correction(p[valid], n_tests))
+
+
+def test_second_pass_against_composed_reference_golden(torch_cuda):
+    """BASELINE config 4's refit after outlier removal, against the golden output of the reference's own functions
+    composed as in SURVEY 8c (tests/golden/pass2_bias_dense.npz)."""
+    from blueberry_b200.fithic import FitHiC
+    g = load_golden("pass_bias_dense")
+    g2 = load_golden("pass2_bias_dense")
+    model = FitHiC("unused", int(g["resolution"]), n_bins=int(g["n_bins"]), max_dist=int(g["max_dist_arg"]), min_dist=int(g["min_dist_arg"]))
+    out = model.fit_transform_arrays(g["chr1"], g["mid1"], g["chr2"], g["mid2"], g["count"], g["frag_chrom"], g["frag_mid"],
+                                     bias=_bias_arg(g), refit=True, q_values=True)
+    assert np.array_equal(out.observed, g2["ref2_observed"])
+    assert out.totals["observedIntraInRangeSum"] == int(g2["ref2_S"])
+    with np.errstate(invalid="ignore"):
+        assert int((out.p_first <= float(g2["threshold"])).sum()) == int(g2["n_outliers"])
+    assert np.array_equal(out.x, g2["ref2_x"]) and np.array_equal(out.y, g2["ref2_y"])
+    assert np.array_equal(out.spline_x, g2["ref2_spline_x"])
+    assert np.array_equal(out.spline_y, g2["ref2_spline_y"])
+    keep = out.keep
+    assert np.array_equal(g["mid1"][keep], g2["ref2_out_mid1"]) and np.array_equal(g["count"][keep], g2["ref2_out_count"])
+    ok, nbad = log10_close(out.p[keep], g2["ref2_out_p"], P_TOL_GOLDEN)
+    assert ok, nbad

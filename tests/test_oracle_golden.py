@@ -67,3 +67,21 @@ def test_bh_is_forward_running_max_not_textbook():
     textbook = np.minimum.accumulate((np.sort(p) * 1000 / np.arange(1, 1001))[::-1])[::-1]
     tb = np.empty(1000); tb[order] = np.minimum(textbook, 1)
     assert (q != tb).sum() > 100
+
+
+def test_two_pass_oracle_matches_composed_reference():
+    """Pass 2 has no reference code; the oracle follows the composition of reference functions of SURVEY 8c,
+    and must reproduce what those functions produced when run for real (tests/golden/pass2_bias_dense.npz)."""
+    g = load_golden("pass_bias_dense")
+    g2 = load_golden("pass2_bias_dense")
+    R = int(g["resolution"])
+    r1, r2, outlier, thr = fo.fithic_two_pass_arrays(g["frag_chrom"], g["frag_mid"], g["chr1"], g["mid1"], g["chr2"], g["mid2"],
+                                                     g["count"], R, int(g["n_bins"]), int(g["ref_min_dist"]), int(g["ref_max_dist"]),
+                                                     bias=golden_bias_dict(g))
+    assert thr == float(g2["threshold"]) and int(outlier.sum()) == int(g2["n_outliers"])
+    assert np.array_equal(np.nonzero(outlier)[0], g2["outlier_idx"])
+    assert np.array_equal(r2.contacts.observed, g2["ref2_observed"]) and r2.contacts.S == int(g2["ref2_S"])
+    assert np.array_equal(np.array(r2.x), g2["ref2_x"]) and np.array_equal(np.array(r2.y), g2["ref2_y"])
+    assert np.array_equal(r2.spline_y, g2["ref2_spline_y"])
+    assert np.array_equal(g["mid1"][r2.keep], g2["ref2_out_mid1"])
+    assert np.array_equal(r2.p[r2.keep], g2["ref2_out_p"])
