@@ -287,8 +287,11 @@ def run_ours(args, out_fd):
     fit_diag = eng.read_fit()          # phase cycles of the last instrumented fit (before the e2e section)
     peak, peak_src = _peaks()
     k4_gbs = K4_BYTES_PER_PAIR * P / (acc["pvalues"] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one K4 launch on this exact workload, from the ncu --set full
+    # capture summarised in profiles/r01_ncu_full_k1_k4.txt (1.1736 GB read + 0.7399 GB written)
+    k4_traffic = 1.9135e9 if (nb == CHR1_BINS and world == 1) else None
     roofline = {"bound": "hbm", "kernel": "pvalues_kernel (K4)", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
-                "frac": k4_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": k4_gbs / peak, "traffic": k4_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * P,
                 "whole_pass_frac": BYTES_PER_PAIR * P / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stage_gbs": {"hist": 12 * P / (acc["hist"] * 1e-3) / 1e9, "pvalues": k4_gbs,
