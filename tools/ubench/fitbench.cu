@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
+#define BBK_QR_PROFILE 1
 #include "../../blueberry_b200/csrc/fit_coop.h"
 
 __global__ void __launch_bounds__(128, 1) k(const double* x, const double* y, int m, double s, double* ws, BbkCoopState* out, long long* cyc) {
@@ -45,6 +46,7 @@ int main(int argc, char** argv) {
         printf("m=%d n=%d ier=%d total %lld cyc | fits %lld piters %lld | rows+QR %lld backsub %lld resid+knots %lld sweep %lld f(p) %lld | per-fit QR %lld\n",
                m, st.n, st.ier, c, st.diag[0], st.diag[1], st.diag[2], st.diag[3], st.diag[4], st.diag[5], st.diag[6],
                st.diag[0] ? st.diag[2] / st.diag[0] : 0);
+        printf("   QR loop only: %lld cycles over %lld half-steps (+f(p) mixed in diag6) -> %.0f cycles per half-step\n", st.diag[7], st.diag[6], (double)st.diag[7] / (double)(st.diag[1] / 1000000)); printf("   half-steps %lld ; warp0 work on odd half-steps (phase A) %lld, on even (phase B) %lld, barrier wait %lld (these are mixed into backsub/resid/sweep slots)\n", st.diag[1] / 1000000, st.diag[3], st.diag[4], st.diag[5]);
     }
     return 0;
 }
