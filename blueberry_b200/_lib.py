@@ -65,6 +65,7 @@ SIGNATURES = {
     "bbk_bh_rank_gathered": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bbk_bh_scatter": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "bbk_bh_fix_ones": (ctypes.c_int, [_vp, _i64, _f64, _vp, _vp]),
+    "bbk_bh_fix_ones_dev": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "bbk_count_band": (ctypes.c_int, [_vp, _i64, _f64, _f64, _vp, _vp]),
     "bbk_synth_n_pairs": (_i64, [_i64, _i64]),
     "bbk_synth_contacts": (ctypes.c_int, [_i64, _i64, _i64, _f64, _f64, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),

@@ -560,6 +560,14 @@ __global__ void __launch_bounds__(BH_THREADS) scatter_q_kernel(const double* src
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[idx[i]] = src[i];
 }
 
+__global__ void __launch_bounds__(BH_THREADS) fix_ones_dev_kernel(const double* p, long long m, double* q, const double* q_ones) {
+    if (q_ones[1] == 0.0) return;                           // q(p == 1) is 1.0: nothing to do
+    const double qo = q_ones[0];
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+        if (p[i] == 1.0) q[i] = qo;
+}
+
 __global__ void __launch_bounds__(BH_THREADS) fix_ones_value_kernel(const double* p, long long m, double* q, double qo) {
     long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
@@ -737,5 +745,16 @@ extern "C" int bbk_p_hist(const double* d_p, int64_t m, int64_t* d_p_hist, void*
     int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
     bh_hist_kernel<<<grid, BH_THREADS, 0, (cudaStream_t)stream>>>(d_p, m, (long long*)d_p_hist);
     BBK_CHECK_LAUNCH("bh_hist_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_bh_fix_ones_dev(const double* d_p, int64_t m, const double* d_q_ones, double* d_q, void* stream) {
+    BBK_REQUIRE(m >= 0, "bbk_bh_fix_ones_dev: negative size");
+    if (m == 0) return BBK_OK;
+    BBK_REQUIRE(d_p && d_q && d_q_ones, "bbk_bh_fix_ones_dev: null pointer");
+    long long want = (m + BH_THREADS - 1) / BH_THREADS;
+    int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+    fix_ones_dev_kernel<<<grid, BH_THREADS, 0, (cudaStream_t)stream>>>(d_p, m, d_q, d_q_ones);
+    BBK_CHECK_LAUNCH("fix_ones_dev_kernel");
     return BBK_OK;
 }

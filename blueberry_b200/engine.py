@@ -23,16 +23,16 @@ def reduce_distance_stats(obs_sum, totals, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    dist.all_reduce(obs_sum, op=dist.ReduceOp.SUM, group=group)
-    sums = totals[:6].clone()
-    mn = totals[6:7].clone()
-    mx = totals[7:8].clone()
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    totals[:6] = sums
-    totals[6:7] = mn
-    totals[7:8] = mx
+    # two collectives: one SUM over [obs_sum | the six sum-type totals], one MAX over [-min, max]
+    nk = obs_sum.numel()
+    pack = torch.cat([obs_sum, totals[:6]])
+    ext = torch.stack([-totals[6], totals[7]])
+    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+    obs_sum.copy_(pack[:nk])
+    totals[:6] = pack[nk:]
+    totals[6] = -ext[0]
+    totals[7] = ext[1]
 
 
 class Shard(object):
@@ -203,22 +203,22 @@ class PassEngine(object):
         ws0 = torch.empty(int(lib.bbk_bh_workspace_bytes(0)), dtype=torch.uint8, device=dev)
         _lib.check(lib.bbk_bh_select(_lib.ptr(p), m, int(n_tests), _lib.ptr(ghist), _lib.ptr(q), _lib.ptr(keys), _lib.ptr(idx),
                                      _lib.ptr(state), _lib.ptr(ws0), ws0.numel(), st), "bbk_bh_select")
-        n_local = int(state[0].item())
-        counts = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        # candidate counts of all ranks with ONE host synchronisation
         if world > 1:
-            all_counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(all_counts, counts, group=group)
-            all_counts = [int(c.item()) for c in all_counts]
+            counts_dev = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts_dev, state[0:1].contiguous(), group=group)
+            all_counts = counts_dev.cpu().tolist()
         else:
-            all_counts = [n_local]
-        n_all = sum(all_counts)
+            all_counts = [int(state[0].item())]
+        n_local = int(all_counts[rank])
+        n_all = int(sum(all_counts))
         if world > 1:
             cap = max(max(all_counts), 1)
-            send = torch.zeros(cap, dtype=torch.int64, device=dev)
-            send[:n_local] = keys[:n_local]
-            recv = [torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(recv, send, group=group)
-            keys_all = torch.cat([r[:c] for r, c in zip(recv, all_counts)]) if n_all else torch.empty(0, dtype=torch.int64, device=dev)
+            recv = torch.empty(world * cap, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(recv, keys[:cap].contiguous() if cap <= keys.numel() else
+                                        torch.cat([keys, torch.zeros(cap - keys.numel(), dtype=torch.int64, device=dev)]), group=group)
+            keys_all = torch.cat([recv[r * cap:r * cap + c] for r, c in enumerate(all_counts)]) if n_all else \
+                torch.empty(0, dtype=torch.int64, device=dev)
         else:
             keys_all = keys[:n_local]
         q_all = torch.empty(max(n_all, 1), dtype=torch.float64, device=dev)
@@ -228,12 +228,11 @@ class PassEngine(object):
             self.bh_ws = torch.empty(need, dtype=torch.uint8, device=dev)
         _lib.check(lib.bbk_bh_rank_gathered(_lib.ptr(keys_all), n_all, _lib.ptr(state), _lib.ptr(q_all), _lib.ptr(q_ones),
                                             _lib.ptr(self.bh_ws), self.bh_ws.numel(), st), "bbk_bh_rank_gathered")
-        off = sum(all_counts[:rank])
+        off = int(sum(all_counts[:rank]))
         if n_local:
             _lib.check(lib.bbk_bh_scatter(_lib.ptr(q_all[off:off + n_local]), _lib.ptr(idx), n_local, _lib.ptr(q), st), "bbk_bh_scatter")
-        qo = q_ones.cpu().numpy()
-        if qo[1] != 0.0:
-            _lib.check(lib.bbk_bh_fix_ones(_lib.ptr(p), m, float(qo[0]), _lib.ptr(q), st), "bbk_bh_fix_ones")
+        # rare: q of the p == 1.0 group below 1 - decided and applied on the device (no host round trip)
+        _lib.check(lib.bbk_bh_fix_ones_dev(_lib.ptr(p), m, _lib.ptr(q_ones), _lib.ptr(q), st), "bbk_bh_fix_ones_dev")
         self.launches += 40
         return n_all
 

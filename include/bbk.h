@@ -193,6 +193,8 @@ int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, const uint64
                          double* d_q_ones, void* d_workspace, size_t workspace_bytes, void* stream);
 int bbk_bh_scatter(const double* d_q_src, const uint32_t* d_idx, int64_t n, double* d_q_dst, void* stream);
 int bbk_bh_fix_ones(const double* d_p, int64_t m, double q_ones, double* d_q, void* stream);
+/* the same, decided on the device from d_q_ones[2] of bbk_bh_rank_gathered (no host round trip) */
+int bbk_bh_fix_ones_dev(const double* d_p, int64_t m, const double* d_q_ones, double* d_q, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6  count_band_regions                               replaces blueberry.pyx:77-91
