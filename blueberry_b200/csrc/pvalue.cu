@@ -364,7 +364,7 @@ __device__ __forceinline__ double bias_lookup(const PvParams& P, const BiasRow& 
 // FAST: 0 <= min_dist, max_dist + R < 2^31, so every in-range quantity fits 31 bits.
 template <bool HAS_CHR, bool HAS_BIAS, bool FAST>
 __device__ __forceinline__ bool record_prior(const PvParams& P, int m1, int m2, int c1, int c2, int k0, int L,
-                                             const BiasRow& shard_row, double* prior_out) {
+                                             const BiasRow& shard_row, bool have_b1, double b1_pre, double* prior_out) {
     const long long d = (long long)m2 - (long long)m1;                   // fithic.py:416
     if (!(P.min_dist <= d && d <= P.max_dist)) return false;
     // i = min(bisect_left(splineX, clamp(d, min_x, max_x)), L-1) == clamp(ceil((d - splineX[0]) / R), 0, L-1)
@@ -390,7 +390,7 @@ __device__ __forceinline__ bool record_prior(const PvParams& P, int m1, int m2, 
             b1 = bias_lookup<FAST>(P, bias_row(P, c1), m1);
             b2 = bias_lookup<FAST>(P, bias_row(P, c2), m2);
         } else {
-            b1 = bias_lookup<FAST>(P, shard_row, m1);
+            b1 = have_b1 ? b1_pre : bias_lookup<FAST>(P, shard_row, m1);
             b2 = bias_lookup<FAST>(P, shard_row, m2);
         }
         prior = prior * (b1 * b2);                                        // :431
@@ -478,11 +478,19 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
             }
             const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
             const int c1s[4] = {x1.x, x1.y, x1.z, x1.w}, c2s[4] = {x2.x, x2.y, x2.z, x2.w};
+            // records that are neighbours in memory usually share their first locus (row-major input): one bias
+            // gather serves the group then (any other order just takes the per-record path)
+            bool same1 = false;
+            double b1g = 1.0;
+            if (HAS_BIAS && !HAS_CHR) {
+                same1 = (a1.x == a1.y) & (a1.y == a1.z) & (a1.z == a1.w);
+                if (same1 && live && fit_ok) b1g = bias_lookup<FAST>(P, shard_row, a1.x);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int cls = 0;                               // 0 final, 1 count == 1, 2 tail sum
                 double prior = 0.0, out = __longlong_as_double(0x7ff8000000000000ll);
-                if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS, FAST>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, &prior))
+                if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS, FAST>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, same1, b1g, &prior))
                     cls = bdtrc_class(cs[e], s_cap, s_fits, prior, &out);
                 const int slot = it * 128 + lane * 4 + e;
                 unsigned b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
@@ -602,7 +610,7 @@ __global__ void pvalues_tail_kernel(PvParams P) {
     if (HAS_CHR) { c1 = P.chr1[i]; c2 = P.chr2[i]; }
     double pv = qnan, prior = 0.0;
     const int c = P.count[i];
-    if (fit_ok && record_prior<HAS_CHR, HAS_BIAS, false>(P, P.mid1[i], P.mid2[i], c1, c2, k0, L, shard_row, &prior)) {
+    if (fit_ok && record_prior<HAS_CHR, HAS_BIAS, false>(P, P.mid1[i], P.mid2[i], c1, c2, k0, L, shard_row, false, 1.0, &prior)) {
         double out;
         int cls = bdtrc_class(c, s_cap, s_fits, prior, &out);
         if (cls == 0) pv = out;
