@@ -282,3 +282,69 @@ class PassEngine(object):
             for p, q in zip(p_outs, q_outs):
                 if p.numel():
                     self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist)
+
+
+class HostPipeline(object):
+    """Successive single-shard passes (one library each) streamed from pinned host memory.
+
+    A pass cannot start scoring before all of its records are on the device (S and the spline need the whole
+    distance table, fithic.py:110-133), so inside one pass the inbound and the outbound copies never overlap.
+    Across passes they do: while library k is being scored and its p/q travel back, library k+1 is already
+    arriving.  `slots` device copies of the record columns and of p/q make that legal; three streams (in, run,
+    out) and per-slot events order them.  Nothing here synchronises the host; call drain() (or wait on the event
+    submit() returns) before reading the host outputs.
+    """
+
+    class _Slot(object):
+        pass
+
+    def __init__(self, engine, max_pairs, chrom=0, slots=2):
+        self.eng = engine
+        self.chrom = int(chrom)
+        self.max_pairs = int(max_pairs)
+        dev = engine.device
+        padded = (self.max_pairs + 1) & ~1
+        self.slots = []
+        for _ in range(int(slots)):
+            s = HostPipeline._Slot()
+            s.mid1, s.mid2, s.count = (torch.empty(self.max_pairs, dtype=torch.int32, device=dev) for _ in range(3))
+            s.p, s.q = (torch.empty(padded, dtype=torch.float64, device=dev) for _ in range(2))
+            s.in_ready, s.run_done, s.out_done = (torch.cuda.Event() for _ in range(3))
+            self.slots.append(s)
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.s_run.wait_stream(torch.cuda.current_stream(dev))      # the engine's tables were filled there
+        self.submitted = 0
+
+    def submit(self, h_mid1, h_mid2, h_count, h_p, h_q=None, n_tests=-1):
+        """Enqueue one pass: pinned int32 host columns in, p (and q when h_q is given) back into pinned float64
+        host buffers.  Returns the event that fires when the outputs are on the host."""
+        n = int(h_mid1.numel())
+        if n > self.max_pairs or h_mid2.numel() != n or h_count.numel() != n or h_p.numel() != n:
+            raise ValueError("library larger than the pipeline's slots, or columns differ in length")
+        for t in (h_mid1, h_mid2, h_count, h_p, h_q):
+            if t is not None and not t.is_pinned():
+                raise ValueError("host buffers must be pinned (torch.Tensor.pin_memory)")
+        s = self.slots[self.submitted % len(self.slots)]
+        self.submitted += 1
+        self.s_in.wait_event(s.run_done)        # the pass that last read this slot's records has finished
+        with torch.cuda.stream(self.s_in):
+            s.mid1[:n].copy_(h_mid1, non_blocking=True)
+            s.mid2[:n].copy_(h_mid2, non_blocking=True)
+            s.count[:n].copy_(h_count, non_blocking=True)
+            s.in_ready.record()
+        self.s_run.wait_event(s.in_ready)
+        self.s_run.wait_event(s.out_done)       # this slot's previous p/q have left the device
+        with torch.cuda.stream(self.s_run):
+            sh = Shard(s.mid1[:n], s.mid2[:n], s.count[:n], chrom=self.chrom)
+            self.eng.run([sh], [s.p[:n]], [s.q[:n]] if h_q is not None else None, n_tests=n_tests)
+            s.run_done.record()
+        self.s_out.wait_event(s.run_done)
+        with torch.cuda.stream(self.s_out):
+            h_p.copy_(s.p[:n], non_blocking=True)
+            if h_q is not None:
+                h_q.copy_(s.q[:n], non_blocking=True)
+            s.out_done.record()
+        return s.out_done
+
+    def drain(self):
+        self.s_out.synchronize()

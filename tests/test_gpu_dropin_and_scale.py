@@ -205,3 +205,49 @@ def test_config1_full_size_against_oracle():
     assert (out.p[ref.keep & (ref.p < 1e-300)] <= 1e-299).all()
     qref = fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum()))
     assert np.array_equal(out.q[out.keep], qref)
+
+
+def test_host_pipeline_matches_serial_passes():
+    """engine.HostPipeline: five different libraries (different sizes and seeds) streamed through two device slots
+    give bit-for-bit the p and q of the same libraries run one at a time on the default stream."""
+    import torch
+    from blueberry_b200 import _lib
+    from blueberry_b200.engine import BiasTables, HostPipeline, PassEngine, Shard
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    R, nb, K = 5000, 6000, 400
+    P = int(lib.bbk_synth_n_pairs(nb, K))
+    rng = np.random.default_rng(5)
+    bias_host = np.exp(rng.normal(0.0, 0.25, size=nb))
+    bias_dev = torch.from_numpy(bias_host).to(dev)
+    eng = PassEngine(R, 100, 0, K * R, nb, dev)
+    eng.set_fragments([nb], [(nb - 1) * R])
+    eng.set_bias(BiasTables([np.where((bias_host < 0.5) | (bias_host > 2), -1.0, bias_host)], [R // 2], dev))
+    libs, want = [], []
+    for i in range(5):
+        cols = [torch.empty(P, dtype=torch.int32, device=dev) for _ in range(3)]
+        _lib.check(lib.bbk_synth_contacts(nb, K, R, 40.0 + 25 * i, 1.08, 100 + i, _lib.ptr(bias_dev), _lib.ptr(cols[0]),
+                                          _lib.ptr(cols[1]), _lib.ptr(cols[2]), _lib.stream_ptr()), "synth")
+        n = P - 1000 * i - (i & 1)                    # ragged sizes, odd and even
+        cols = [c[:n].contiguous() for c in cols]
+        p = torch.empty(n + 1, dtype=torch.float64, device=dev)[:n]
+        q = torch.empty(n + 1, dtype=torch.float64, device=dev)[:n]
+        eng.run([Shard(*cols)], [p], [q])
+        want.append((p.cpu(), q.cpu()))
+        libs.append([c.cpu().pin_memory() for c in cols])
+    torch.cuda.synchronize()
+    pipe = HostPipeline(eng, P, slots=2)
+    outs = []
+    for cols in libs:
+        n = cols[0].numel()
+        h_p, h_q = torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+        outs.append((h_p, h_q, pipe.submit(cols[0], cols[1], cols[2], h_p, h_q)))
+    outs[0][2].synchronize()                          # the event of the first library alone makes its outputs readable
+    assert torch.equal(outs[0][0].view(torch.int64), want[0][0].view(torch.int64))
+    pipe.drain()
+    for (h_p, h_q, _), (p, q) in zip(outs, want):
+        assert torch.equal(h_p.view(torch.int64), p.view(torch.int64))
+        assert torch.equal(h_q.view(torch.int64), q.view(torch.int64))
+    assert (want[0][0][:100000] != want[1][0][:100000]).any()
+    with pytest.raises(ValueError):
+        pipe.submit(libs[0][0], libs[0][1], libs[0][2], torch.empty(libs[0][0].numel(), dtype=torch.float64))
