@@ -12,10 +12,17 @@
 //   * the q formula keeps the reference's two roundings: (p * N) / rank.
 // Device pipeline (no host synchronisation; candidate count lives on the device):
 //   [coarse hist] -> threshold (1 CTA) -> compact + write q=1/NaN (the 16 B/pair pass)
-//   -> LSD radix sort of (key, index), 8 x 8 bits, passes with a uniform digit skipped
-//   -> head flags + running max (3-phase scan) -> scatter q (and rank) to input order.
-// BBK_BH_POSITIONAL (blueberry.pyx:40: input already sorted) skips everything but the scan.
+//   -> ONE cooperative launch (one CTA per SM, grid-wide barriers between phases) that ranks the candidates:
+//      LSD radix sort of (key, index), 8 x 8 bits, passes with a uniform digit skipped, then head flags +
+//      running max and the scatter of q (and rank) to input order.
+//      The candidate set is usually small (1e5 of 1e8 rows on BASELINE config 2), so this step is bound by
+//      dependent launches, not by bytes: 27 launches became 1 launch with 17 grid barriers.
+// BBK_BH_POSITIONAL (blueberry.pyx:40: input already sorted) skips everything but the scan (three small kernels).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -217,142 +224,6 @@ __device__ __forceinline__ Chunk chunk_of(long long n, int G, int b) {
     return c;
 }
 
-__global__ void __launch_bounds__(BH_THREADS) sort_hist_kernel(BhLayout L, int pass) {
-    __shared__ unsigned sh[256];
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-    const BhState* st = L.st;
-    const long long n = (long long)st->n_cand;
-    const unsigned long long* keys = L.keys[sort_parity(st, pass)];
-    const int Ge = eff_blocks(n, L.G);
-    if ((int)blockIdx.x >= Ge) return;
-    Chunk c = chunk_of(n, L.G, blockIdx.x);
-    const int shift = 8 * pass;
-    for (long long i = c.lo + threadIdx.x; i < c.hi; i += blockDim.x)
-        atomicAdd(&sh[(unsigned)(keys[i] >> shift) & 255u], 1u);
-    __syncthreads();
-    L.block_hist[(size_t)threadIdx.x * Ge + blockIdx.x] = sh[threadIdx.x];
-}
-
-// one CTA of 1024 threads: exclusive scan of the digit-major table [256][G], skip detection.
-// Warp w owns digits 8w..8w+7 and walks each digit's G block counts with coalesced loads.
-__global__ void __launch_bounds__(1024) sort_scan_kernel(BhLayout L, int pass) {
-    __shared__ unsigned tot[256];
-    __shared__ unsigned dbase[256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = eff_blocks((long long)L.st->n_cand, L.G);
-    constexpr int MAX_IT = 32;                               // G <= 1024 block columns
-    for (int dd = 0; dd < 8; ++dd) {
-        const int d = warp * 8 + dd;
-        unsigned* row = L.block_hist + (size_t)d * G;
-        unsigned v[MAX_IT];
-        const int n_it = (G + 31) >> 5;
-#pragma unroll
-        for (int k = 0; k < MAX_IT; ++k) {                   // all loads of the row in flight at once
-            int b = k * 32 + lane;
-            v[k] = (k < n_it && b < G) ? row[b] : 0u;
-        }
-        unsigned carry = 0;
-#pragma unroll
-        for (int k = 0; k < MAX_IT; ++k) {
-            if (k < n_it) {
-                unsigned x = v[k];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-                int b = k * 32 + lane;
-                if (b < G) row[b] = carry + x - v[k];        // exclusive, relative to the digit's start
-                carry += __shfl_sync(0xffffffffu, x, 31);
-            }
-        }
-        if (lane == 0) tot[d] = carry;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {                                  // exclusive scan of the 256 digit totals
-        unsigned carry = 0;
-        for (int d0 = 0; d0 < 256; d0 += 32) {
-            unsigned v = tot[d0 + lane], x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            dbase[d0 + lane] = carry + x - v;
-            carry += __shfl_sync(0xffffffffu, x, 31);
-        }
-    }
-    __syncthreads();
-    for (int dd = 0; dd < 8; ++dd) {
-        const int d = warp * 8 + dd;
-        unsigned* row = L.block_hist + (size_t)d * G;
-        const unsigned add = dbase[d];
-        if (add) for (int b = lane; b < G; b += 32) row[b] += add;
-    }
-    if (threadIdx.x < 32) {
-        const unsigned n = (unsigned)L.st->n_cand;
-        int uniform = 0;
-        for (int d = lane; d < 256; d += 32) uniform |= (tot[d] == n);
-        uniform = __any_sync(0xffffffffu, uniform);
-        if (lane == 0) L.st->skip[pass] = (uniform || n == 0) ? 1 : 0;
-    }
-}
-
-__global__ void __launch_bounds__(BH_THREADS) sort_scatter_kernel(BhLayout L, int pass) {
-    __shared__ unsigned base[256];
-    __shared__ unsigned whist[SORT_WARPS][256];
-    const BhState* st = L.st;
-    if (st->skip[pass]) return;
-    const long long n = (long long)st->n_cand;
-    const int par = sort_parity(st, pass);
-    const unsigned long long* kin = L.keys[par];
-    const unsigned* iin = L.idx[par];
-    unsigned long long* kout = L.keys[par ^ 1];
-    unsigned* iout = L.idx[par ^ 1];
-    const int shift = 8 * pass;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Ge = eff_blocks(n, L.G);
-    if ((int)blockIdx.x >= Ge) return;
-    base[threadIdx.x] = L.block_hist[(size_t)threadIdx.x * Ge + blockIdx.x];
-    Chunk c = chunk_of(n, L.G, blockIdx.x);
-    for (long long tile = c.lo; tile < c.hi; tile += SORT_TILE) {
-        for (int d = lane; d < 256; d += 32) whist[warp][d] = 0;
-        __syncthreads();
-        unsigned long long key[SORT_IPT];
-        unsigned val[SORT_IPT], loc[SORT_IPT];
-        const long long wbase = tile + (long long)warp * (32 * SORT_IPT);
-#pragma unroll
-        for (int it = 0; it < SORT_IPT; ++it) {
-            long long i = wbase + it * 32 + lane;
-            bool live = i < c.hi;
-            key[it] = live ? kin[i] : 0;
-            val[it] = live ? iin[i] : 0;
-            unsigned dg = live ? ((unsigned)(key[it] >> shift) & 255u) : 256u;
-            unsigned peers = __match_any_sync(0xffffffffu, dg);
-            unsigned rank = __popc(peers & ((1u << lane) - 1));
-            unsigned before = live ? whist[warp][dg] : 0;
-            __syncwarp();
-            if (live && rank == 0) whist[warp][dg] = before + __popc(peers);
-            __syncwarp();
-            loc[it] = before + rank;
-        }
-        __syncthreads();
-        {   // exclusive scan over warps, per digit; advance the running base of this block
-            unsigned run = base[threadIdx.x];
-#pragma unroll
-            for (int w = 0; w < SORT_WARPS; ++w) { unsigned v = whist[w][threadIdx.x]; whist[w][threadIdx.x] = run; run += v; }
-            base[threadIdx.x] = run;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < SORT_IPT; ++it) {
-            long long i = wbase + it * 32 + lane;
-            if (i < c.hi) {
-                unsigned dg = (unsigned)(key[it] >> shift) & 255u;
-                unsigned pos = whist[warp][dg] + loc[it];
-                kout[pos] = key[it];
-                iout[pos] = val[it];
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ---- running max over the sorted candidates --------------------------------------------------
 // element i contributes (value, head): value = head ? min((p*N)/(i+1), 1) : -inf ; head index = i or -1
 struct ScanParams {
@@ -528,6 +399,271 @@ __global__ void __launch_bounds__(BH_THREADS) scan_apply_kernel(ScanParams S) {
     }
 }
 
+// ---- the candidates' ranking in one cooperative launch ---------------------------------------------
+// One CTA of 1024 threads per SM; CTA b owns a contiguous chunk of whole tiles.  Per radix pass:
+//   count the chunk's digits -> table[b][256] | grid barrier | every active CTA sums the table's columns itself
+//   (its own prefix over earlier CTAs + the digit totals: no scan CTA, no extra barrier), then scatters its tiles
+//   in order, ranking equal digits inside a warp with match_any (stable) | grid barrier.
+// Then the forward running max over the sorted keys: chunk partials | grid barrier | prefix over earlier CTAs + apply.
+constexpr int RK_THREADS = 1024;
+constexpr int RK_WARPS = RK_THREADS / 32;
+constexpr int RK_IPT = 4;
+constexpr int RK_TILE = RK_THREADS * RK_IPT;
+
+struct RankParams {
+    BhLayout L;
+    double* q;               // output (input order, or gathered order for bbk_bh_rank_gathered)
+    long long* rank;         // optional
+};
+
+__device__ __forceinline__ int rk_eff_blocks(long long n, int G) {
+    long long g = (n + RK_TILE - 1) / RK_TILE;
+    if (g < 1) g = 1;
+    return g < G ? (int)g : G;
+}
+__device__ __forceinline__ Chunk rk_chunk(long long n, int Ge, int b) {
+    Chunk c;
+    if (b >= Ge) { c.lo = c.hi = n; return c; }
+    long long per = (n + Ge - 1) / Ge;
+    per = (per + RK_TILE - 1) / RK_TILE * RK_TILE;
+    c.lo = (long long)b * per;
+    c.hi = c.lo + per;
+    if (c.lo > n) c.lo = n;
+    if (c.hi > n) c.hi = n;
+    return c;
+}
+
+// (running max, index of the last tie-group head): max in both fields, identity (-inf, -1)
+struct MaxHead { double v; long long h; };
+__device__ __forceinline__ MaxHead mh_combine(const MaxHead& a, const MaxHead& b) {
+    MaxHead r;
+    r.v = (a.v > b.v) ? a.v : b.v;
+    r.h = a.h > b.h ? a.h : b.h;
+    return r;
+}
+__device__ __forceinline__ MaxHead mh_elem(const unsigned long long* keys, long long i, double N) {
+    MaxHead e;
+    const unsigned long long k = keys[i];
+    if (i == 0 || keys[i - 1] != k) {
+        double bh = (value_of(k) * N) / (double)(i + 1);     // two roundings, as fithic.py:474 / blueberry.pyx:68
+        e.v = (1.0 < bh) ? 1.0 : bh;
+        e.h = i;
+    } else { e.v = -INFINITY; e.h = -1; }
+    return e;
+}
+
+__global__ void __launch_bounds__(RK_THREADS, 1) bh_rank_kernel(RankParams R) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned base[256];                   // digit counts of the chunk, then the running output cursor per digit
+    __shared__ unsigned col_pre[4][256], col_tot[4][256];
+    __shared__ unsigned wsum[8];
+    __shared__ unsigned whist[RK_WARPS][256];
+    __shared__ int sh_skip;
+    __shared__ double wv[RK_WARPS];
+    __shared__ long long wh[RK_WARPS];
+    BhState* st = R.L.st;
+    const long long n = (long long)st->n_cand;
+    const int b = blockIdx.x, Ge = rk_eff_blocks(n, gridDim.x);
+    const bool active = b < Ge;
+    const Chunk c = rk_chunk(n, Ge, b);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned* table = R.L.block_hist;                // [Ge][256]
+    int par = 0;
+    for (int pass = 0; pass < NPASS; ++pass) {
+        const int shift = 8 * pass;
+        const unsigned long long* kin = R.L.keys[par];
+        if (active) {
+            if (t < 256) base[t] = 0;
+            if (t == 0) sh_skip = 0;
+            __syncthreads();
+            for (long long i = c.lo + t; i < c.hi; i += RK_THREADS) atomicAdd(&base[(unsigned)(kin[i] >> shift) & 255u], 1u);
+            __syncthreads();
+            if (t < 256) table[(size_t)b * 256 + t] = base[t];
+        }
+        grid.sync();
+        if (active) {
+            {   // column sums of the table: thread (part, d) takes every 4th CTA row
+                const int d = t & 255, part = t >> 8;
+                unsigned pre = 0, tot = 0;
+                for (int bb = part; bb < Ge; bb += 4) {
+                    unsigned v = table[(size_t)bb * 256 + d];
+                    tot += v;
+                    if (bb < b) pre += v;
+                }
+                col_pre[part][d] = pre; col_tot[part][d] = tot;
+            }
+            __syncthreads();
+            unsigned pre = 0, tot = 0, x = 0;
+            if (t < 256) {
+                pre = col_pre[0][t] + col_pre[1][t] + col_pre[2][t] + col_pre[3][t];
+                tot = col_tot[0][t] + col_tot[1][t] + col_tot[2][t] + col_tot[3][t];
+                if ((long long)tot == n) sh_skip = 1;                    // every key has this digit: nothing moves
+                x = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (lane == 31) wsum[warp] = x;
+            }
+            __syncthreads();
+            if (t < 256) {
+                unsigned before = 0;
+                for (int w = 0; w < warp; ++w) before += wsum[w];
+                base[t] = before + x - tot + pre;                        // digits below + same digit in earlier CTAs
+            }
+            __syncthreads();
+            const bool skip = sh_skip != 0;
+            if (t == 0 && b == 0) st->skip[pass] = skip ? 1 : 0;
+            if (!skip) {
+                const unsigned* iin = R.L.idx[par];
+                unsigned long long* kout = R.L.keys[par ^ 1];
+                unsigned* iout = R.L.idx[par ^ 1];
+                for (long long tile = c.lo; tile < c.hi; tile += RK_TILE) {
+                    for (int d = lane; d < 256; d += 32) whist[warp][d] = 0;
+                    __syncwarp();
+                    unsigned long long key[RK_IPT];
+                    unsigned val[RK_IPT], loc[RK_IPT];
+                    const long long wbase = tile + (long long)warp * (32 * RK_IPT);
+#pragma unroll
+                    for (int it = 0; it < RK_IPT; ++it) {
+                        const long long i = wbase + it * 32 + lane;
+                        const bool live = i < c.hi;
+                        key[it] = live ? kin[i] : 0;
+                        val[it] = live ? iin[i] : 0;
+                    }
+#pragma unroll
+                    for (int it = 0; it < RK_IPT; ++it) {
+                        const bool live = wbase + it * 32 + lane < c.hi;
+                        const unsigned dg = live ? ((unsigned)(key[it] >> shift) & 255u) : 256u;
+                        const unsigned peers = __match_any_sync(0xffffffffu, dg);
+                        const unsigned rk = __popc(peers & ((1u << lane) - 1));
+                        const unsigned before = live ? whist[warp][dg] : 0;
+                        __syncwarp();
+                        if (live && rk == 0) whist[warp][dg] = before + __popc(peers);
+                        __syncwarp();
+                        loc[it] = before + rk;
+                    }
+                    __syncthreads();
+                    if (t < 256) {   // exclusive scan over warps, per digit; advance the running cursor of this CTA
+                        unsigned run = base[t];
+#pragma unroll 8
+                        for (int w = 0; w < RK_WARPS; ++w) { unsigned v = whist[w][t]; whist[w][t] = run; run += v; }
+                        base[t] = run;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int it = 0; it < RK_IPT; ++it) {
+                        if (wbase + it * 32 + lane < c.hi) {
+                            const unsigned dg = (unsigned)(key[it] >> shift) & 255u;
+                            const unsigned pos = whist[warp][dg] + loc[it];
+                            kout[pos] = key[it];
+                            iout[pos] = val[it];
+                        }
+                    }
+                    __syncthreads();
+                }
+                par ^= 1;
+            }
+        }
+        grid.sync();
+    }
+
+    // ---- forward running max over the sorted keys; thread t scans a contiguous slice of the chunk
+    const unsigned long long* keys = R.L.keys[par];
+    const unsigned* idx = R.L.idx[par];
+    const double N = (double)st->n_tests;
+    const MaxHead ident = {-INFINITY, -1};
+    long long lo = c.lo, hi = c.lo;
+    MaxHead excl = ident;                            // everything before this thread's slice, inside the chunk
+    if (active) {
+        const long long len = c.hi - c.lo, per = (len + RK_THREADS - 1) / RK_THREADS;
+        lo = c.lo + (long long)t * per; hi = lo + per;
+        if (lo > c.hi) lo = c.hi;
+        if (hi > c.hi) hi = c.hi;
+        MaxHead acc = ident;
+        for (long long i = lo; i < hi; ++i) acc = mh_combine(acc, mh_elem(keys, i, N));
+        MaxHead inc = acc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            MaxHead up;
+            up.v = __shfl_up_sync(0xffffffffu, inc.v, o);
+            up.h = __shfl_up_sync(0xffffffffu, inc.h, o);
+            if (lane >= o) inc = mh_combine(up, inc);
+        }
+        if (lane == 31) { wv[warp] = inc.v; wh[warp] = inc.h; }
+        excl.v = __shfl_up_sync(0xffffffffu, inc.v, 1);
+        excl.h = __shfl_up_sync(0xffffffffu, inc.h, 1);
+        if (lane == 0) excl = ident;
+        __syncthreads();
+        MaxHead wpre = ident;
+        for (int w = 0; w < warp; ++w) { MaxHead e = {wv[w], wh[w]}; wpre = mh_combine(wpre, e); }
+        excl = mh_combine(wpre, excl);
+        if (t == RK_THREADS - 1) {
+            MaxHead all = mh_combine(excl, acc);
+            R.L.part_max[b] = all.v;
+            R.L.part_head[b] = all.h;
+        }
+    }
+    grid.sync();
+    if (active) {
+        MaxHead run = ident;                         // chunks of the earlier CTAs
+        for (int bb = lane; bb < b; bb += 32) { MaxHead e = {R.L.part_max[bb], R.L.part_head[bb]}; run = mh_combine(run, e); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MaxHead other;
+            other.v = __shfl_xor_sync(0xffffffffu, run.v, o);
+            other.h = __shfl_xor_sync(0xffffffffu, run.h, o);
+            run = mh_combine(run, other);
+        }
+        run = mh_combine(run, excl);
+        for (long long i = lo; i < hi; ++i) {
+            run = mh_combine(run, mh_elem(keys, i, N));
+            const unsigned o = idx[i];
+            R.q[o] = run.v;
+            if (R.rank) R.rank[o] = run.h + 1;
+        }
+    }
+    if (b == 0 && warp == 0) {                       // the p == 1.0 group: one tie group after every candidate
+        MaxHead all = ident;
+        for (int bb = lane; bb < Ge; bb += 32) { MaxHead e = {R.L.part_max[bb], R.L.part_head[bb]}; all = mh_combine(all, e); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MaxHead other;
+            other.v = __shfl_xor_sync(0xffffffffu, all.v, o);
+            other.h = __shfl_xor_sync(0xffffffffu, all.h, o);
+            all = mh_combine(all, other);
+        }
+        if (lane == 0) {
+            st->total_max = all.v;
+            double bh = (1.0 * N) / (double)(st->n_cand + 1);
+            bh = (1.0 < bh) ? 1.0 : bh;
+            double qo = (all.v > bh) ? all.v : bh;
+            if (st->tau_key != ~0ull) qo = 1.0;      // saturated before the ones
+            st->q_ones = qo;
+            st->need_ones_fix = (qo != 1.0 && st->n_ones > 0) ? 1 : 0;
+        }
+    }
+}
+
+int rank_grid() {            // CTAs of bh_rank_kernel that are resident together (cooperative launch): one per SM
+    static int g = 0;
+    if (g == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_rank_kernel, RK_THREADS, 0) != cudaSuccess || per_sm < 1) return 0;
+        g = bbk_num_sms();
+    }
+    return g;
+}
+
+int launch_rank(const BhLayout& L, double* q, long long* rank, cudaStream_t st) {
+    int g = rank_grid();
+    if (g <= 0 || g > L.G) { bbk_set_error("bh_rank_kernel: cooperative launch not possible on this device"); return BBK_E_CUDA; }
+    RankParams R;
+    R.L = L; R.q = q; R.rank = rank;
+    void* args[] = {&R};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel, dim3(g), dim3(RK_THREADS), args, 0, st);
+    if (e != cudaSuccess) { bbk_set_error("bh_rank_kernel: %s", cudaGetErrorString(e)); return BBK_E_CUDA; }
+    return BBK_OK;
+}
+
 // rare: q of the p == 1.0 group is below 1 (N smaller than the number of candidates)
 __global__ void __launch_bounds__(BH_THREADS) ones_fix_kernel(const double* p, long long m, double* q, const BhState* st) {
     if (!st->need_ones_fix) return;
@@ -616,21 +752,16 @@ extern "C" int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int
         BBK_CHECK_LAUNCH("bh_threshold_kernel");
         bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, L.keys[0], L.idx[0], want_rank, (long long*)d_rank);
         BBK_CHECK_LAUNCH("bh_compact_kernel");
-        for (int pass = 0; pass < NPASS; ++pass) {
-            sort_hist_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
-            BBK_CHECK_LAUNCH("sort_hist_kernel");
-            sort_scan_kernel<<<1, 1024, 0, st>>>(L, pass);
-            BBK_CHECK_LAUNCH("sort_scan_kernel");
-            sort_scatter_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
-            BBK_CHECK_LAUNCH("sort_scatter_kernel");
-        }
+        int rc = launch_rank(L, d_q, (long long*)d_rank, st);
+        if (rc != BBK_OK) return rc;
+    } else {
+        scan_partial_kernel<<<G, BH_THREADS, 0, st>>>(S);
+        BBK_CHECK_LAUNCH("scan_partial_kernel");
+        scan_prefix_kernel<<<1, 32, 0, st>>>(S);
+        BBK_CHECK_LAUNCH("scan_prefix_kernel");
+        scan_apply_kernel<<<G, BH_THREADS, 0, st>>>(S);
+        BBK_CHECK_LAUNCH("scan_apply_kernel");
     }
-    scan_partial_kernel<<<G, BH_THREADS, 0, st>>>(S);
-    BBK_CHECK_LAUNCH("scan_partial_kernel");
-    scan_prefix_kernel<<<1, 32, 0, st>>>(S);
-    BBK_CHECK_LAUNCH("scan_prefix_kernel");
-    scan_apply_kernel<<<G, BH_THREADS, 0, st>>>(S);
-    BBK_CHECK_LAUNCH("scan_apply_kernel");
     if (mode == BBK_BH_UNSORTED && !d_rank) {
         long long want = (m + BH_THREADS - 1) / BH_THREADS;
         int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
@@ -692,23 +823,9 @@ extern "C" int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, c
         int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
         load_keys_kernel<<<grid, BH_THREADS, 0, st>>>((const unsigned long long*)d_keys_all, n_all, L.keys[0], L.idx[0]);
         BBK_CHECK_LAUNCH("load_keys_kernel");
-        for (int pass = 0; pass < NPASS; ++pass) {
-            sort_hist_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
-            BBK_CHECK_LAUNCH("sort_hist_kernel");
-            sort_scan_kernel<<<1, 1024, 0, st>>>(L, pass);
-            BBK_CHECK_LAUNCH("sort_scan_kernel");
-            sort_scatter_kernel<<<G, BH_THREADS, 0, st>>>(L, pass);
-            BBK_CHECK_LAUNCH("sort_scatter_kernel");
-        }
     }
-    ScanParams S;
-    S.L = L; S.p_in = nullptr; S.m = n_all; S.q = d_q_all; S.rank = nullptr; S.positional = 0;
-    scan_partial_kernel<<<G, BH_THREADS, 0, st>>>(S);
-    BBK_CHECK_LAUNCH("scan_partial_kernel");
-    scan_prefix_kernel<<<1, 32, 0, st>>>(S);
-    BBK_CHECK_LAUNCH("scan_prefix_kernel");
-    scan_apply_kernel<<<G, BH_THREADS, 0, st>>>(S);
-    BBK_CHECK_LAUNCH("scan_apply_kernel");
+    int rc = launch_rank(L, d_q_all, nullptr, st);
+    if (rc != BBK_OK) return rc;
     export_ones_kernel<<<1, 1, 0, st>>>(L.st, d_q_ones);
     BBK_CHECK_LAUNCH("export_ones_kernel");
     return BBK_OK;

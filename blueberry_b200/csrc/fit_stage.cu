@@ -202,9 +202,13 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         __syncthreads();
         if (sh.status == BBK_FIT_OK) {
             BbkCoopWs cw;
-            bbk_coop_ws_carve(base + 2 * m, m, &cw);
-            if (base == pool) bbk_coop_univariate_spline_t<true>(xs, ys, m, sh.s, &sh.st, &cw);    // everything in shared memory
-            else              bbk_coop_univariate_spline_t<false>(xs, ys, m, sh.s, &sh.st, &cw);   // large m: global workspace
+            if (base == pool) {                              // everything in shared memory
+                bbk_coop_ws_carve(pool + 2 * m, m, &cw);
+                bbk_coop_univariate_spline_t<true>(pool, pool + m, m, sh.s, &sh.st, &cw);
+            } else {                                         // large m: global workspace
+                bbk_coop_ws_carve(base + 2 * m, m, &cw);
+                bbk_coop_univariate_spline_t<false>(xs, ys, m, sh.s, &sh.st, &cw);
+            }
             __syncthreads();
             const int n = sh.st.n;
             for (int i = tid; i < m + 4; i += FIT_THREADS) {

@@ -176,7 +176,8 @@ class PassEngine(object):
         _lib.check(self.lib.bbk_bh_qvalues(_lib.ptr(p), m, int(n_tests), mode, _lib.ptr(self.p_hist) if use_hist else None,
                                            _lib.ptr(q), _lib.ptr(rank), _lib.ptr(self.bh_ws), self.bh_ws.numel(),
                                            _lib.stream_ptr()), "bbk_bh_qvalues")
-        self.launches += (4 if mode == _lib.BH_POSITIONAL else 33 - (1 if use_hist else 0))
+        # init, [coarse histogram], threshold, compact, rank (one cooperative launch), ones fix
+        self.launches += (4 if mode == _lib.BH_POSITIONAL else 6 - (1 if use_hist else 0))
 
     def qvalues_global(self, p, q, n_tests=-1, group=None, hist=None):
         """Genome-wide Benjamini-Hochberg across the ranks of `group`: every rank passes its shard's p and gets
@@ -233,7 +234,7 @@ class PassEngine(object):
             _lib.check(lib.bbk_bh_scatter(_lib.ptr(q_all[off:off + n_local]), _lib.ptr(idx), n_local, _lib.ptr(q), st), "bbk_bh_scatter")
         # rare: q of the p == 1.0 group below 1 - decided and applied on the device (no host round trip)
         _lib.check(lib.bbk_bh_fix_ones_dev(_lib.ptr(p), m, _lib.ptr(q_ones), _lib.ptr(q), st), "bbk_bh_fix_ones_dev")
-        self.launches += 40
+        self.launches += 10       # select (4 kernels) + rank_gathered (4) + scatter + ones fix
         return n_all
 
     # ------------------------------------------------------------------ results

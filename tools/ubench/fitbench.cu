@@ -4,7 +4,9 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
+#ifndef NO_QR_PROFILE
 #define BBK_QR_PROFILE 1
+#endif
 #include "../../blueberry_b200/csrc/fit_coop.h"
 
 __global__ void __launch_bounds__(128, 1) k(const double* x, const double* y, int m, double s, double* ws, BbkCoopState* out, long long* cyc) {
@@ -46,7 +48,16 @@ int main(int argc, char** argv) {
         printf("m=%d n=%d ier=%d total %lld cyc | fits %lld piters %lld | rows+QR %lld backsub %lld resid+knots %lld sweep %lld f(p) %lld | per-fit QR %lld\n",
                m, st.n, st.ier, c, st.diag[0], st.diag[1], st.diag[2], st.diag[3], st.diag[4], st.diag[5], st.diag[6],
                st.diag[0] ? st.diag[2] / st.diag[0] : 0);
-        printf("   QR loop only: %lld cycles over %lld half-steps (+f(p) mixed in diag6) -> %.0f cycles per half-step\n", st.diag[7], st.diag[6], (double)st.diag[7] / (double)(st.diag[1] / 1000000)); printf("   half-steps %lld ; warp0 work on odd half-steps (phase A) %lld, on even (phase B) %lld, barrier wait %lld (these are mixed into backsub/resid/sweep slots)\n", st.diag[1] / 1000000, st.diag[3], st.diag[4], st.diag[5]);
+#ifdef BBK_QR_PROFILE
+        long long pr[8];
+        cudaMemcpyFromSymbol(pr, bbk_qr_prof, sizeof(pr));
+        printf("   QR loops: %lld half-steps, %lld cycles -> %.0f per half-step\n", pr[0], pr[1], (double)pr[1] / (double)pr[0]);
+        for (int w = 0; w < 2; ++w)
+            printf("   warp %d per half-step: work on odd half-steps %.0f, on even %.0f, barrier wait %.0f\n", w,
+                   2.0 * pr[2 + 3 * w] / pr[0], 2.0 * pr[3 + 3 * w] / pr[0], (double)pr[4 + 3 * w] / pr[0]);
+        long long zero[8] = {0};
+        cudaMemcpyToSymbol(bbk_qr_prof, zero, sizeof(zero));
+#endif
     }
     return 0;
 }
