@@ -231,8 +231,8 @@ def run_ours(args, out_fd):
     def bh():
         if genome_q:      # all-reduce of the p histogram + all-gather of the candidate keys (2 host syncs)
             eng.qvalues_global(p, q, n_tests=-1, group=group, hist=eng.p_hist)
-        else:
-            eng.qvalues(p, q, n_tests=-1, use_hist=True)
+        else:             # K4 pre-filled q and listed the small p (bbk_pvalues_bh): no second pass over p
+            eng.qvalues(p, q, n_tests=-1, use_hist=True, prepared=True)
 
     p_first = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P] if two_pass else None
     p_outlier = 1.0 / float(world * (nb * (K + 1) - K * (K + 1) // 2 - nb))   # 1 / possibleIntraInRangeCount (d = R..K*R)
@@ -247,7 +247,7 @@ def run_ours(args, out_fd):
             eng.hist_excluding([shard], [p_first], p_outlier)
             eng.allreduce_stats(group)
             eng.fit()
-        eng.pvalues(shard, p, with_hist=True)
+        eng.pvalues(shard, p, with_hist=True, q_out=None if genome_q else q)
         bh()
 
     def barrier():
@@ -295,7 +295,7 @@ def run_ours(args, out_fd):
         ev[0].record(); eng.hist([shard])
         ev[1].record(); eng.allreduce_stats(group)
         ev[2].record(); eng.fit()
-        ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True)
+        ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True, q_out=None if genome_q else q)
         ev[4].record(); bh()
         ev[5].record()
         torch.cuda.synchronize()

@@ -41,7 +41,7 @@ struct BhState {                    // device-resident control block (first byte
     double total_max;               // running max over all candidates
     int need_ones_fix;              // q_ones != 1.0 -> rewrite the ones
     int skip[NPASS];
-    int pad;
+    int use_list;                   // prepared mode: K4's small-p list holds every candidate (saturation below BBK_SMALL_P)
 };
 
 struct BhLayout {
@@ -75,11 +75,7 @@ size_t bh_layout(void* base, long long m, int G, BhLayout* L) {
     return off;
 }
 
-// order-preserving map double -> u64 (total order of IEEE values; -0 < +0)
-__device__ __forceinline__ unsigned long long key_of(double v) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
+__device__ __forceinline__ unsigned long long key_of(double v) { return bbk_key_of(v); }
 __device__ __forceinline__ double value_of(unsigned long long k) {
     unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
     return __longlong_as_double((long long)b);
@@ -95,6 +91,7 @@ __global__ void bh_init_kernel(BhState* st, long long* phist, const long long* p
         st->n_cand = 0; st->n_ones = 0; st->n_nan = 0; st->n_valid = 0; st->tau_key = ~0ull;
         st->n_tests = n_tests; st->q_ones = 1.0; st->total_max = 0.0; st->need_ones_fix = 0;
         for (int p = 0; p < NPASS; ++p) st->skip[p] = 0;
+        st->use_list = 0;
     }
 }
 
@@ -123,7 +120,7 @@ __global__ void __launch_bounds__(BH_THREADS) bh_hist_kernel(const double* p, lo
 }
 
 // one CTA of 1024 threads (4 buckets each): totals, N, and the saturation bucket
-__global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const long long* phist, int prune) {
+__global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const long long* phist, int prune, int prepared) {
     __shared__ long long part[1024];
     __shared__ int first_bucket;
     const int t = threadIdx.x;
@@ -163,7 +160,10 @@ __global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const l
         st->n_nan = (unsigned long long)phist[BBK_PHIST_BINS + 1];
         st->n_valid = (unsigned long long)(total + ones);
         st->n_tests = n_tests;
-        st->tau_key = first_bucket < BBK_PHIST_BINS ? (((unsigned long long)first_bucket << 51) | 0x8000000000000000ull) : ~0ull;
+        const unsigned long long tau = first_bucket < BBK_PHIST_BINS ? (((unsigned long long)first_bucket << 51) | 0x8000000000000000ull) : ~0ull;
+        st->tau_key = tau;
+        // prepared mode: K4's bit per record (p < BBK_SMALL_P) stands in for the pass over p when it covers every candidate
+        st->use_list = (prepared && tau <= bbk_key_of(BBK_SMALL_P)) ? 1 : 0;
     }
 }
 
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const l
 __global__ void __launch_bounds__(BH_THREADS) bh_compact_kernel(const double* p, long long m, double* q, BhState* st,
                                                                 unsigned long long* keys, unsigned* idx, int keep_ones,
                                                                 long long* rank) {
+    if (st->use_list) return;                                // K4 pre-filled q and listed every candidate
     const unsigned long long tau = st->tau_key;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     long long stride = (long long)gridDim.x * blockDim.x;
@@ -193,6 +194,51 @@ __global__ void __launch_bounds__(BH_THREADS) bh_compact_kernel(const double* p,
                 unsigned long long pos = base + __popc(mask & ((1u << lane) - 1));
                 keys[pos] = k;
                 idx[pos] = (unsigned)i;
+            }
+        }
+    }
+}
+
+// prepared mode: the candidates are among the records K4 flagged (p < BBK_SMALL_P): m/8 bytes of flags plus one
+// sector per flagged record instead of the 16 B/pair pass.  One flag word per thread; the lanes of a warp pop their
+// set bits in rounds so that each round costs one atomic on the candidate counter.
+__global__ void __launch_bounds__(BH_THREADS) bh_mask_filter_kernel(BhState* st, const unsigned* mask, const double* p, long long m,
+                                                                    unsigned long long* keys, unsigned* idx) {
+    if (!st->use_list) return;
+    const unsigned long long tau = st->tau_key;
+    const long long n_words = ((m >> 2) + 31) / 32 * 4;      // 4 words per (started) block of 32 four-record groups
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_iter = (n_words + 1 + stride - 1) / stride;       // + 1: a pseudo word for the last m % 4 records
+    const int lane = threadIdx.x & 31;
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long it = 0; it < n_iter; ++it, w += stride) {
+        unsigned bits = 0;
+        long long rec0 = 0;
+        int step = 4;
+        if (w < n_words) { bits = mask[w]; rec0 = (w >> 2) * 128 + (w & 3); }
+        else if (w == n_words) { bits = (1u << (m & 3)) - 1; rec0 = (m >> 2) << 2; step = 1; }     // unflagged tail: look at all
+        while (__any_sync(0xffffffffu, bits != 0)) {
+            bool cand = false;
+            unsigned long long k = 0;
+            long long rec = 0;
+            if (bits) {
+                const int l = __ffs(bits) - 1;
+                bits &= bits - 1;
+                rec = rec0 + (long long)step * l;
+                const double v = p[rec];
+                k = bbk_key_of(v);
+                cand = !isnan(v) && v != 1.0 && k < tau;
+            }
+            const unsigned vote = __ballot_sync(0xffffffffu, cand);
+            if (vote) {
+                unsigned long long base = 0;
+                if (lane == __ffs(vote) - 1) base = atomicAdd(&st->n_cand, (unsigned long long)__popc(vote));
+                base = __shfl_sync(0xffffffffu, base, __ffs(vote) - 1);
+                if (cand) {
+                    const unsigned long long pos = base + __popc(vote & ((1u << lane) - 1));
+                    keys[pos] = k;
+                    idx[pos] = (unsigned)rec;
+                }
             }
         }
     }
@@ -748,7 +794,7 @@ extern "C" int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int
             BBK_CHECK_LAUNCH("bh_hist_kernel");
         }
         const int want_rank = d_rank != nullptr;
-        bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, want_rank ? 0 : 1);
+        bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, want_rank ? 0 : 1, 0);
         BBK_CHECK_LAUNCH("bh_threshold_kernel");
         bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, L.keys[0], L.idx[0], want_rank, (long long*)d_rank);
         BBK_CHECK_LAUNCH("bh_compact_kernel");
@@ -768,6 +814,50 @@ extern "C" int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int
         ones_fix_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st);
         BBK_CHECK_LAUNCH("ones_fix_kernel");
     }
+    return BBK_OK;
+}
+
+// K4's flag bits (m/8 bytes) live in the sort's second index buffer (4 m bytes), which nothing uses before the first radix pass
+unsigned* bbk_bh_mask_buffer(void* workspace, long long m) {
+    BhLayout L;
+    bh_layout(workspace, m, sort_blocks(), &L);
+    return L.idx[1];
+}
+
+extern "C" int bbk_bh_qvalues_prepared(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist, double* d_q,
+                                       void* d_workspace, size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(m >= 0 && m < (1ll << 32), "bbk_bh_qvalues_prepared: m must be in [0, 2^32)");
+    if (m == 0) return BBK_OK;
+    BBK_REQUIRE(d_p && d_q && d_p_hist && d_workspace, "bbk_bh_qvalues_prepared: null pointer");
+    BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_qvalues_prepared: workspace must be 256-byte aligned");
+    const int G = sort_blocks();
+    BhLayout L;
+    size_t need = bh_layout(d_workspace, m, G, &L);
+    if (workspace_bytes < need) {
+        bbk_set_error("bbk_bh_qvalues_prepared: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return BBK_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = bbk_num_sms();
+    bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist, n_tests);
+    BBK_CHECK_LAUNCH("bh_init_kernel");
+    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, 1);
+    BBK_CHECK_LAUNCH("bh_threshold_kernel");
+    {
+        long long words = ((m >> 2) + 31) / 32 * 4 + 1, wantw = (words + BH_THREADS - 1) / BH_THREADS;
+        int gridw = (int)(wantw < (long long)sms * 8 ? wantw : (long long)sms * 8);
+        bh_mask_filter_kernel<<<gridw, BH_THREADS, 0, st>>>(L.st, L.idx[1], d_p, m, L.keys[0], L.idx[0]);
+        BBK_CHECK_LAUNCH("bh_mask_filter_kernel");
+    }
+    long long want = (m + BH_THREADS - 1) / BH_THREADS;
+    int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+    // saturation above BBK_SMALL_P (many significant rows): the 16 B/pair pass after all; otherwise returns at once
+    bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, L.keys[0], L.idx[0], 0, nullptr);
+    BBK_CHECK_LAUNCH("bh_compact_kernel");
+    int rc = launch_rank(L, d_q, nullptr, st);
+    if (rc != BBK_OK) return rc;
+    ones_fix_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st);
+    BBK_CHECK_LAUNCH("ones_fix_kernel");
     return BBK_OK;
 }
 
@@ -792,7 +882,7 @@ extern "C" int bbk_bh_select(const double* d_p, int64_t m, int64_t n_tests, cons
     cudaStream_t st = (cudaStream_t)stream;
     bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist_global, n_tests);
     BBK_CHECK_LAUNCH("bh_init_kernel");
-    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1);
+    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, 0);
     BBK_CHECK_LAUNCH("bh_threshold_kernel");
     if (m > 0) {
         long long want = (m + BH_THREADS - 1) / BH_THREADS;

@@ -11,6 +11,14 @@
 void bbk_set_error(const char* fmt, ...);
 int bbk_num_sms();
 
+// K4 -> K5 hand-over (bbk_pvalues_bh / bbk_bh_qvalues_prepared): K4 leaves one bit per record, p < BBK_SMALL_P, so that
+// the q-value step finds its candidates from m/8 bytes instead of another pass over p.  Exact whatever the bound: when
+// the saturation bucket lies above it, K5 falls back to its own pass.
+// Layout: uint4 per 128 consecutive records; bit l of word e = record 128 j + 4 l + e.
+#define BBK_SMALL_P 0.03125
+// where K4 puts the bits inside K5's workspace (defined in bh.cu)
+unsigned* bbk_bh_mask_buffer(void* workspace, long long m);
+
 #define BBK_CHECK_CUDA(expr)                                                                  \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
@@ -36,6 +44,12 @@ int bbk_num_sms();
             return BBK_E_INVALID;                                                             \
         }                                                                                     \
     } while (0)
+
+// order-preserving map double -> u64 (total order of IEEE values; -0 < +0)
+__device__ __forceinline__ unsigned long long bbk_key_of(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
 
 // streaming 128-bit load that does not allocate in L1 (each record is read exactly once)
 __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {

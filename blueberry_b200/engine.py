@@ -160,21 +160,41 @@ class PassEngine(object):
                    "bbk_fit")
         self.launches += 1
 
-    def pvalues(self, shard, p_out, with_hist=False):
-        bias = ctypes.byref(self.bias.struct) if self.bias is not None else None
-        _lib.check(self.lib.bbk_pvalues(_lib.ptr(shard.chr1), _lib.ptr(shard.chr2), _lib.ptr(shard.mid1), _lib.ptr(shard.mid2),
-                                        _lib.ptr(shard.count), shard.n, shard.chrom, self.R, self.min_dist, self.max_dist,
-                                        _lib.ptr(self.fit_result), _lib.ptr(self.spline_y), bias, _lib.ptr(p_out),
-                                        _lib.ptr(self.p_hist) if with_hist else None, _lib.stream_ptr()), "bbk_pvalues")
-        self.launches += 1
-
-    def qvalues(self, p, q, n_tests=-1, use_hist=False, rank=None, mode=_lib.BH_UNSORTED):
-        m = int(p.numel())
-        need = int(self.lib.bbk_bh_workspace_bytes(m))
+    def _bh_workspace(self, m):
+        need = int(self.lib.bbk_bh_workspace_bytes(int(m)))
         if self.bh_ws is None or self.bh_ws.numel() < need:
             self.bh_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.bh_ws
+
+    def pvalues(self, shard, p_out, with_hist=False, q_out=None):
+        """K4.  with_hist: also fill self.p_hist (zero it first).  q_out (with with_hist): the hand-over of
+        bbk_pvalues_bh - q pre-filled and the small p listed for qvalues(..., prepared=True) right after."""
+        bias = ctypes.byref(self.bias.struct) if self.bias is not None else None
+        args = (_lib.ptr(shard.chr1), _lib.ptr(shard.chr2), _lib.ptr(shard.mid1), _lib.ptr(shard.mid2),
+                _lib.ptr(shard.count), shard.n, shard.chrom, self.R, self.min_dist, self.max_dist,
+                _lib.ptr(self.fit_result), _lib.ptr(self.spline_y), bias, _lib.ptr(p_out))
+        if q_out is not None:
+            if not with_hist:
+                raise ValueError("the K4 -> K5 hand-over needs the histogram (with_hist=True)")
+            ws = self._bh_workspace(shard.n)
+            _lib.check(self.lib.bbk_pvalues_bh(*args, _lib.ptr(self.p_hist), _lib.ptr(q_out), _lib.ptr(ws), ws.numel(),
+                                               _lib.stream_ptr()), "bbk_pvalues_bh")
+        else:
+            _lib.check(self.lib.bbk_pvalues(*args, _lib.ptr(self.p_hist) if with_hist else None, _lib.stream_ptr()), "bbk_pvalues")
+        self.launches += 1
+
+    def qvalues(self, p, q, n_tests=-1, use_hist=False, rank=None, mode=_lib.BH_UNSORTED, prepared=False):
+        m = int(p.numel())
+        ws = self._bh_workspace(m)
+        if prepared:
+            if rank is not None or mode != _lib.BH_UNSORTED or not use_hist:
+                raise ValueError("prepared q-values: unsorted mode with the K4 histogram, no ranks")
+            _lib.check(self.lib.bbk_bh_qvalues_prepared(_lib.ptr(p), m, int(n_tests), _lib.ptr(self.p_hist), _lib.ptr(q),
+                                                        _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_bh_qvalues_prepared")
+            self.launches += 6       # init, threshold, list filter, compact (returns at once), rank, ones fix
+            return
         _lib.check(self.lib.bbk_bh_qvalues(_lib.ptr(p), m, int(n_tests), mode, _lib.ptr(self.p_hist) if use_hist else None,
-                                           _lib.ptr(q), _lib.ptr(rank), _lib.ptr(self.bh_ws), self.bh_ws.numel(),
+                                           _lib.ptr(q), _lib.ptr(rank), _lib.ptr(ws), ws.numel(),
                                            _lib.stream_ptr()), "bbk_bh_qvalues")
         # init, [coarse histogram], threshold, compact, rank (one cooperative launch), ones fix
         self.launches += (4 if mode == _lib.BH_POSITIONAL else 6 - (1 if use_hist else 0))
@@ -256,13 +276,13 @@ class PassEngine(object):
         fuse_hist = q_outs is not None and len(shards) == 1
         if fuse_hist:
             self.p_hist.zero_()
-        for sh, p in zip(shards, p_outs):
+        for i, (sh, p) in enumerate(zip(shards, p_outs)):
             if sh.n:
-                self.pvalues(sh, p, with_hist=fuse_hist)
+                self.pvalues(sh, p, with_hist=fuse_hist, q_out=q_outs[i] if fuse_hist else None)
         if q_outs is not None:
             for p, q in zip(p_outs, q_outs):
                 if p.numel():
-                    self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist)
+                    self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist, prepared=fuse_hist)
 
     def run(self, shards, p_outs, q_outs=None, n_tests=-1, group=None):
         """The whole pass over `shards`; p_outs[i] (float64, len shards[i].n) receives the p-values.
@@ -276,13 +296,13 @@ class PassEngine(object):
         fuse_hist = q_outs is not None and len(shards) == 1
         if fuse_hist:
             self.p_hist.zero_()
-        for sh, p in zip(shards, p_outs):
+        for i, (sh, p) in enumerate(zip(shards, p_outs)):
             if sh.n:
-                self.pvalues(sh, p, with_hist=fuse_hist)
+                self.pvalues(sh, p, with_hist=fuse_hist, q_out=q_outs[i] if fuse_hist else None)
         if q_outs is not None:
             for p, q in zip(p_outs, q_outs):
                 if p.numel():
-                    self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist)
+                    self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist, prepared=fuse_hist)
 
 
 class HostPipeline(object):

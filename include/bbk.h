@@ -153,6 +153,20 @@ int bbk_pvalues(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_m
                 int64_t max_dist, const BbkFitResult* d_fit, const double* d_spline_y, const BbkBiasTable* bias,
                 double* d_p, int64_t* d_p_hist, void* stream);
 
+/* K4 with the hand-over to K5 (one shard whose q-values are wanted, ranked on its own): besides p and the histogram,
+ * K4 stores q = 1.0 (NaN where p is NaN) for every record and lists (key, index) of the records with p < 2^-5 inside
+ * the q-value workspace.  bbk_bh_qvalues_prepared then ranks from that list - a few MB - instead of re-reading p
+ * and re-writing q (16 B/pair); K4 is not bound by DRAM, so the extra 8 B/pair it writes are free.  If the
+ * saturation bucket lies at or above 2^-5 (a large share of significant rows) the prepared call falls back to the
+ * full pass by itself: results are identical to bbk_pvalues + bbk_bh_qvalues in every case.
+ * d_p_hist must be zeroed (all BBK_PHIST_LEN entries) before the call; d_bh_workspace: bbk_bh_workspace_bytes(n_pairs),
+ * and it must reach bbk_bh_qvalues_prepared untouched. */
+int bbk_pvalues_bh(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                   const int32_t* d_count, int64_t n_pairs, int32_t shard_chrom, int64_t resolution, int64_t min_dist,
+                   int64_t max_dist, const BbkFitResult* d_fit, const double* d_spline_y, const BbkBiasTable* bias,
+                   double* d_p, int64_t* d_p_hist, double* d_q, void* d_bh_workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K5  Benjamini-Hochberg q-values as the reference computes them: a FORWARD running max of
  *     min(p * N / rank, 1)   (fithic.py:466-487, blueberry.pyx:40-75) - not the textbook reverse
@@ -168,6 +182,9 @@ int bbk_pvalues(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_m
 size_t bbk_bh_workspace_bytes(int64_t m);
 int bbk_bh_qvalues(const double* d_p, int64_t m, int64_t n_tests, int32_t mode, const int64_t* d_p_hist,
                    double* d_q, int64_t* d_rank, void* d_workspace, size_t workspace_bytes, void* stream);
+/* after bbk_pvalues_bh on the same d_p / d_p_hist / d_q / workspace: BBK_BH_UNSORTED without ranks */
+int bbk_bh_qvalues_prepared(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist, double* d_q,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5, genome-wide across ranks: the reference's q-value step ranks the p-values of ALL chromosomes

@@ -251,3 +251,47 @@ def test_host_pipeline_matches_serial_passes():
     assert (want[0][0][:100000] != want[1][0][:100000]).any()
     with pytest.raises(ValueError):
         pipe.submit(libs[0][0], libs[0][1], libs[0][2], torch.empty(libs[0][0].numel(), dtype=torch.float64))
+
+
+@pytest.mark.parametrize("n_tests", [-1, 25])
+def test_k4_handover_matches_two_pass_qvalues(n_tests):
+    """bbk_pvalues_bh + bbk_bh_qvalues_prepared (K4 pre-fills q and lists the small p) against bbk_pvalues +
+    bbk_bh_qvalues, bit for bit.  n_tests = 25 pushes the saturation bucket above 2^-5, so the prepared call has
+    to fall back to the full pass on its own (and q of the p == 1.0 rows drops below 1)."""
+    import torch
+    from blueberry_b200 import _lib
+    from blueberry_b200.engine import BiasTables, PassEngine, Shard
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    R, nb, K = 5000, 7001, 300
+    P = int(lib.bbk_synth_n_pairs(nb, K))
+    assert P % 4 != 0                                 # the last records go through the tail kernel
+    rng = np.random.default_rng(9)
+    bias_host = np.exp(rng.normal(0.0, 0.25, size=nb))
+    bias_dev = torch.from_numpy(bias_host).to(dev)
+    cols = [torch.empty(P, dtype=torch.int32, device=dev) for _ in range(3)]
+    _lib.check(lib.bbk_synth_contacts(nb, K, R, 120.0, 1.08, 77, _lib.ptr(bias_dev), _lib.ptr(cols[0]), _lib.ptr(cols[1]),
+                                      _lib.ptr(cols[2]), _lib.stream_ptr()), "synth")
+    eng = PassEngine(R, 100, 0, K * R, nb, dev)
+    eng.set_fragments([nb], [(nb - 1) * R])
+    eng.set_bias(BiasTables([np.where((bias_host < 0.5) | (bias_host > 2), -1.0, bias_host)], [R // 2], dev))
+    sh = Shard(*cols)
+    eng.hist([sh]); eng.allreduce_stats(None); eng.fit()
+    p0, q0, p1, q1 = (torch.empty(P + 3, dtype=torch.float64, device=dev)[:P] for _ in range(4))
+    eng.p_hist.zero_()
+    eng.pvalues(sh, p0, with_hist=True)
+    eng.qvalues(p0, q0, n_tests=n_tests, use_hist=True)
+    hist0 = eng.p_hist.clone()
+    eng.p_hist.zero_()
+    q1.fill_(-7.0)
+    eng.pvalues(sh, p1, with_hist=True, q_out=q1)
+    eng.qvalues(p1, q1, n_tests=n_tests, use_hist=True, prepared=True)
+    torch.cuda.synchronize()
+    assert torch.equal(p0.view(torch.int64), p1.view(torch.int64))
+    assert torch.equal(hist0[:4098], eng.p_hist[:4098])
+    assert torch.equal(q0.view(torch.int64), q1.view(torch.int64))
+    use_list = int(eng.bh_ws[100:104].view(torch.int32)[0])
+    assert use_list == (1 if n_tests < 0 else 0)
+    if n_tests > 0:
+        assert float(q1[p1 == 1.0][0]) < 1.0
+    assert int((q1 < 1.0).sum()) > 1000
