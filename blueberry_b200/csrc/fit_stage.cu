@@ -47,7 +47,7 @@ struct FitShared {
     double s, min_x, max_x;
     long long t[7];
     long long slice_tot[FIT_THREADS];
-    int n_blocks;
+    double cmax[FIT_THREADS], cmin[FIT_THREADS];      // antitonic regression: extrema of each thread's chunk
 };
 
 __device__ __forceinline__ double* pick(double* pool, size_t pool_doubles, size_t need, double* global_fallback) {
@@ -268,22 +268,19 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         }
         for (int i = tid; i < L; i += FIT_THREADS) vraw[i] = P.spline_raw[i];
         __syncthreads();
-        if (tid == 0) {
-            sh.t[4] = clock64();
-            sh.n_blocks = bbk_antitonic_pava_blocks(vraw, L, wmean, wcount, wstart);
+        // pool-adjacent-violators, cut into the pieces between safe cuts (fit_stage.h): chunk extrema, piece starts, then
+        // every thread runs the pieces that start in its chunk and writes their block means straight to spline_y
+        if (tid == 0) sh.t[4] = clock64();
+        bbk_pava_phase1(vraw, L, FIT_THREADS, tid, sh.cmax, sh.cmin);
+        if (tid == FIT_THREADS - 1) {
             double res = 0.0;
             for (int j = 0; j < m; ++j) res = res + rterm[j];
             P.result->residual = res;
         }
         __syncthreads();
-        {   // expand the blocks: element i of the reversed view belongs to the last block with start <= i
-            const int nb = sh.n_blocks;
-            for (int i = tid; i < L; i += FIT_THREADS) {
-                int lo = 0, hi = nb - 1;
-                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (wstart[mid] <= i) lo = mid; else hi = mid - 1; }
-                P.spline_y[L - 1 - i] = wmean[lo];
-            }
-        }
+        bbk_pava_phase2(vraw, L, FIT_THREADS, tid, sh.cmax, sh.cmin, wcount, wstart);
+        __syncthreads();
+        bbk_pava_phase3(vraw, L, FIT_THREADS, tid, wstart, wmean, wcount, P.spline_y);
         for (int i = L + tid; i < P.nkeys; i += FIT_THREADS) { P.spline_y[i] = 0.0; P.spline_raw[i] = 0.0; }
     }
     __syncthreads();

@@ -537,8 +537,7 @@ BBK_HD int bbk_antitonic_pava_blocks(const double* v, int L, double* wmean, doub
     double xb_prev = v[L - 1], wb_prev = 1.0;
     wmean[0] = xb_prev;
     wcount[0] = 1.0;
-    start[0] = 0;
-    start[1] = 1;
+    if (start) { start[0] = 0; start[1] = 1; }
     double nxt = L > 1 ? v[L - 2] : 0.0;          // element i of the reversed view, loaded one step ahead
     for (int i = 1; i < L; ++i) {
         b += 1;
@@ -566,9 +565,82 @@ BBK_HD int bbk_antitonic_pava_blocks(const double* v, int L, double* wmean, doub
         }
         wmean[b] = xb_prev = xb;
         wcount[b] = wb_prev = wb;
-        start[b + 1] = i + 1;
+        if (start) start[b + 1] = i + 1;
     }
     return b + 1;
+}
+
+// The same regression cut into independent pieces.  In the reversed (non-decreasing) view u, pool-adjacent-
+// violators never merges across a position where every value on the left is below every value on the right, so
+// the pieces between such cuts can be run separately - each with exactly the operations, in exactly the order,
+// that the one-pass algorithm would have spent on it - and a smooth, mostly monotone curve falls into thousands
+// of one-element pieces plus a few wiggles.  A block mean can exceed the largest pooled value by accumulated
+// rounding, so a cut needs a relative gap of 1e-9 (the rounding of <= 1e5 additions is below 2e-11); where the
+// gap is smaller no cut is made, which is always exact.
+// `nt` workers each own a contiguous chunk of u; phases are separated by barriers on the device (the host
+// driver below runs the workers of a phase one after the other).
+//   phase 1: chunk extrema                    -> cmax[t], cmin[t]
+//   phase 2: flags[i] = 1 where a piece starts (uses wcount as scratch)
+//   phase 3: every worker runs the pieces that START in its chunk and writes out[]
+BBK_HD void bbk_pava_chunk(int L, int nt, int t, int* a, int* b) {
+    const int per = (L + nt - 1) / nt;
+    int lo = t * per, hi = lo + per;
+    if (lo > L) lo = L;
+    if (hi > L) hi = L;
+    *a = lo; *b = hi;
+}
+BBK_HD void bbk_pava_phase1(const double* v, int L, int nt, int t, double* cmax, double* cmin) {
+    int a, b;
+    bbk_pava_chunk(L, nt, t, &a, &b);
+    double mx = -INFINITY, mn = INFINITY;
+    for (int i = a; i < b; ++i) { double u = v[L - 1 - i]; mx = u > mx ? u : mx; mn = u < mn ? u : mn; }
+    cmax[t] = mx; cmin[t] = mn;
+}
+BBK_HD void bbk_pava_phase2(const double* v, int L, int nt, int t, const double* cmax, const double* cmin, double* wcount, int32_t* flags) {
+    int a, b;
+    bbk_pava_chunk(L, nt, t, &a, &b);
+    if (a >= b) return;
+    double pm = -INFINITY, sm = INFINITY;
+    for (int k = 0; k < t; ++k) pm = cmax[k] > pm ? cmax[k] : pm;
+    for (int k = t + 1; k < nt; ++k) sm = cmin[k] < sm ? cmin[k] : sm;
+    for (int i = b - 1; i >= a; --i) {            // wcount[i] = min of u[i+1 ..]
+        wcount[i] = sm;
+        double u = v[L - 1 - i];
+        sm = u < sm ? u : sm;
+    }
+    if (a == 0) flags[0] = 1;
+    for (int i = a; i < b; ++i) {                 // pm = max of u[.. i]
+        double u = v[L - 1 - i];
+        pm = u > pm ? u : pm;
+        if (i + 1 < L) {
+            double right = wcount[i];
+            flags[i + 1] = (right - pm > 1e-9 * (fabs(pm) + fabs(right))) ? 1 : 0;
+        }
+    }
+}
+BBK_HD void bbk_pava_phase3(const double* v, int L, int nt, int t, const int32_t* flags, double* wmean, double* wcount, double* out) {
+    int a, b;
+    bbk_pava_chunk(L, nt, t, &a, &b);
+    for (int s = a; s < b; ++s) {
+        if (!flags[s]) continue;
+        int e = s + 1;
+        while (e < L && !flags[e]) ++e;
+        if (e == s + 1) { out[L - 1 - s] = v[L - 1 - s]; continue; }
+        const int nb = bbk_antitonic_pava_blocks(v + (L - e), e - s, wmean + s, wcount + s, (int32_t*)0);
+        int j = s;
+        for (int blk = 0; blk < nb; ++blk) {
+            const double val = wmean[s + blk];
+            const int len = (int)wcount[s + blk];
+            for (int k = 0; k < len; ++k, ++j) out[L - 1 - j] = val;
+        }
+    }
+}
+// host driver (tests/host_harness): cmax / cmin hold nt doubles each
+BBK_HD void bbk_antitonic_pava_segmented(const double* v, int L, double* out, double* wmean, double* wcount, int32_t* flags,
+                                         double* cmax, double* cmin, int nt) {
+    for (int t = 0; t < nt; ++t) bbk_pava_phase1(v, L, nt, t, cmax, cmin);
+    for (int t = 0; t < nt; ++t) bbk_pava_phase2(v, L, nt, t, cmax, cmin, wcount, flags);
+    for (int t = 0; t < nt; ++t) bbk_pava_phase3(v, L, nt, t, flags, wmean, wcount, out);
 }
 
 BBK_HD void bbk_antitonic_pava(const double* v, int L, double* out, double* wmean, double* wcount, int32_t* start) {

@@ -60,4 +60,11 @@ void th_antitonic(const double* v, int L, double* out) {
     bbk_antitonic_pava(v, L, out, wm.data(), wc.data(), st.data());
 }
 
+// the cut-into-pieces variant the kernel runs, `nt` emulated workers
+void th_antitonic_segmented(const double* v, int L, int nt, double* out) {
+    std::vector<double> wm(L + 1), wc(L + 1), cmax(nt), cmin(nt);
+    std::vector<int32_t> flags(L + 2, 0);
+    bbk_antitonic_pava_segmented(v, L, out, wm.data(), wc.data(), flags.data(), cmax.data(), cmin.data(), nt);
+}
+
 }

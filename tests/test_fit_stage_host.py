@@ -103,6 +103,45 @@ def test_antitonic_regression_is_bit_identical_to_sklearn(harness):
         assert np.array_equal(out, ref)
 
 
+def test_segmented_antitonic_regression_is_bit_identical_to_sklearn(harness):
+    """The kernel's variant (pieces between safe cuts, run by 128 workers): smooth mostly-monotone curves, noisy ones,
+    ties, plateaus, near-ties one ulp apart (no cut may be made there), increasing input (one big pool), NaN-free edge sizes."""
+    from sklearn.isotonic import IsotonicRegression
+    rng = np.random.default_rng(4)
+    cases = []
+    for trial in range(80):
+        L = int(rng.integers(1, 3000))
+        base = 1e-3 * (np.arange(L) + 1.0) ** -1.08
+        kind = trial % 8
+        if kind == 0:
+            v = base                                                             # strictly decreasing: all singletons
+        elif kind == 1:
+            v = base * (1 + 0.2 * rng.normal(0, 1, L) * (rng.random(L) < 0.3))   # scattered wiggles
+        elif kind == 2:
+            v = base * (1 + 0.02 * np.sin(np.arange(L) / 7.0))                   # smooth oscillation
+        elif kind == 3:
+            v = base.copy(); v[rng.integers(0, L, L // 3 + 1)] = v[0]            # many exact ties
+        elif kind == 4:
+            v = np.sort(rng.random(L))                                           # increasing: one pool
+        elif kind == 5:
+            v = np.repeat(base[:max(L // 5, 1)], 5)[:L]                          # plateaus (ties pool)
+            L = len(v)
+        elif kind == 6:
+            v = base.copy()                                                      # neighbours one ulp apart, both ways
+            k = rng.integers(0, L, L // 4 + 1)
+            v[k] = np.nextafter(v[np.maximum(k - 1, 0)], rng.choice([0.0, 1.0], len(k)))
+        else:
+            v = rng.normal(0, 1, L)                                              # noise, negative values
+        cases.append(np.ascontiguousarray(v, dtype=np.float64))
+    for v in cases:
+        L = len(v)
+        ref = IsotonicRegression(increasing=False).fit_transform(np.arange(L), v)
+        for nt in (128, 7, 1):
+            out = np.full(L, -1.0)
+            harness.th_antitonic_segmented(_p(v), L, nt, _p(out))
+            assert np.array_equal(out, ref), (L, nt)
+
+
 @pytest.mark.parametrize("name", PASS_CASES)
 def test_equal_occupancy_binning_is_bit_identical_to_the_reference(name, harness):
     from oracle import fithic_oracle as fo
