@@ -1,0 +1,67 @@
+"""ctypes binding of libbbkio.so (include/bbk_io.h): the host-side file formats either side of the pass."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libbbkio.so")
+
+_vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+SIGNATURES = {
+    "bbkio_last_error": (None, [ctypes.c_char_p, ctypes.c_size_t]),
+    "bbkio_write_significances": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), _i32, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _i64, _i32, _i32, ctypes.POINTER(_i64)]),
+    "bbkio_format_double": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
+}
+_lib = None
+
+
+class BbkIoError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BbkIoError("%s not found: build it with `python -m blueberry_b200.build`" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def write_significances(path, chrom_names, chr1, mid1, chr2, mid2, count, p, q=None, threads=0, level=1):
+    """fithic.py:410-435 on arrays; returns the number of rows written (those with p <= 1)."""
+    lib = load()
+    n = len(p)
+    names = (ctypes.c_char_p * len(chrom_names))(*[str(s).encode() for s in chrom_names])
+    c1 = None if chr1 is None else np.ascontiguousarray(chr1, dtype=np.int32)
+    c2 = None if chr2 is None else np.ascontiguousarray(chr2, dtype=np.int32)
+    m1, m2 = np.ascontiguousarray(mid1, dtype=np.int64), np.ascontiguousarray(mid2, dtype=np.int64)
+    cnt = np.ascontiguousarray(count, dtype=np.int64)
+    pp = np.ascontiguousarray(p, dtype=np.float64)
+    qq = None if q is None else np.ascontiguousarray(q, dtype=np.float64)
+    rows = _i64(0)
+    rc = lib.bbkio_write_significances(os.fsencode(path), names, len(chrom_names), _ptr(c1), _ptr(m1), _ptr(c2), _ptr(m2),
+                                       _ptr(cnt), _ptr(pp), _ptr(qq), n, int(threads), int(level), ctypes.byref(rows))
+    if rc != 0:
+        buf = ctypes.create_string_buffer(512)
+        lib.bbkio_last_error(buf, 512)
+        raise BbkIoError("bbkio_write_significances failed (code %d): %s" % (rc, buf.value.decode(errors="replace")))
+    return int(rows.value)
+
+
+def format_double(x):
+    buf = ctypes.create_string_buffer(64)
+    n = load().bbkio_format_double(float(x), buf)
+    return buf.raw[:n].decode()

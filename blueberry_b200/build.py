@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libbbk.so")
+IO_LIB = os.path.join(LIBDIR, "libbbkio.so")      # host-side file formats (include/bbk_io.h): g++ + zlib, no CUDA
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--threads", "0"]
 # (source, extra flags).  fit_stage.cu: FMA contraction off - its knot search must round like the CPU library.
@@ -42,8 +43,22 @@ def nvcc_path():
     return "nvcc"
 
 
+def build_io(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    src = os.path.join(CSRC, "io_host.cpp")
+    hdr = os.path.join(os.path.dirname(HERE), "include", "bbk_io.h")
+    if not force and os.path.exists(IO_LIB) and os.path.getmtime(IO_LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return IO_LIB
+    cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-o", IO_LIB, src, "-lz", "-lpthread"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return IO_LIB
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
+    build_io(force, verbose)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
         return LIB
     nvcc = nvcc_path()

@@ -503,17 +503,9 @@ def fit_spline(mainDic, x, y, yerr, infilename, outfilename, biasDic, resolution
 
 def _write_significances(path, chroms, c1, m1, c2, m2, cnt, p, q):
     """fithic.py:410-435: header + one row per record with p_val <= 1; q column is the literal -1
-    unless q-values were asked for."""
-    import pandas as pd
-    keep = p <= 1
-    names = np.asarray(chroms.names, dtype=object)
-    df = pd.DataFrame({
-        "chr1": names[c1[keep]], "fragmentMid1": m1[keep], "chr2": names[c2[keep]], "fragmentMid2": m2[keep],
-        "contactCount": cnt[keep], "p-value": p[keep],
-        "q-value": (np.full(int(keep.sum()), -1, dtype=np.int64) if q is None else q[keep]),
-    })
-    with gzip.open(path, "wt", compresslevel=1) as fh:
-        df.to_csv(fh, sep="\t", index=False, lineterminator="\n")
+    unless q-values were asked for.  Formatted and compressed by all host cores (libbbkio.so, include/bbk_io.h)."""
+    from . import _io
+    _io.write_significances(path, list(chroms.names), c1, m1, c2, m2, cnt, p, q)
 
 
 def fithic(libname, resolution, n_bins, min_dist, max_dist, n_passes, interactions, frags, biases, verbose,

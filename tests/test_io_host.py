@@ -1,0 +1,90 @@
+"""libbbkio.so (include/bbk_io.h): the significances writer against a line-by-line restatement of fithic.py:410-435.
+Host code only - these tests need no GPU."""
+import ctypes
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def io():
+    from blueberry_b200 import build, _io
+    build.build_io()
+    _io.load()
+    return _io
+
+
+def _reference_text(names, c1, m1, c2, m2, cnt, p, q):
+    """What fithic.py:410-435 writes (the reference never has q: it writes -1; with q we format it like p)."""
+    out = ["chr1\tfragmentMid1\tchr2\tfragmentMid2\tcontactCount\tp-value\tq-value\n"]
+    for i in range(len(p)):
+        if p[i] <= 1:
+            out.append("{}\t{}\t{}\t{}\t{}\t{}\t{}\n".format(names[c1[i]], m1[i], names[c2[i]], m2[i], cnt[i], p[i],
+                                                            -1 if q is None else q[i]))
+    return "".join(out)
+
+
+def test_header_symbols_are_exported(io):
+    text = open(os.path.join(ROOT, "include", "bbk_io.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(bbkio_[a-z0-9_]+)\s*\(", text)))
+    assert names == sorted(io.SIGNATURES)
+    lib = ctypes.CDLL(io.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n)
+
+
+def test_double_formatting_is_numpys(io):
+    rng = np.random.default_rng(1)
+    vals = [0.0, -0.0, 1.0, 0.5, 1e-4, 9.999e-5, 1e-5, 1e16, 9999999999999998.0, 1e15, 123456789.123, 5e-324,
+            1.7976931348623157e308, 2.2250738585072014e-308, 0.1, 1 / 3, 1e22, 1e-300, 0.0001234, 1e-7, 3.0e-310, float("nan")]
+    vals += list(np.exp(rng.uniform(-700, 700, 20000)))
+    vals += list(rng.random(20000))
+    bits = rng.integers(0, 2 ** 63 - 1, 20000, dtype=np.int64).view(np.float64)
+    vals += [float(x) for x in bits if np.isfinite(x)]
+    for x in vals:
+        assert io.format_double(x) == "{}".format(np.float64(x)), repr(x)
+
+
+@pytest.mark.parametrize("n,threads,with_q", [(0, 1, False), (1, 1, True), (5000, 1, False), (300001, 3, True), (300001, 0, False)])
+def test_writer_matches_the_reference_loop(io, tmp_path, n, threads, with_q):
+    rng = np.random.default_rng(n + threads)
+    names = ["chr1", "chrX", "chr10_random"]
+    c1 = rng.integers(0, 3, n).astype(np.int32)
+    c2 = rng.integers(0, 3, n).astype(np.int32)
+    m1 = rng.integers(0, 250_000_000, n)
+    m2 = m1 + rng.integers(-5, 2000, n) * 5000
+    cnt = rng.integers(0, 5000, n)
+    p = np.exp(rng.uniform(-720, 0.0, n))
+    p[rng.random(n) < 0.3] = 1.0
+    p[rng.random(n) < 0.05] = np.nan               # rows the reference drops (fithic.py:434)
+    p[rng.random(n) < 0.01] = 1.5
+    p[rng.random(n) < 0.01] = 0.0
+    q = np.minimum(p * 3.7, 1.0) if with_q else None
+    path = str(tmp_path / "out.significances.txt.gz")
+    rows = io.write_significances(path, names, c1, m1, c2, m2, cnt, p, q, threads=threads, level=1)
+    want = _reference_text(names, c1, m1, c2, m2, cnt, p, q)
+    with gzip.open(path, "rt") as fh:
+        got = fh.read()
+    assert got == want
+    assert rows == int((p <= 1).sum())
+    if n:
+        import pandas as pd            # what FithicContactMap does with the file (datatypes.pyx:314)
+        m = pd.read_csv(path, sep="\t", usecols=[1, 3, 4, 5, 6], engine="c", dtype="float64").values
+        assert m.shape == (rows, 5)
+
+
+def test_single_chromosome_shortcut_and_errors(io, tmp_path):
+    p = np.array([0.5, np.nan, 1.0])
+    path = str(tmp_path / "one.gz")
+    assert io.write_significances(path, ["chr7"], None, [10, 20, 30], None, [15, 25, 35], [1, 2, 0], p) == 2
+    assert gzip.open(path, "rt").read().splitlines()[1:] == ["chr7\t10\tchr7\t15\t1\t0.5\t-1", "chr7\t30\tchr7\t35\t0\t1.0\t-1"]
+    with pytest.raises(io.BbkIoError):
+        io.write_significances(str(tmp_path / "nodir" / "x.gz"), ["chr7"], None, [1], None, [2], [3], np.array([0.1]))
+    with pytest.raises(io.BbkIoError):
+        io.write_significances(path, ["chr7"], np.array([1], np.int32), [1], np.array([0], np.int32), [2], [3], np.array([0.1]))
