@@ -200,47 +200,54 @@ __global__ void __launch_bounds__(BH_THREADS) bh_compact_kernel(const double* p,
 }
 
 // prepared mode: the candidates are among the records K4 flagged (p < BBK_SMALL_P): m/8 bytes of flags plus one
-// sector per flagged record instead of the 16 B/pair pass.  One flag word per thread; the lanes of a warp pop their
-// set bits in rounds so that each round costs one atomic on the candidate counter.
+// sector per flagged record instead of the 16 B/pair pass.  One flag word per thread and grid step; every set bit is an
+// independent scattered read.  Candidates are staged in shared memory and appended with ONE global atomic per CTA
+// flush: a warp-aggregated atomic per round was 1e5 same-address atomics on cfg2 - 100 us on their own.
+constexpr int MF_CAP = 2048;
 __global__ void __launch_bounds__(BH_THREADS) bh_mask_filter_kernel(BhState* st, const unsigned* mask, const double* p, long long m,
                                                                     unsigned long long* keys, unsigned* idx) {
+    __shared__ unsigned long long s_keys[MF_CAP];
+    __shared__ unsigned s_idx[MF_CAP];
+    __shared__ unsigned s_cnt;
+    __shared__ unsigned long long s_base;
     if (!st->use_list) return;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     const unsigned long long tau = st->tau_key;
     const long long n_words = ((m >> 2) + 31) / 32 * 4;      // 4 words per (started) block of 32 four-record groups
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n_iter = (n_words + 1 + stride - 1) / stride;       // + 1: a pseudo word for the last m % 4 records
-    const int lane = threadIdx.x & 31;
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long it = 0; it < n_iter; ++it, w += stride) {
-        unsigned bits = 0;
-        long long rec0 = 0;
-        int step = 4;
-        if (w < n_words) { bits = mask[w]; rec0 = (w >> 2) * 128 + (w & 3); }
-        else if (w == n_words) { bits = (1u << (m & 3)) - 1; rec0 = (m >> 2) << 2; step = 1; }     // unflagged tail: look at all
-        while (__any_sync(0xffffffffu, bits != 0)) {
-            bool cand = false;
-            unsigned long long k = 0;
-            long long rec = 0;
-            if (bits) {
+    for (long long it = 0; it <= n_iter; ++it, w += stride) {
+        if (it < n_iter) {
+            unsigned bits = 0;
+            long long rec0 = 0;
+            int step = 4;
+            if (w < n_words) { bits = mask[w]; rec0 = (w >> 2) * 128 + (w & 3); }
+            else if (w == n_words) { bits = (1u << (m & 3)) - 1; rec0 = (m >> 2) << 2; step = 1; }     // unflagged tail: look at all
+            while (bits) {
                 const int l = __ffs(bits) - 1;
                 bits &= bits - 1;
-                rec = rec0 + (long long)step * l;
+                const long long rec = rec0 + (long long)step * l;
                 const double v = p[rec];
-                k = bbk_key_of(v);
-                cand = !isnan(v) && v != 1.0 && k < tau;
-            }
-            const unsigned vote = __ballot_sync(0xffffffffu, cand);
-            if (vote) {
-                unsigned long long base = 0;
-                if (lane == __ffs(vote) - 1) base = atomicAdd(&st->n_cand, (unsigned long long)__popc(vote));
-                base = __shfl_sync(0xffffffffu, base, __ffs(vote) - 1);
-                if (cand) {
-                    const unsigned long long pos = base + __popc(vote & ((1u << lane) - 1));
-                    keys[pos] = k;
-                    idx[pos] = (unsigned)rec;
+                const unsigned long long k = bbk_key_of(v);
+                if (!isnan(v) && v != 1.0 && k < tau) {
+                    const unsigned pos = atomicAdd(&s_cnt, 1u);
+                    if (pos < MF_CAP) { s_keys[pos] = k; s_idx[pos] = (unsigned)rec; }
+                    else { const unsigned long long g = atomicAdd(&st->n_cand, 1ull); keys[g] = k; idx[g] = (unsigned)rec; }   // stage full
                 }
             }
         }
+        __syncthreads();
+        const unsigned staged = s_cnt < (unsigned)MF_CAP ? s_cnt : (unsigned)MF_CAP;
+        if (staged >= MF_CAP / 2 || (it == n_iter && staged > 0)) {      // CTA-uniform
+            if (threadIdx.x == 0) s_base = atomicAdd(&st->n_cand, (unsigned long long)staged);
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < staged; i += blockDim.x) { keys[s_base + i] = s_keys[i]; idx[s_base + i] = s_idx[i]; }
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = 0;
+        }
+        __syncthreads();
     }
 }
 
