@@ -230,7 +230,7 @@ def run_ours(args, out_fd):
 
     def bh():
         if genome_q:      # all-reduce of the p histogram + all-gather of the candidate keys (2 host syncs)
-            eng.qvalues_global(p, q, n_tests=-1, group=group, hist=eng.p_hist)
+            eng.qvalues_global(p, q, n_tests=-1, group=group, hist=eng.p_hist, prepared=True)
         else:             # K4 pre-filled q and listed the small p (bbk_pvalues_bh): no second pass over p
             eng.qvalues(p, q, n_tests=-1, use_hist=True, prepared=True)
 
@@ -247,7 +247,7 @@ def run_ours(args, out_fd):
             eng.hist_excluding([shard], [p_first], p_outlier)
             eng.allreduce_stats(group)
             eng.fit()
-        eng.pvalues(shard, p, with_hist=True, q_out=None if genome_q else q)
+        eng.pvalues(shard, p, with_hist=True, q_out=q)
         bh()
 
     def barrier():
@@ -295,7 +295,7 @@ def run_ours(args, out_fd):
         ev[0].record(); eng.hist([shard])
         ev[1].record(); eng.allreduce_stats(group)
         ev[2].record(); eng.fit()
-        ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True, q_out=None if genome_q else q)
+        ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True, q_out=q)
         ev[4].record(); bh()
         ev[5].record()
         torch.cuda.synchronize()

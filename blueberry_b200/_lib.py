@@ -65,6 +65,7 @@ SIGNATURES = {
     "bbk_bh_qvalues": (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bbk_p_hist": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "bbk_bh_select": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bbk_bh_select_prepared": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bbk_bh_rank_gathered": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bbk_bh_scatter": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "bbk_bh_fix_ones": (ctypes.c_int, [_vp, _i64, _f64, _vp, _vp]),

@@ -875,31 +875,51 @@ extern "C" int bbk_bh_qvalues_prepared(const double* d_p, int64_t m, int64_t n_t
 //   all-reduce(p_hist)  ->  bbk_bh_select  ->  all-gather(candidate keys)  ->  bbk_bh_rank_gathered
 //   ->  bbk_bh_scatter (and bbk_bh_fix_ones in the rare case q(p == 1) < 1)
 // ---------------------------------------------------------------------------------------------------
-extern "C" int bbk_bh_select(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
-                             uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
-                             void* stream) {
+static int bh_select_impl(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                          uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
+                          bool prepared, void* stream) {
     BBK_REQUIRE(m >= 0 && m < (1ll << 32), "bbk_bh_select: m must be in [0, 2^32)");
     BBK_REQUIRE(d_p_hist_global && d_state && d_workspace, "bbk_bh_select: null pointer");
     BBK_REQUIRE(m == 0 || (d_p && d_q && d_keys && d_idx), "bbk_bh_select: null array");
     BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_select: workspace must be 256-byte aligned");
     const int G = sort_blocks();
     BhLayout L;
-    size_t need = bh_layout(d_workspace, 0, G, &L);
+    // prepared: the workspace is the one bbk_pvalues_bh left the flag bits in (laid out for m records)
+    size_t need = bh_layout(d_workspace, prepared ? m : 0, G, &L);
     if (workspace_bytes < need) { bbk_set_error("bbk_bh_select: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return BBK_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    const int sms = bbk_num_sms();
     bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist_global, n_tests);
     BBK_CHECK_LAUNCH("bh_init_kernel");
-    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, 0);
+    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, prepared ? 1 : 0);
     BBK_CHECK_LAUNCH("bh_threshold_kernel");
     if (m > 0) {
+        if (prepared) {
+            long long words = ((m >> 2) + 31) / 32 * 4 + 1, wantw = (words + BH_THREADS - 1) / BH_THREADS;
+            int gridw = (int)(wantw < (long long)sms * 8 ? wantw : (long long)sms * 8);
+            bh_mask_filter_kernel<<<gridw, BH_THREADS, 0, st>>>(L.st, L.idx[1], d_p, m, (unsigned long long*)d_keys, d_idx);
+            BBK_CHECK_LAUNCH("bh_mask_filter_kernel");
+        }
         long long want = (m + BH_THREADS - 1) / BH_THREADS;
-        int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
+        int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
         bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, (unsigned long long*)d_keys, d_idx, 0, nullptr);
         BBK_CHECK_LAUNCH("bh_compact_kernel");
     }
     export_state_kernel<<<1, 1, 0, st>>>(L.st, (unsigned long long*)d_state);
     BBK_CHECK_LAUNCH("export_state_kernel");
     return BBK_OK;
+}
+
+extern "C" int bbk_bh_select(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                             uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
+                             void* stream) {
+    return bh_select_impl(d_p, m, n_tests, d_p_hist_global, d_q, d_keys, d_idx, d_state, d_workspace, workspace_bytes, false, stream);
+}
+
+extern "C" int bbk_bh_select_prepared(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                                      uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace,
+                                      size_t workspace_bytes, void* stream) {
+    return bh_select_impl(d_p, m, n_tests, d_p_hist_global, d_q, d_keys, d_idx, d_state, d_workspace, workspace_bytes, true, stream);
 }
 
 extern "C" int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, const uint64_t* d_state, double* d_q_all,

@@ -199,12 +199,13 @@ class PassEngine(object):
         # init, [coarse histogram], threshold, compact, rank (one cooperative launch), ones fix
         self.launches += (4 if mode == _lib.BH_POSITIONAL else 6 - (1 if use_hist else 0))
 
-    def qvalues_global(self, p, q, n_tests=-1, group=None, hist=None):
+    def qvalues_global(self, p, q, n_tests=-1, group=None, hist=None, prepared=False):
         """Genome-wide Benjamini-Hochberg across the ranks of `group`: every rank passes its shard's p and gets
         the q-values its rows would have if all shards had been ranked together (the reference's q-value step,
         utils.py:31-90 -> blueberry.pyx:40).  Two collectives: all-reduce of the 4096-bucket p histogram and
         all-gather of the candidate keys below the common saturation bucket.  `hist`: this shard's coarse
-        histogram when K4 already filled it (self.p_hist), else it is computed here.  Synchronises the host twice
+        histogram when K4 already filled it (self.p_hist), else it is computed here.  prepared: K4 ran with q_out=q
+        (bbk_pvalues_bh), so q is pre-filled and the candidates come from its flag bits.  Synchronises the host once
         (candidate counts).  With one rank the result equals qvalues() bit for bit."""
         import torch.distributed as dist
         lib, dev = self.lib, self.device
@@ -221,9 +222,14 @@ class PassEngine(object):
         keys = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
         idx = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
         state = torch.zeros(4, dtype=torch.int64, device=dev)
-        ws0 = torch.empty(int(lib.bbk_bh_workspace_bytes(0)), dtype=torch.uint8, device=dev)
-        _lib.check(lib.bbk_bh_select(_lib.ptr(p), m, int(n_tests), _lib.ptr(ghist), _lib.ptr(q), _lib.ptr(keys), _lib.ptr(idx),
-                                     _lib.ptr(state), _lib.ptr(ws0), ws0.numel(), st), "bbk_bh_select")
+        if prepared:
+            ws0 = self._bh_workspace(m)          # holds K4's flag bits
+            _lib.check(lib.bbk_bh_select_prepared(_lib.ptr(p), m, int(n_tests), _lib.ptr(ghist), _lib.ptr(q), _lib.ptr(keys),
+                                                  _lib.ptr(idx), _lib.ptr(state), _lib.ptr(ws0), ws0.numel(), st), "bbk_bh_select_prepared")
+        else:
+            ws0 = torch.empty(int(lib.bbk_bh_workspace_bytes(0)), dtype=torch.uint8, device=dev)
+            _lib.check(lib.bbk_bh_select(_lib.ptr(p), m, int(n_tests), _lib.ptr(ghist), _lib.ptr(q), _lib.ptr(keys), _lib.ptr(idx),
+                                         _lib.ptr(state), _lib.ptr(ws0), ws0.numel(), st), "bbk_bh_select")
         # candidate counts of all ranks with ONE host synchronisation
         if world > 1:
             counts_dev = torch.empty(world, dtype=torch.int64, device=dev)

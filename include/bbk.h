@@ -206,6 +206,12 @@ int bbk_p_hist(const double* d_p, int64_t m, int64_t* d_p_hist, void* stream);
 int bbk_bh_select(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
                   uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
                   void* stream);
+/* bbk_bh_select after bbk_pvalues_bh on the same d_p / d_q: q is already pre-filled and the candidates come from K4's flag
+ * bits (d_workspace = the workspace given to bbk_pvalues_bh, untouched since); falls back to the full pass by itself when the
+ * GLOBAL saturation bucket lies at or above 2^-5.  Same outputs as bbk_bh_select. */
+int bbk_bh_select_prepared(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                           uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
+                           void* stream);
 int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, const uint64_t* d_state, double* d_q_all,
                          double* d_q_ones, void* d_workspace, size_t workspace_bytes, void* stream);
 int bbk_bh_scatter(const double* d_q_src, const uint32_t* d_idx, int64_t n, double* d_q_dst, void* stream);

@@ -291,6 +291,13 @@ def test_k4_handover_matches_two_pass_qvalues(n_tests):
     assert torch.equal(hist0[:4098], eng.p_hist[:4098])
     assert torch.equal(q0.view(torch.int64), q1.view(torch.int64))
     use_list = int(eng.bh_ws[100:104].view(torch.int32)[0])
+    # the genome-wide (multi-GPU) pipeline with one rank, fed by the same hand-over
+    q2 = torch.full((P + 3,), -7.0, dtype=torch.float64, device=dev)[:P]
+    eng.p_hist.zero_()
+    eng.pvalues(sh, p1, with_hist=True, q_out=q2)
+    eng.qvalues_global(p1, q2, n_tests=n_tests, hist=eng.p_hist, prepared=True)
+    torch.cuda.synchronize()
+    assert torch.equal(q0.view(torch.int64), q2.view(torch.int64))
     assert use_list == (1 if n_tests < 0 else 0)
     if n_tests > 0:
         assert float(q1[p1 == 1.0][0]) < 1.0
