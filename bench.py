@@ -305,8 +305,9 @@ def run_ours(args, out_fd):
     peak, peak_src = _peaks()
     k4_gbs = K4_BYTES_PER_PAIR * P / (acc["pvalues"] * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of one K4 launch on this exact workload, from the ncu --set full
-    # capture summarised in profiles/r01_ncu_full_k1_k4.txt (1.1736 GB read + 0.7399 GB written)
-    k4_traffic = 1.9135e9 if (nb == CHR1_BINS and world == 1) else None
+    # capture summarised in profiles/r01_ncu_full_final.txt (1.1738 GB read + 1.5203 GB written: with the K4 -> K5
+    # hand-over K4 also writes the 8 B/pair of q that the SURVEY's byte table books under K5)
+    k4_traffic = 2.6941e9 if (nb == CHR1_BINS and not two_pass) else None
     roofline = {"bound": "hbm", "kernel": "pvalues_kernel (K4)", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                 "frac": k4_gbs / peak, "traffic": k4_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * P,
