@@ -24,6 +24,7 @@ SOURCES = [
     ("pvalue.cu", []),
     ("bh.cu", []),
     ("band.cu", []),
+    ("decimate.cu", []),
     ("synth.cu", []),
 ]
 

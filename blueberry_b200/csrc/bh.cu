@@ -467,6 +467,8 @@ struct RankParams {
     BhLayout L;
     double* q;               // output (input order, or gathered order for bbk_bh_rank_gathered)
     long long* rank;         // optional
+    long long n_host;        // >= 0: number of (key, index) pairs, known to the host; < 0: BhState::n_cand
+    int src;                 // buffer (0 / 1) the pairs start in; a sort-only launch leaves the result there
 };
 
 __device__ __forceinline__ int rk_eff_blocks(long long n, int G) {
@@ -505,6 +507,7 @@ __device__ __forceinline__ MaxHead mh_elem(const unsigned long long* keys, long 
     return e;
 }
 
+template <bool SCAN>
 __global__ void __launch_bounds__(RK_THREADS, 1) bh_rank_kernel(RankParams R) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned base[256];                   // digit counts of the chunk, then the running output cursor per digit
@@ -515,13 +518,13 @@ __global__ void __launch_bounds__(RK_THREADS, 1) bh_rank_kernel(RankParams R) {
     __shared__ double wv[RK_WARPS];
     __shared__ long long wh[RK_WARPS];
     BhState* st = R.L.st;
-    const long long n = (long long)st->n_cand;
+    const long long n = R.n_host >= 0 ? R.n_host : (long long)st->n_cand;
     const int b = blockIdx.x, Ge = rk_eff_blocks(n, gridDim.x);
     const bool active = b < Ge;
     const Chunk c = rk_chunk(n, Ge, b);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     unsigned* table = R.L.block_hist;                // [Ge][256]
-    int par = 0;
+    int par = R.src;
     for (int pass = 0; pass < NPASS; ++pass) {
         const int shift = 8 * pass;
         const unsigned long long* kin = R.L.keys[par];
@@ -619,6 +622,17 @@ __global__ void __launch_bounds__(RK_THREADS, 1) bh_rank_kernel(RankParams R) {
         grid.sync();
     }
 
+    if (!SCAN) {
+        // sort only (bbk_decimate): the caller finds the sorted pairs where it put the unsorted ones
+        int fin = R.src;
+        for (int ps = 0; ps < NPASS; ++ps) fin ^= (st->skip[ps] ? 0 : 1);      // inactive CTAs did not follow the flips
+        par = fin;
+        if (par != R.src) {
+            const long long stride = (long long)gridDim.x * RK_THREADS;
+            for (long long i = (long long)b * RK_THREADS + t; i < n; i += stride) { R.L.keys[R.src][i] = R.L.keys[par][i]; R.L.idx[R.src][i] = R.L.idx[par][i]; }
+        }
+        return;
+    }
     // ---- forward running max over the sorted keys; thread t scans a contiguous slice of the chunk
     const unsigned long long* keys = R.L.keys[par];
     const unsigned* idx = R.L.idx[par];
@@ -700,7 +714,7 @@ int rank_grid() {            // CTAs of bh_rank_kernel that are resident togethe
     static int g = 0;
     if (g == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_rank_kernel, RK_THREADS, 0) != cudaSuccess || per_sm < 1) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_rank_kernel<true>, RK_THREADS, 0) != cudaSuccess || per_sm < 1) return 0;
         g = bbk_num_sms();
     }
     return g;
@@ -710,12 +724,39 @@ int launch_rank(const BhLayout& L, double* q, long long* rank, cudaStream_t st) 
     int g = rank_grid();
     if (g <= 0 || g > L.G) { bbk_set_error("bh_rank_kernel: cooperative launch not possible on this device"); return BBK_E_CUDA; }
     RankParams R;
-    R.L = L; R.q = q; R.rank = rank;
+    R.L = L; R.q = q; R.rank = rank; R.n_host = -1; R.src = 0;
     void* args[] = {&R};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel, dim3(g), dim3(RK_THREADS), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel<true>, dim3(g), dim3(RK_THREADS), args, 0, st);
     if (e != cudaSuccess) { bbk_set_error("bh_rank_kernel: %s", cudaGetErrorString(e)); return BBK_E_CUDA; }
     return BBK_OK;
 }
+
+}  // namespace
+
+// ---- the radix sort alone, for the other kernels of the library (decimate.cu): stable LSD sort of n (u64 key, u32 value)
+// pairs that sit in buffer `src` of a workspace laid out by bbk_bh_workspace_bytes(capacity); the result is left in the
+// same buffer.  n_host < 0: the count is BhState::n_cand (device), see bbk_sort_count_ptr.
+void bbk_sort_buffers(void* workspace, long long capacity, int which, unsigned long long** keys, unsigned** idx) {
+    BhLayout L;
+    bh_layout(workspace, capacity, bbk_num_sms() * 4 > 1024 ? 1024 : bbk_num_sms() * 4, &L);
+    *keys = L.keys[which];
+    *idx = L.idx[which];
+}
+unsigned long long* bbk_sort_count_ptr(void* workspace) { return &((BhState*)workspace)->n_cand; }
+int bbk_sort_pairs(void* workspace, long long capacity, long long n_host, int src, cudaStream_t st) {
+    int g = rank_grid();
+    BhLayout L;
+    bh_layout(workspace, capacity, bbk_num_sms() * 4 > 1024 ? 1024 : bbk_num_sms() * 4, &L);
+    if (g <= 0 || g > L.G) { bbk_set_error("bbk_sort_pairs: cooperative launch not possible on this device"); return BBK_E_CUDA; }
+    RankParams R;
+    R.L = L; R.q = nullptr; R.rank = nullptr; R.n_host = n_host; R.src = src;
+    void* args[] = {&R};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel<false>, dim3(g), dim3(RK_THREADS), args, 0, st);
+    if (e != cudaSuccess) { bbk_set_error("bbk_sort_pairs: %s", cudaGetErrorString(e)); return BBK_E_CUDA; }
+    return BBK_OK;
+}
+
+namespace {
 
 // rare: q of the p == 1.0 group is below 1 (N smaller than the number of candidates)
 __global__ void __launch_bounds__(BH_THREADS) ones_fix_kernel(const double* p, long long m, double* q, const BhState* st) {

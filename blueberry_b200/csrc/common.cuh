@@ -18,6 +18,11 @@ int bbk_num_sms();
 #define BBK_SMALL_P 0.03125
 // where K4 puts the bits inside K5's workspace (defined in bh.cu)
 unsigned* bbk_bh_mask_buffer(void* workspace, long long m);
+// the library's radix sort on its own (bh.cu): n (u64 key, u32 value) pairs in buffer `src` (0 / 1) of a workspace of
+// bbk_bh_workspace_bytes(capacity) bytes, stable, result left in the same buffer; n_host < 0: count at bbk_sort_count_ptr
+void bbk_sort_buffers(void* workspace, long long capacity, int which, unsigned long long** keys, unsigned** idx);
+unsigned long long* bbk_sort_count_ptr(void* workspace);
+int bbk_sort_pairs(void* workspace, long long capacity, long long n_host, int src, cudaStream_t st);
 
 #define BBK_CHECK_CUDA(expr)                                                                  \
     do {                                                                                      \

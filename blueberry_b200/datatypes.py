@@ -1,0 +1,78 @@
+"""FithicContactMap - the consumer of the pass's output file (blueberry/datatypes.pyx:274-350), SURVEY.md 8f row 1.
+
+Same attributes (`map`: (n, 5) float64 rows (mid1, mid2, contactCount, p, q); `regions`; `resolution`) and methods
+(`decimate`, `contacts`, `to_matrix`) as the reference class; `decimate` - the sort / reduce-by-key - runs on the GPU
+(K7, `bbk_decimate` in include/bbk.h).  The reference constructor builds its path from a hard-coded NFS template
+(datatypes.pyx:26, :310); here the file name is given directly (`FithicContactMap(path, resolution)`), or use
+`FithicContactMap.from_arrays(map, resolution)`.
+"""
+import numpy as np
+
+from .utils import Q_LOWER_BOUND
+
+
+class FithicContactMap(object):
+    def __init__(self, filename, resolution=1000, chromosome=None, celltype=None):
+        import pandas
+        self.resolution = resolution
+        self.filename = filename
+        self.chromosome = chromosome
+        self.celltype = celltype
+        # datatypes.pyx:314: columns fragmentMid1, fragmentMid2, contactCount, p-value, q-value
+        self.map = pandas.read_csv(self.filename, sep="\t", usecols=[1, 3, 4, 5, 6], engine='c', dtype='float64').values
+        self.regions = np.union1d(self.map[:, 0], self.map[:, 1])
+
+    @classmethod
+    def from_arrays(cls, map5, resolution=1000, chromosome=None, celltype=None):
+        self = cls.__new__(cls)
+        self.resolution = resolution
+        self.filename = None
+        self.chromosome = chromosome
+        self.celltype = celltype
+        self.map = np.ascontiguousarray(map5, dtype=np.float64).reshape(-1, 5)
+        self.regions = np.union1d(self.map[:, 0], self.map[:, 1])
+        return self
+
+    def decimate(self, resolution=5000):
+        """datatypes.pyx:317-339: round both midpoints to the coarser grid ((int(mid) + r) / r * r - r/2, Python-2 integer
+        division) and fold the rows that coincide - sum of counts, product of p, min of q, in file order."""
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BbkError("FithicContactMap.decimate needs a CUDA device (blueberry_b200 has no CPU fallback)")
+        dev = torch.device("cuda:%d" % torch.cuda.current_device())
+        n = int(self.map.shape[0])
+        self.resolution = resolution
+        if n == 0:
+            return
+        cols = torch.from_numpy(np.ascontiguousarray(self.map.T)).to(dev)                 # (5, n): one column per row
+        out = torch.empty((5, n), dtype=torch.float64, device=dev)
+        n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = torch.empty(int(lib.bbk_decimate_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.bbk_decimate(_lib.ptr(cols[0]), _lib.ptr(cols[1]), _lib.ptr(cols[2]), _lib.ptr(cols[3]), _lib.ptr(cols[4]),
+                                    n, int(resolution), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+                                    _lib.ptr(out[4]), _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_decimate")
+        g = int(n_out.item())
+        if g < 0:
+            raise ValueError("decimate: a midpoint is outside [0, 2^31)")
+        self.map = np.ascontiguousarray(out[:, :g].T.cpu().numpy())
+        self.regions = np.union1d(self.map[:, 0], self.map[:, 1])
+
+    def contacts(self):
+        """datatypes.pyx:341-350: all contacts with a q-value <= Q_LOWER_BOUND, as (mid1, mid2) rows."""
+        return self.map[self.map[:, 4] <= Q_LOWER_BOUND, :2]
+
+    def to_matrix(self, statistic='count', n_bins=None):
+        """datatypes.pyx:352-388: the chosen column as a dense 2-d matrix indexed by bin.  The reference sizes the matrix
+        from a KR-norm vector it loads from a hard-coded path; here `n_bins` (default: enough for the largest midpoint)."""
+        col = {'count': 2, 'p': 3, 'q': 4}.get(statistic)
+        if col is None:
+            raise ValueError
+        r = self.resolution
+        i = ((self.map[:, 0] - r / 2) / r).astype(np.int64)
+        j = ((self.map[:, 1] - r / 2) / r).astype(np.int64)
+        d = int(n_bins) if n_bins is not None else (int(max(i.max(), j.max())) + 1 if len(i) else 0)
+        matrix = np.zeros((d, d))
+        matrix[i, j] = self.map[:, col]          # later rows win, like the reference's loop
+        return matrix

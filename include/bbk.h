@@ -227,6 +227,19 @@ int bbk_bh_fix_ones_dev(const double* d_p, int64_t m, const double* d_q_ones, do
 int bbk_count_band(const double* d_regions, int64_t n, double low, double high, int64_t* d_result, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7  FithicContactMap.decimate                        replaces datatypes.pyx:317-339  
+ *     mid' = (int(mid) + r) / r * r - r/2 (Python-2 integer division) for both midpoints of every row, then rows with
+ *     equal (mid1', mid2') are folded in file order: count = count_i + count, p = p_i * p, q = min(q_i, q) from (0, 1, 1).
+ * Columns in (the five columns of the reference's (n, 5) float64 map), columns out (capacity n), groups in the order
+ * of their first row in the file.  *d_n_out: number of groups, or -1 when a coordinate is outside [0, 2^31).
+ * The sum and the product are folded by one thread per group, member by member, so they round like the reference's loop.
+ * ------------------------------------------------------------------------------------------- */
+size_t bbk_decimate_workspace_bytes(int64_t n);
+int bbk_decimate(const double* d_mid1, const double* d_mid2, const double* d_count, const double* d_p, const double* d_q,
+                 int64_t n, int64_t resolution, double* d_out_mid1, double* d_out_mid2, double* d_out_count, double* d_out_p,
+                 double* d_out_q, int64_t* d_n_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Synthetic contact records of the BASELINE shapes, generated on the device (bench only).
  * Fills mid1/mid2/count for one chromosome of n_bins bins: all (i, i+d), 0 <= d <= K, row-major.
  * d_bias (nullable): per-bin visibility multiplying the Poisson mean.  Returns records written

@@ -118,6 +118,22 @@ def _pass2_case():
     print("pass2_bias_dense outliers", ref2["n_outliers"], "S", ref2["S"], "rows", len(out["p"]))
 
 
+def _decimate_case():
+    """FithicContactMap.decimate (datatypes.pyx:317-339) run from the reference's own method source."""
+    rng = np.random.default_rng(17)
+    n = 6000
+    m1 = rng.integers(0, 500, n) * 1000 + 500
+    m2 = m1 + rng.integers(0, 80, n) * 1000
+    mp = np.stack([m1, m2, rng.integers(0, 60, n), rng.random(n) ** 4, np.minimum(rng.random(n) ** 2 * 3, 1.0)], axis=1).astype(np.float64)
+    mp[rng.choice(n, 200, replace=False), 4] = -1.0          # the literal q the reference's own files carry (fithic.py:435)
+    mp = np.concatenate([mp, mp[rng.choice(n, 500)]])        # exact duplicates
+    mp = mp[rng.permutation(len(mp))]                        # not sorted: groups appear interleaved
+    out5 = run_reference.run_reference_decimate(mp, 5000)
+    out25 = run_reference.run_reference_decimate(out5, 25000)
+    np.savez_compressed(os.path.join(GOLDEN, "decimate.npz"), map_in=mp, ref_5000=out5, ref_25000_of_5000=out25)
+    print("decimate", mp.shape, "->", out5.shape, "->", out25.shape)
+
+
 def main():
     if not ref_loader.reference_available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -131,6 +147,7 @@ def main():
     _pass_case("pass_messy", [300, 220, 90], 5000, 1000000, 20000, 60.0, 7, True, True, n_bins=40, messy=True)
     _bh_case()
     _pass2_case()
+    _decimate_case()
 
 
 if __name__ == "__main__":

@@ -137,3 +137,27 @@ def run_reference_two_pass(frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count, 
             "observed": np.array([main[k][1] for k in keys], np.int64), "S": int(ref.observedIntraInRangeSum),
             "x": np.array(x), "y": np.array(y), "spline_x": np.array(spline_x, np.int64), "spline_y": np.array(new_y),
             "out": out}
+
+
+def run_reference_decimate(map5, resolution):
+    """FithicContactMap.decimate (datatypes.pyx:317-339) itself: the method's source is read from where it lies, exec'd as
+    plain Python (the body uses nothing of Cython) on a stand-in object, with ONE edit - the two `/` of line 331 become
+    `//`, Python 2's integer division on the integer midpoints.  Returns the (g, 5) map it leaves in self.map."""
+    import textwrap
+    import types
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "blueberry", "datatypes.pyx")
+    lines = open(path).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip().startswith("def decimate(self"))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].strip().startswith("def "))
+    body = lines[start:end]
+    old = "/ resolution * resolution - resolution/2"
+    hit = [i for i, l in enumerate(body) if old in l]
+    if len(hit) != 1:
+        raise RuntimeError("reference datatypes.pyx decimate changed; the edit no longer applies")
+    body[hit[0]] = body[hit[0]].replace(old, "// resolution * resolution - resolution//2")
+    src = textwrap.dedent("\n".join(body).replace("\t", "    "))
+    ns = {"numpy": np}
+    exec(compile(src, path, "exec"), ns)
+    obj = types.SimpleNamespace(map=np.array(map5, dtype=np.float64, copy=True), resolution=None, regions=None)
+    ns["decimate"](obj, resolution)
+    return obj.map

@@ -302,3 +302,50 @@ def test_k4_handover_matches_two_pass_qvalues(n_tests):
     if n_tests > 0:
         assert float(q1[p1 == 1.0][0]) < 1.0
     assert int((q1 < 1.0).sum()) > 1000
+
+
+def test_decimate_matches_reference_golden_and_oracle(tmp_path):
+    """K7 (bbk_decimate through FithicContactMap.decimate) against the golden output of the reference's own method
+    (tests/golden/decimate.npz), bit for bit including the order-dependent sum and product, then against the oracle on
+    larger inputs: unsorted files, exact duplicates, one giant group, a single row, an empty map."""
+    from blueberry_b200.datatypes import FithicContactMap
+    from oracle import datatypes_oracle as do
+    g = load_golden("decimate")
+    cm = FithicContactMap.from_arrays(g["map_in"], resolution=1000)
+    cm.decimate(5000)
+    assert cm.resolution == 5000
+    assert np.array_equal(cm.map, g["ref_5000"])
+    assert np.array_equal(cm.regions, np.union1d(g["ref_5000"][:, 0], g["ref_5000"][:, 1]))
+    cm.decimate(25000)
+    assert np.array_equal(cm.map, g["ref_25000_of_5000"])
+    assert np.array_equal(cm.contacts(), do.contacts(g["ref_25000_of_5000"]))
+    rng = np.random.default_rng(31)
+    for n, span, shuffle in ((200000, 3000, True), (150001, 40, False), (1, 5, False), (70000, 1, True)):
+        m1 = rng.integers(0, span, n) * 1000 + 500
+        m2 = m1 + rng.integers(0, max(span // 10, 1), n) * 1000
+        mp = np.stack([m1, m2, rng.integers(0, 40, n), rng.random(n) ** 2, np.minimum(rng.random(n) * 2, 1.0)], axis=1).astype(np.float64)
+        if not shuffle:
+            mp = mp[np.lexsort((mp[:, 1], mp[:, 0]))]
+        cm = FithicContactMap.from_arrays(mp)
+        cm.decimate(5000)
+        assert np.array_equal(cm.map, do.decimate(mp, 5000)), (n, span)
+    empty = FithicContactMap.from_arrays(np.zeros((0, 5)))
+    empty.decimate(5000)
+    assert empty.map.shape == (0, 5)
+    with pytest.raises(ValueError):
+        FithicContactMap.from_arrays(np.array([[1e12, 5.0, 1, 0.5, 0.5]])).decimate(5000)
+    # the reader: a file written by the pass's own writer
+    from blueberry_b200 import _io
+    path = str(tmp_path / "x.significances.txt.gz")
+    mp = g["map_in"]
+    _io.write_significances(path, ["chr1"], None, mp[:, 0].astype(np.int64), None, mp[:, 1].astype(np.int64), mp[:, 2].astype(np.int64),
+                            mp[:, 3], mp[:, 4])
+    cm = FithicContactMap(path, resolution=1000)
+    # pandas' default float parser (what datatypes.pyx:314 uses) is not round-trip exact (relative error up to ~1e-12 on
+    # 17-digit decimals): the integer columns are exact, and the file itself is exact under float_precision='round_trip'
+    assert np.array_equal(cm.map[:, :3], mp[:, :3])
+    assert np.allclose(cm.map[:, 3:], mp[:, 3:], rtol=1e-11, atol=0.0)
+    import pandas
+    exact = pandas.read_csv(path, sep="\t", usecols=[1, 3, 4, 5, 6], engine='c', dtype='float64', float_precision='round_trip').values
+    assert np.array_equal(exact, mp)
+    assert cm.to_matrix('count', n_bins=600).sum() > 0

@@ -85,3 +85,18 @@ def test_two_pass_oracle_matches_composed_reference():
     assert np.array_equal(r2.spline_y, g2["ref2_spline_y"])
     assert np.array_equal(g["mid1"][r2.keep], g2["ref2_out_mid1"])
     assert np.array_equal(r2.p[r2.keep], g2["ref2_out_p"])
+
+
+def test_decimate_oracle_matches_reference_method_output():
+    """oracle/datatypes_oracle.decimate against tests/golden/decimate.npz (FithicContactMap.decimate run from the
+    reference's own method source, datatypes.pyx:317-339, by oracle/make_golden.py)."""
+    from oracle import datatypes_oracle as do
+    g = load_golden("decimate")
+    out5 = do.decimate(g["map_in"], 5000)
+    assert np.array_equal(out5, g["ref_5000"])
+    assert np.array_equal(do.decimate(out5, 25000), g["ref_25000_of_5000"])
+    # the rounding rule on a few hand-checked values: (mid + r) // r * r - r // 2
+    m = np.array([[500.0, 4500.0, 1, 0.5, 1.0], [4999.0, 5000.0, 2, 0.5, 0.2], [0.0, 9999.0, 3, 0.25, 0.7]])
+    d = do.decimate(m, 5000)
+    assert d.tolist() == [[2500.0, 2500.0, 1.0, 0.5, 1.0], [2500.0, 7500.0, 5.0, 0.125, 0.2]]
+    assert do.contacts(np.array([[1.0, 2.0, 3, 0.1, 0.01], [3.0, 4.0, 3, 0.1, 0.011]])).tolist() == [[1.0, 2.0]]

@@ -35,3 +35,16 @@ def test_live_reference_cython_helpers():
     assert np.array_equal(np.asarray(cy.benjamini_hochberg(p, 777)), fo.benjamini_hochberg_sorted(p, 777))
     reg = np.sort(rng.choice(10**6, 800, replace=False)).astype(np.float64) * 37
     assert cy.count_band_regions(reg) == fo.count_band_regions(reg)
+
+
+def test_live_reference_decimate():
+    """The restatement of FithicContactMap.decimate against the reference's own method body, executed here."""
+    import numpy as np
+    from oracle import datatypes_oracle as do, run_reference
+    rng = np.random.default_rng(23)
+    n = 3000
+    m1 = rng.integers(0, 300, n) * 1000 + 500
+    m2 = m1 + rng.integers(0, 40, n) * 1000
+    mp = np.stack([m1, m2, rng.integers(0, 30, n), rng.random(n) ** 3, rng.random(n)], axis=1).astype(np.float64)
+    for r in (2000, 5000, 25000):
+        assert np.array_equal(run_reference.run_reference_decimate(mp, r), do.decimate(mp, r))
