@@ -25,6 +25,7 @@ SOURCES = [
     ("bh.cu", []),
     ("band.cu", []),
     ("decimate.cu", []),
+    ("contactmap.cu", []),
     ("synth.cu", []),
 ]
 

@@ -76,3 +76,73 @@ class FithicContactMap(object):
         matrix = np.zeros((d, d))
         matrix[i, j] = self.map[:, col]          # later rows win, like the reference's loop
         return matrix
+
+
+class ContactMap(object):
+    """The raw contact map next to the pass (blueberry/datatypes.pyx:31-171) as BAND RECORDS on the GPU instead of the
+    reference's dense (n_bins+1)^2 matrix (impossible beyond ~25 kb on chr1): `bin1 <= bin2`, `value`.
+
+    Same constructor inputs as the reference reads (RAWobserved rows pos1, pos2, count; the KRnorm and KRexpected
+    vectors), given as paths or arrays instead of its hard-coded NFS templates; `normalize()` is the reference's
+    KR balancing + observed/expected + nan_to_num in one elementwise kernel (K8); `to_dense()` rebuilds the
+    reference's matrix for small maps.
+    """
+
+    def __init__(self, raw, kr_norm, kr_expected, resolution=1000, chromosome=None, celltype=None):
+        import pandas
+        import torch
+        from . import _lib
+        self.resolution = int(resolution)
+        self.chromosome = chromosome
+        self.celltype = celltype
+        self.filename = raw if isinstance(raw, str) else None
+        self.KRnorm = np.loadtxt(kr_norm) if isinstance(kr_norm, str) else np.asarray(kr_norm, dtype=np.float64)
+        self.KRexpected = np.loadtxt(kr_expected) if isinstance(kr_expected, str) else np.asarray(kr_expected, dtype=np.float64)
+        self.n_bins = int(self.KRnorm.shape[0])                                           # datatypes.pyx:96
+        if isinstance(raw, str):
+            data = pandas.read_csv(raw, delimiter="\t", engine='c', dtype='float64', header=None).values   # :101
+        else:
+            data = np.stack([np.asarray(c, dtype=np.float64) for c in raw], axis=1)
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BbkError("ContactMap needs a CUDA device (blueberry_b200 has no CPU fallback)")
+        self._dev = torch.device("cuda:%d" % torch.cuda.current_device())
+        n = int(data.shape[0])
+        cols = torch.from_numpy(np.ascontiguousarray(data[:, :3].T)).to(self._dev)
+        self.bin1 = torch.empty(n, dtype=torch.int32, device=self._dev)
+        self.bin2 = torch.empty(n, dtype=torch.int32, device=self._dev)
+        self.value = torch.empty(n, dtype=torch.float64, device=self._dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        _lib.check(lib.bbk_contact_band_ingest(_lib.ptr(cols[0]), _lib.ptr(cols[1]), _lib.ptr(cols[2]), n, self.resolution, self.n_bins,
+                                               _lib.ptr(self.bin1), _lib.ptr(self.bin2), _lib.ptr(self.value), _lib.ptr(bad),
+                                               _lib.stream_ptr()), "bbk_contact_band_ingest")
+        if int(bad.item()):
+            raise IndexError("a contact falls outside the (n_bins+1)^2 map the KRnorm vector defines")
+        clean = np.nan_to_num(data)
+        self.regions = np.union1d(clean[:, 0], clean[:, 1])                               # :119-120
+        self.regions.sort()
+
+    def normalize(self):
+        """datatypes.pyx:143-171: value /= KRnorm[i] * KRnorm[j] * KRexpected[j - i], then nan_to_num."""
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        kr = torch.from_numpy(np.ascontiguousarray(self.KRnorm, dtype=np.float64)).to(self._dev)
+        ke = torch.from_numpy(np.ascontiguousarray(self.KRexpected, dtype=np.float64)).to(self._dev)
+        if ke.numel() < self.n_bins:
+            raise IndexError("KRexpected is shorter than KRnorm")
+        bad = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        _lib.check(lib.bbk_contact_band_normalize(_lib.ptr(self.bin1), _lib.ptr(self.bin2), _lib.ptr(self.value), int(self.value.numel()),
+                                                  _lib.ptr(kr), _lib.ptr(ke), self.n_bins, _lib.ptr(self.value), _lib.ptr(bad),
+                                                  _lib.stream_ptr()), "bbk_contact_band_normalize")
+        if int(bad.item()):
+            raise ZeroDivisionError("float division")        # what the reference's checked division raises (datatypes.pyx:168)
+
+    def to_dense(self):
+        """The reference's `matrix` attribute: (n_bins+1)^2, both triangles; a repeated cell keeps the last record."""
+        d = self.n_bins + 1
+        i, j, v = self.bin1.cpu().numpy(), self.bin2.cpu().numpy(), self.value.cpu().numpy()
+        matrix = np.zeros((d, d), dtype=np.float64)
+        matrix[i, j] = v
+        matrix[j, i] = v
+        return matrix

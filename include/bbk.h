@@ -240,6 +240,24 @@ int bbk_decimate(const double* d_mid1, const double* d_mid2, const double* d_cou
                  double* d_out_q, int64_t* d_n_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K8  ContactMap ingest + normalize on band records    replaces datatypes.pyx:99-120 and :143-171  
+ * The reference holds the map as a dense (n_bins+1)^2 float64 matrix; here the RAWobserved rows stay records.
+ * ingest:    bin = int(nan_to_num(pos) / resolution) for both positions (:104, :111-112), stored as bin1 <= bin2 (the
+ *            reference writes both triangles, :115-116); value = nan_to_num(count).  *d_bad != 0 afterwards when a
+ *            bin is negative or > n_bins (outside the reference's matrix).
+ * normalize: value / (KRnorm[bin1] * KRnorm[bin2] * KRexpected[bin2 - bin1]) for bin2 < n_bins (:166-168; the loop
+ *            never reaches row / column n_bins), then nan_to_num (:171).  d_out may alias d_value.  *d_bad != 0 when a
+ *            divisor is exactly 0.0: the reference's (Cython, checked) division raises ZeroDivisionError there.
+ * Scattering the records into a zero matrix gives the reference's matrix when no (bin1, bin2) repeats (for repeats
+ * the reference keeps the last row of the file; records keep them all).
+ * ------------------------------------------------------------------------------------------- */
+int bbk_contact_band_ingest(const double* d_pos1, const double* d_pos2, const double* d_count, int64_t n, int64_t resolution,
+                            int32_t n_bins, int32_t* d_bin1, int32_t* d_bin2, double* d_value, int32_t* d_bad, void* stream);
+int bbk_contact_band_normalize(const int32_t* d_bin1, const int32_t* d_bin2, const double* d_value, int64_t n,
+                               const double* d_kr_norm, const double* d_kr_expected, int32_t n_bins, double* d_out,
+                               int32_t* d_bad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Synthetic contact records of the BASELINE shapes, generated on the device (bench only).
  * Fills mid1/mid2/count for one chromosome of n_bins bins: all (i, i+d), 0 <= d <= K, row-major.
  * d_bias (nullable): per-bin visibility multiplying the Poisson mean.  Returns records written

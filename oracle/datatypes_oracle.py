@@ -38,3 +38,33 @@ def regions(map5):
     """datatypes.pyx:315,339: every midpoint that takes part in a contact."""
     m = np.asarray(map5)
     return np.union1d(m[:, 0], m[:, 1])
+
+
+def contact_map_dense(pos1, pos2, count, n_bins, resolution):
+    """datatypes.pyx:99-120: the dense (n_bins+1)^2 matrix the reference builds from the RAWobserved rows
+    (data = nan_to_num(data); j = int(pos1 / resolution); both triangles; a repeated cell keeps the last row)."""
+    d = n_bins + 1
+    data = np.nan_to_num(np.stack([np.asarray(pos1, dtype=np.float64), np.asarray(pos2, dtype=np.float64),
+                                   np.asarray(count, dtype=np.float64)], axis=1))
+    matrix = np.zeros((d, d), dtype=np.float64)
+    for a, b, c in data:
+        j, k = int(a / resolution), int(b / resolution)
+        matrix[j, k] = c
+        matrix[k, j] = c
+    regions = np.union1d(data[:, 0], data[:, 1])
+    return matrix, regions
+
+
+def normalize_dense(matrix, kr_norm, kr_expected, n_bins):
+    """datatypes.pyx:143-171: KR balancing and observed/expected in place, then nan_to_num.  The reference's division is
+    Cython's checked C division: a divisor of exactly 0.0 raises ZeroDivisionError (NaN divisors just give NaN -> 0)."""
+    m = np.array(matrix, dtype=np.float64, copy=True)
+    with np.errstate(invalid="ignore"):
+        for i in range(n_bins):
+            for j in range(n_bins - i):
+                den = kr_norm[j] * kr_norm[j + i] * kr_expected[i]
+                if den == 0.0:
+                    raise ZeroDivisionError("float division")
+                m[j, j + i] /= den
+                m[j + i, j] = m[j, j + i]
+    return np.nan_to_num(m)

@@ -134,6 +134,28 @@ def _decimate_case():
     print("decimate", mp.shape, "->", out5.shape, "->", out25.shape)
 
 
+def _contact_map_case():
+    """ContactMap.__init__ + normalize (datatypes.pyx:88-171), the reference compiled verbatim."""
+    rng = np.random.default_rng(29)
+    nb, R = 120, 5000
+    kr = rng.random(nb) + 0.5
+    kr[rng.choice(nb, 6, replace=False)] = np.nan                   # unmappable bins, as in real KRnorm files
+    ke = np.sort(rng.random(nb) * 80 + 0.5)[::-1].copy()
+    pairs = [(i, j) for i in range(nb + 1) for j in range(i, min(i + 40, nb + 1))]
+    sel = rng.choice(len(pairs), 2500, replace=False)
+    b1 = np.array([pairs[k][0] for k in sel])
+    b2 = np.array([pairs[k][1] for k in sel])
+    swap = rng.random(len(sel)) < 0.3                               # rows of the lower triangle
+    pos1 = np.where(swap, b2, b1) * R
+    pos2 = np.where(swap, b1, b2) * R
+    cnt = rng.integers(1, 500, len(sel)).astype(np.float64)
+    cnt[rng.choice(len(sel), 10, replace=False)] = np.nan           # nan_to_num at ingest (:104)
+    before, after, regions, n_bins = run_reference.run_reference_contact_map(pos1, pos2, cnt, kr, ke, R)
+    np.savez_compressed(os.path.join(GOLDEN, "contact_map.npz"), resolution=R, pos1=pos1, pos2=pos2, count=cnt, kr_norm=kr,
+                        kr_expected=ke, ref_matrix=before, ref_normalized=after, ref_regions=regions, ref_n_bins=n_bins)
+    print("contact_map", before.shape, "records", len(sel), "nonzero after", int(np.count_nonzero(after)))
+
+
 def main():
     if not ref_loader.reference_available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -148,6 +170,7 @@ def main():
     _bh_case()
     _pass2_case()
     _decimate_case()
+    _contact_map_case()
 
 
 if __name__ == "__main__":

@@ -155,3 +155,52 @@ def load_reference_cython():
         sys.path.insert(0, d)
     import importlib
     return importlib.import_module("blueberry_ref.blueberry")
+
+
+_SETUP_DT = r'''
+import sys
+from setuptools import setup, Extension
+from Cython.Build import cythonize
+import numpy
+ext = Extension("blueberry_ref.datatypes", ["blueberry_ref/datatypes.pyx"], include_dirs=[numpy.get_include()],
+                define_macros=[("NPY_NO_DEPRECATED_API", "NPY_1_7_API_VERSION")])
+setup(name="blueberry_ref_dt", ext_modules=cythonize([ext], language_level=2, build_dir="cy_build", quiet=True),
+      script_args=["build_ext", "--build-lib", ".", "--build-temp", "cy_tmp", "-q"])
+'''
+
+
+def build_reference_datatypes(force=False):
+    """Cythonize /root/reference/blueberry/datatypes.pyx VERBATIM into oracle/_ref/ (next to blueberry.pyx's build).
+    Its constructors read hard-coded NFS path templates held in module globals (datatypes.pyx:25-29);
+    load_reference_datatypes() points those globals at temporary files, which is how ContactMap is driven here."""
+    if build_reference_cython(force) is None:
+        return None
+    pkg = os.path.join(REF_BUILD_DIR, "blueberry_ref")
+    have = any(f.startswith("datatypes.") and f.endswith(".so") for f in os.listdir(pkg))
+    if have and not force:
+        return REF_BUILD_DIR
+    if not reference_available():
+        return None
+    with open(os.path.join(REF_BUILD_DIR, "_setup_ref_dt.py"), "w") as fh:
+        fh.write(_SETUP_DT)
+    link = os.path.join(pkg, "datatypes.pyx")
+    if os.path.lexists(link):
+        os.remove(link)
+    os.symlink(os.path.join(REFERENCE_ROOT, "blueberry", "datatypes.pyx"), link)
+    try:
+        subprocess.check_call([sys.executable, "_setup_ref_dt.py"], cwd=REF_BUILD_DIR, stdout=subprocess.DEVNULL)
+    finally:
+        os.remove(link)
+    return REF_BUILD_DIR
+
+
+def load_reference_datatypes():
+    """Import the verbatim-compiled datatypes.pyx.  It does `from blueberry import *` at import (datatypes.pyx:23): the
+    compiled blueberry.pyx is registered under that name first."""
+    d = build_reference_datatypes()
+    if d is None:
+        return None
+    bb = load_reference_cython()
+    sys.modules.setdefault("blueberry", bb)
+    import importlib
+    return importlib.import_module("blueberry_ref.datatypes")

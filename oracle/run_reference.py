@@ -161,3 +161,27 @@ def run_reference_decimate(map5, resolution):
     obj = types.SimpleNamespace(map=np.array(map5, dtype=np.float64, copy=True), resolution=None, regions=None)
     ns["decimate"](obj, resolution)
     return obj.map
+
+
+def run_reference_contact_map(pos1, pos2, count, kr_norm, kr_expected, resolution):
+    """The reference's ContactMap (datatypes.pyx:88-171), compiled verbatim: constructor (dense scatter of the RAWobserved
+    rows) then normalize().  Its input paths come from module-level templates (datatypes.pyx:27-29); they are pointed at
+    temporary files here.  Returns (matrix after __init__, matrix after normalize, regions, n_bins)."""
+    dt = ref_loader.load_reference_datatypes()
+    tmp = tempfile.mkdtemp(prefix="bbk_refcm_")
+    dt.RAW_DIR = os.path.join(tmp, "{0}.chr{1}.{2}.RAWobserved")
+    dt.KR_NORM = os.path.join(tmp, "{0}.chr{1}.{2}.KRnorm")
+    dt.KR_EXP = os.path.join(tmp, "{0}.chr{1}.{2}.KRexpected")
+    for tag in (resolution // 1000, resolution / 1000):            # Python 2 formats an int here, Python 3 a float
+        for path, vec in ((dt.KR_NORM.format("cell", 1, tag), kr_norm), (dt.KR_EXP.format("cell", 1, tag), kr_expected)):
+            with open(path, "w") as fh:
+                for v in vec:
+                    fh.write("%r\n" % float(v))
+        with open(dt.RAW_DIR.format("cell", 1, tag), "w") as fh:
+            for a, b, c in zip(pos1, pos2, count):
+                fh.write("%r\t%r\t%r\n" % (float(a), float(b), float(c)))
+    cm = dt.ContactMap("cell", 1, resolution)
+    before = np.array(cm.matrix, copy=True)
+    regions = np.array(cm.regions, copy=True)
+    cm.normalize()
+    return before, np.array(cm.matrix, copy=True), regions, int(cm.n_bins)

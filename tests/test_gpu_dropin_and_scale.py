@@ -349,3 +349,33 @@ def test_decimate_matches_reference_golden_and_oracle(tmp_path):
     exact = pandas.read_csv(path, sep="\t", usecols=[1, 3, 4, 5, 6], engine='c', dtype='float64', float_precision='round_trip').values
     assert np.array_equal(exact, mp)
     assert cm.to_matrix('count', n_bins=600).sum() > 0
+
+
+def test_contact_map_band_records_match_compiled_reference(tmp_path):
+    """K8 (band ingest + normalize) against the golden matrices of the reference's ContactMap (compiled verbatim):
+    the records scattered into a zero matrix ARE the reference's matrix, before and after normalize()."""
+    from blueberry_b200.datatypes import ContactMap
+    g = load_golden("contact_map")
+    R = int(g["resolution"])
+    cm = ContactMap((g["pos1"], g["pos2"], g["count"]), g["kr_norm"], g["kr_expected"], resolution=R)
+    assert cm.n_bins == int(g["ref_n_bins"])
+    assert np.array_equal(cm.to_dense(), g["ref_matrix"])
+    assert np.array_equal(cm.regions, g["ref_regions"])
+    cm.normalize()
+    assert np.array_equal(cm.to_dense(), g["ref_normalized"])
+    # from files, like the reference reads them
+    raw, krp, kep = str(tmp_path / "c.RAWobserved"), str(tmp_path / "c.KRnorm"), str(tmp_path / "c.KRexpected")
+    with open(raw, "w") as fh:
+        for a, b, c in zip(g["pos1"], g["pos2"], g["count"]):
+            fh.write("%r\t%r\t%r\n" % (float(a), float(b), float(c)))
+    np.savetxt(krp, g["kr_norm"]); np.savetxt(kep, g["kr_expected"])
+    cm2 = ContactMap(raw, krp, kep, resolution=R)
+    cm2.normalize()
+    assert np.allclose(cm2.to_dense(), g["ref_normalized"], rtol=1e-12, atol=0)      # savetxt's %.18e text round trip
+    kr = g["kr_norm"].copy()
+    kr[int(np.nanargmax(kr))] = 0.0
+    bad = ContactMap((g["pos1"], g["pos2"], g["count"]), kr, g["kr_expected"], resolution=R)
+    with pytest.raises(ZeroDivisionError):
+        bad.normalize()
+    with pytest.raises(IndexError):
+        ContactMap((g["pos1"] + 10 ** 7, g["pos2"], g["count"]), g["kr_norm"], g["kr_expected"], resolution=R)

@@ -100,3 +100,18 @@ def test_decimate_oracle_matches_reference_method_output():
     d = do.decimate(m, 5000)
     assert d.tolist() == [[2500.0, 2500.0, 1.0, 0.5, 1.0], [2500.0, 7500.0, 5.0, 0.125, 0.2]]
     assert do.contacts(np.array([[1.0, 2.0, 3, 0.1, 0.01], [3.0, 4.0, 3, 0.1, 0.011]])).tolist() == [[1.0, 2.0]]
+
+
+def test_contact_map_oracle_matches_compiled_reference_output():
+    """oracle/datatypes_oracle.contact_map_dense / normalize_dense against tests/golden/contact_map.npz (the reference's
+    ContactMap compiled verbatim and run by oracle/make_golden.py, datatypes.pyx:88-171)."""
+    from oracle import datatypes_oracle as do
+    g = load_golden("contact_map")
+    m, regions = do.contact_map_dense(g["pos1"], g["pos2"], g["count"], int(g["ref_n_bins"]), int(g["resolution"]))
+    assert np.array_equal(m, g["ref_matrix"])
+    assert np.array_equal(regions, g["ref_regions"])
+    assert np.array_equal(do.normalize_dense(m, g["kr_norm"], g["kr_expected"], int(g["ref_n_bins"])), g["ref_normalized"])
+    kr = g["kr_norm"].copy()
+    kr[5] = 0.0
+    with pytest.raises(ZeroDivisionError):
+        do.normalize_dense(m, kr, g["kr_expected"], int(g["ref_n_bins"]))

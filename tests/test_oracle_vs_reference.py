@@ -48,3 +48,21 @@ def test_live_reference_decimate():
     mp = np.stack([m1, m2, rng.integers(0, 30, n), rng.random(n) ** 3, rng.random(n)], axis=1).astype(np.float64)
     for r in (2000, 5000, 25000):
         assert np.array_equal(run_reference.run_reference_decimate(mp, r), do.decimate(mp, r))
+
+
+def test_live_reference_contact_map():
+    """The dense ContactMap restatement against the reference class itself (compiled verbatim into oracle/_ref)."""
+    import numpy as np
+    from oracle import datatypes_oracle as do, run_reference
+    rng = np.random.default_rng(41)
+    nb, R = 30, 10000
+    kr = rng.random(nb) + 0.5
+    kr[[2, 11]] = np.nan
+    ke = rng.random(nb) * 20 + 1
+    b1 = rng.integers(0, nb + 1, 200)
+    b2 = np.minimum(b1 + rng.integers(0, 8, 200), nb)
+    cnt = rng.integers(1, 90, 200).astype(np.float64)
+    before, after, regions, n_bins = run_reference.run_reference_contact_map(b1 * R, b2 * R, cnt, kr, ke, R)
+    m, reg = do.contact_map_dense(b1 * R, b2 * R, cnt, n_bins, R)
+    assert n_bins == nb and np.array_equal(m, before) and np.array_equal(reg, regions)
+    assert np.array_equal(do.normalize_dense(m, kr, ke, n_bins), after)

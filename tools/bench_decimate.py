@@ -1,0 +1,62 @@
+"""Throughput of K7 (bbk_decimate) on device-resident columns, and of the oracle loop on a sample.
+
+    python tools/bench_decimate.py [rows]        (needs a GPU; the oracle leg is the CPU restatement of datatypes.pyx:317-339)
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from blueberry_b200 import _lib
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(5)
+    nb, K = 49851, 2000
+    i = torch.randint(0, nb, (n,), device=dev, generator=gen)
+    i, _ = torch.sort(i)                                         # row-major like a significances file
+    d = torch.randint(0, K, (n,), device=dev, generator=gen)
+    cols = torch.empty((5, n), dtype=torch.float64, device=dev)
+    cols[0] = (i * 1000 + 500).double()
+    cols[1] = ((i + d) * 1000 + 500).double()
+    cols[2] = torch.randint(0, 40, (n,), device=dev, generator=gen).double()
+    cols[3] = torch.rand(n, device=dev, generator=gen, dtype=torch.float64) ** 2
+    cols[4] = torch.rand(n, device=dev, generator=gen, dtype=torch.float64)
+    out = torch.empty((5, n), dtype=torch.float64, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.bbk_decimate_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+
+    def run():
+        _lib.check(lib.bbk_decimate(*[_lib.ptr(cols[k]) for k in range(5)], n, 5000, *[_lib.ptr(out[k]) for k in range(5)],
+                                    _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_decimate")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    g = int(n_out.item())
+    print("bbk_decimate: %d rows -> %d groups, %.2f ms, %.2f G rows/s, %.0f GB/s of the 40 B/row read + 40 B/group written"
+          % (n, g, ms, n / ms / 1e6, (40.0 * n + 40.0 * g) / ms / 1e6))
+    from oracle import datatypes_oracle as do
+    k = 300_000
+    sample = cols[:, :k].T.contiguous().cpu().numpy()
+    t = time.time()
+    ref = do.decimate(sample, 5000)
+    dt = time.time() - t
+    print("oracle loop (1 core): %d rows in %.2f s = %.3f M rows/s" % (k, dt, k / dt / 1e6))
+
+
+if __name__ == "__main__":
+    main()
