@@ -13,6 +13,12 @@ SIGNATURES = {
     "bbkio_write_significances": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), _i32, _vp, _vp, _vp, _vp, _vp,
                                                  _vp, _vp, _i64, _i32, _i32, ctypes.POINTER(_i64)]),
     "bbkio_format_double": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
+    "bbkio_read_interactions": (ctypes.c_int, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
+    "bbkio_table_rows": (_i64, [_vp]),
+    "bbkio_table_n_chrom": (_i32, [_vp]),
+    "bbkio_table_chrom_name": (ctypes.c_char_p, [_vp, _i32]),
+    "bbkio_table_copy": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bbkio_table_free": (None, [_vp]),
 }
 _lib = None
 
@@ -59,6 +65,37 @@ def write_significances(path, chrom_names, chr1, mid1, chr2, mid2, count, p, q=N
         lib.bbkio_last_error(buf, 512)
         raise BbkIoError("bbkio_write_significances failed (code %d): %s" % (rc, buf.value.decode(errors="replace")))
     return int(rows.value)
+
+
+def _raise(lib, what, rc):
+    buf = ctypes.create_string_buffer(512)
+    lib.bbkio_last_error(buf, 512)
+    msg = buf.value.decode(errors="replace")
+    if rc == -4:
+        # the reference's own failure for a malformed row: ValueError from the tuple unpack / int() (fithic.py:245-247)
+        raise ValueError(msg.split(": ", 1)[-1])
+    raise BbkIoError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def read_interactions(path, threads=0):
+    """fithic.py:243-247 on a whole file: returns (names, chr1, mid1, chr2, mid2, count) with chr1/chr2 int32 ids into
+    `names` (order of first appearance), the rest int64.  One thread inflates, the others parse."""
+    lib = load()
+    handle = _vp()
+    rc = lib.bbkio_read_interactions(os.fsencode(path), int(threads), ctypes.byref(handle))
+    if rc != 0:
+        _raise(lib, "bbkio_read_interactions", rc)
+    try:
+        n = int(lib.bbkio_table_rows(handle))
+        names = [lib.bbkio_table_chrom_name(handle, i).decode() for i in range(int(lib.bbkio_table_n_chrom(handle)))]
+        c1, c2 = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        m1, m2, cnt = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        rc = lib.bbkio_table_copy(handle, _ptr(c1), _ptr(m1), _ptr(c2), _ptr(m2), _ptr(cnt))
+        if rc != 0:
+            _raise(lib, "bbkio_table_copy", rc)
+    finally:
+        lib.bbkio_table_free(handle)
+    return names, c1, m1, c2, m2, cnt
 
 
 def format_double(x):

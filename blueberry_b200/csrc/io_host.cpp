@@ -1,4 +1,5 @@
 // io_host.cpp - libbbkio.so: the significances writer of include/bbk_io.h (host only).
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdarg>
@@ -192,3 +193,249 @@ extern "C" int bbkio_write_significances(const char* path, const char* const* ch
     if (rows_written) *rows_written = total;
     return rc;
 }
+
+// =====================================================================================================================
+// reader: the interactions file (fithic.py:243-247)
+// =====================================================================================================================
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <unordered_map>
+
+struct BbkioTable {
+    std::vector<std::string> names;
+    std::vector<int32_t> chr1, chr2;
+    std::vector<int64_t> mid1, mid2, count;
+};
+
+namespace {
+
+struct Block {                       // whole lines of text + the (1-based) number of its first line
+    std::string text;
+    long long first_line = 0;
+    long long index = 0;
+};
+
+struct Parsed {
+    std::vector<int32_t> chr1, chr2;                 // block-local name ids
+    std::vector<int64_t> mid1, mid2, count;
+    std::vector<std::string> names;                  // block-local names in order of first appearance
+    std::string error;
+};
+
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+// Python's int() on a field: optional sign, decimal digits (underscore separators and other exotica are not accepted)
+inline bool parse_int(const char* b, const char* e, int64_t* out) {
+    if (b == e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = *b == '-'; ++b; }
+    if (b == e || e - b > 18) return false;
+    int64_t v = 0;
+    for (; b < e; ++b) {
+        if (*b < '0' || *b > '9') return false;
+        v = v * 10 + (*b - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
+void parse_block(const Block& B, Parsed& P) {
+    std::unordered_map<std::string, int32_t> ids;
+    const char* p = B.text.data();
+    const char* end = p + B.text.size();
+    long long line_no = B.first_line;
+    auto name_id = [&](const char* b, const char* e) {
+        std::string s(b, e);
+        auto it = ids.find(s);
+        if (it != ids.end()) return it->second;
+        int32_t id = (int32_t)P.names.size();
+        ids.emplace(s, id);
+        P.names.push_back(std::move(s));
+        return id;
+    };
+    const size_t guess = B.text.size() / 28 + 16;
+    P.chr1.reserve(guess); P.chr2.reserve(guess); P.mid1.reserve(guess); P.mid2.reserve(guess); P.count.reserve(guess);
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char* tb[6];
+        const char* te[6];
+        int nf = 0;
+        const char* q = p;
+        while (q < eol) {
+            while (q < eol && is_space(*q)) ++q;
+            if (q == eol) break;
+            const char* b = q;
+            while (q < eol && !is_space(*q)) ++q;
+            if (nf < 6) { tb[nf] = b; te[nf] = q; }
+            ++nf;
+        }
+        if (nf != 5) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), nf < 5 ? "line %lld: not enough values to unpack (expected 5, got %d)"
+                                               : "line %lld: too many values to unpack (expected 5)", line_no, nf);
+            P.error = msg;
+            return;
+        }
+        int64_t m1, m2, c;
+        if (!parse_int(tb[1], te[1], &m1) || !parse_int(tb[3], te[3], &m2) || !parse_int(tb[4], te[4], &c)) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "line %lld: invalid literal for int() with base 10", line_no);
+            P.error = msg;
+            return;
+        }
+        P.chr1.push_back(name_id(tb[0], te[0]));
+        P.chr2.push_back(name_id(tb[2], te[2]));
+        P.mid1.push_back(m1); P.mid2.push_back(m2); P.count.push_back(c);
+        p = eol + 1;
+        ++line_no;
+    }
+}
+
+}  // namespace
+
+extern "C" int bbkio_read_interactions(const char* path, int32_t threads, BbkioTable** out) {
+    if (!path || !out) { set_error("bbkio_read_interactions: bad arguments"); return BBKIO_E_INVALID; }
+    *out = nullptr;
+    gzFile gz = gzopen(path, "rb");                  // reads plain text too; continues over concatenated members
+    if (!gz) { set_error("bbkio_read_interactions: cannot open %s", path); return BBKIO_E_IO; }
+    gzbuffer(gz, 1 << 20);
+    int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_space;
+    std::deque<Block> queue;
+    bool done = false, failed = false;
+    std::vector<Parsed> results;                     // indexed by block
+    std::mutex res_mu;
+    std::string first_error;
+    long long first_error_block = -1;
+    auto worker = [&]() {
+        for (;;) {
+            Block B;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return !queue.empty() || done; });
+                if (queue.empty()) return;
+                B = std::move(queue.front());
+                queue.pop_front();
+            }
+            cv_space.notify_one();
+            Parsed P;
+            parse_block(B, P);
+            std::lock_guard<std::mutex> lk(res_mu);
+            if (!P.error.empty() && (first_error_block < 0 || B.index < first_error_block)) { first_error_block = B.index; first_error = P.error; failed = true; }
+            if ((long long)results.size() <= B.index) results.resize(B.index + 1);
+            results[B.index] = std::move(P);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t) pool.emplace_back(worker);
+    const size_t CHUNK = 8u << 20;
+    std::string carry;
+    long long line_no = 1, index = 0;
+    int io_rc = BBKIO_OK;
+    std::vector<char> buf(CHUNK);
+    for (;;) {
+        int got = gzread(gz, buf.data(), (unsigned)CHUNK);
+        if (got < 0) { int e; set_error("bbkio_read_interactions: %s", gzerror(gz, &e)); io_rc = BBKIO_E_ZLIB; break; }
+        const bool last = got == 0;
+        Block B;
+        if (!last) {
+            // cut at the last newline; the rest waits for the next chunk
+            int cut = got;
+            while (cut > 0 && buf[cut - 1] != '\n') --cut;
+            B.text = std::move(carry);
+            B.text.append(buf.data(), (size_t)cut);
+            carry.assign(buf.data() + cut, (size_t)(got - cut));
+            if (cut == 0) { carry = std::move(B.text) + carry; continue; }       // no newline in this chunk yet
+        } else {
+            if (carry.empty()) break;
+            B.text = std::move(carry);                                       // last line without a newline
+            carry.clear();
+        }
+        B.first_line = line_no;
+        B.index = index++;
+        for (char ch : B.text) line_no += ch == '\n';
+        if (last && (B.text.empty() || B.text.back() != '\n')) line_no += 1;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_space.wait(lk, [&] { return (int)queue.size() < 2 * T; });
+            queue.push_back(std::move(B));
+        }
+        cv_work.notify_one();
+        if (last) break;
+        { std::lock_guard<std::mutex> lk(res_mu); if (failed) break; }
+    }
+    { std::lock_guard<std::mutex> lk(mu); done = true; }
+    cv_work.notify_all();
+    for (auto& th : pool) th.join();
+    gzclose(gz);
+    if (io_rc != BBKIO_OK) return io_rc;
+    if (failed) { set_error("bbkio_read_interactions: %s", first_error.c_str()); return BBKIO_E_PARSE; }
+    // stitch: global name ids in order of first appearance over the blocks
+    BbkioTable* Tb = new BbkioTable();
+    std::unordered_map<std::string, int32_t> gids;
+    size_t total = 0;
+    for (auto& P : results) total += P.mid1.size();
+    Tb->chr1.resize(total); Tb->chr2.resize(total); Tb->mid1.resize(total); Tb->mid2.resize(total); Tb->count.resize(total);
+    std::vector<size_t> offs(results.size() + 1, 0);
+    std::vector<std::vector<int32_t>> luts(results.size());
+    for (size_t b = 0; b < results.size(); ++b) {
+        offs[b + 1] = offs[b] + results[b].mid1.size();
+        // first appearance inside a block is not by row for chr2 before chr1 of the same row: keep the row order exact
+        auto& P = results[b];
+        luts[b].assign(P.names.size(), -1);
+        for (size_t i = 0; i < P.chr1.size(); ++i) {
+            for (int32_t loc : {P.chr1[i], P.chr2[i]}) {
+                if (luts[b][loc] >= 0) continue;
+                auto it = gids.find(P.names[loc]);
+                if (it == gids.end()) { int32_t id = (int32_t)Tb->names.size(); gids.emplace(P.names[loc], id); Tb->names.push_back(P.names[loc]); luts[b][loc] = id; }
+                else luts[b][loc] = it->second;
+            }
+            bool all = true;
+            for (int32_t v : luts[b]) all = all && v >= 0;
+            if (all) break;
+        }
+    }
+    std::vector<std::thread> copy_pool;
+    std::atomic<size_t> next(0);
+    for (int t = 0; t < T; ++t) {
+        copy_pool.emplace_back([&]() {
+            for (;;) {
+                size_t b = next.fetch_add(1);
+                if (b >= results.size()) return;
+                auto& P = results[b];
+                const size_t o = offs[b], m = P.mid1.size();
+                for (size_t i = 0; i < m; ++i) { Tb->chr1[o + i] = luts[b][P.chr1[i]]; Tb->chr2[o + i] = luts[b][P.chr2[i]]; }
+                if (m) {
+                    memcpy(&Tb->mid1[o], P.mid1.data(), m * sizeof(int64_t));
+                    memcpy(&Tb->mid2[o], P.mid2.data(), m * sizeof(int64_t));
+                    memcpy(&Tb->count[o], P.count.data(), m * sizeof(int64_t));
+                }
+                Parsed().chr1.swap(P.chr1); Parsed().mid1.swap(P.mid1); Parsed().mid2.swap(P.mid2); Parsed().count.swap(P.count); Parsed().chr2.swap(P.chr2);
+            }
+        });
+    }
+    for (auto& th : copy_pool) th.join();
+    *out = Tb;
+    return BBKIO_OK;
+}
+
+extern "C" int64_t bbkio_table_rows(const BbkioTable* t) { return t ? (int64_t)t->mid1.size() : 0; }
+extern "C" int32_t bbkio_table_n_chrom(const BbkioTable* t) { return t ? (int32_t)t->names.size() : 0; }
+extern "C" const char* bbkio_table_chrom_name(const BbkioTable* t, int32_t id) {
+    return (t && id >= 0 && id < (int32_t)t->names.size()) ? t->names[id].c_str() : nullptr;
+}
+extern "C" int bbkio_table_copy(const BbkioTable* t, int32_t* chr1, int64_t* mid1, int32_t* chr2, int64_t* mid2, int64_t* count) {
+    if (!t) { set_error("bbkio_table_copy: null table"); return BBKIO_E_INVALID; }
+    const size_t n = t->mid1.size();
+    if (chr1 && n) memcpy(chr1, t->chr1.data(), n * sizeof(int32_t));
+    if (chr2 && n) memcpy(chr2, t->chr2.data(), n * sizeof(int32_t));
+    if (mid1 && n) memcpy(mid1, t->mid1.data(), n * sizeof(int64_t));
+    if (mid2 && n) memcpy(mid2, t->mid2.data(), n * sizeof(int64_t));
+    if (count && n) memcpy(count, t->count.data(), n * sizeof(int64_t));
+    return BBKIO_OK;
+}
+extern "C" void bbkio_table_free(BbkioTable* t) { delete t; }

@@ -99,11 +99,11 @@ def _parse_fragments(path, chroms):
 
 
 def _parse_interactions(path, chroms):
-    df = _read_table(path, 5)                                  # fithic.py:245
-    if df.shape[1] != 5:
-        raise ValueError("too many values to unpack (expected 5)")
-    return (chroms.encode(df[0].values), df[1].values.astype(np.int64), chroms.encode(df[2].values),
-            df[3].values.astype(np.int64), df[4].values.astype(np.int64))
+    """fithic.py:243-247 on the whole file, by the native reader (libbbkio.so, include/bbk_io.h)."""
+    from . import _io
+    names, c1, m1, c2, m2, cnt = _io.read_interactions(path)
+    lut = chroms.encode(names) if names else np.zeros(0, dtype=np.int32)
+    return lut[c1], m1, lut[c2], m2, cnt
 
 
 # =================================================================================================

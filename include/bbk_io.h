@@ -35,6 +35,22 @@ int bbkio_write_significances(const char* path, const char* const* chrom_names, 
                               const double* p, const double* q, int64_t n, int32_t threads, int32_t level,
                               int64_t* rows_written);
 
+/* replaces the read loop of fithic.py:243-247 (`chr1, mid1, chr2, mid2, contactCount = line.rstrip().split()`).
+ * Reads a gzip (or plain) text file of whitespace-separated rows into columns: one thread inflates, `threads` parse.
+ * Chromosome names become small ids in order of first appearance (bbkio_table_chrom_name gives them back).
+ * Errors like the reference's unpack / int(): a row with fewer or more than 5 fields, or a non-integer mid / count,
+ * fails the call (BBKIO_E_PARSE; bbkio_last_error names the line).  Blank lines fail too (zero fields), as in the reference.
+ * The table is owned by the library until bbkio_table_free. */
+#define BBKIO_E_PARSE (-4)
+typedef struct BbkioTable BbkioTable;
+int bbkio_read_interactions(const char* path, int32_t threads, BbkioTable** out);
+int64_t bbkio_table_rows(const BbkioTable* t);
+int32_t bbkio_table_n_chrom(const BbkioTable* t);
+const char* bbkio_table_chrom_name(const BbkioTable* t, int32_t id);
+/* copies the five columns out (each pointer may be NULL to skip that column) */
+int bbkio_table_copy(const BbkioTable* t, int32_t* chr1, int64_t* mid1, int32_t* chr2, int64_t* mid2, int64_t* count);
+void bbkio_table_free(BbkioTable* t);
+
 /* "{}".format(float64) into buf (at least 32 bytes); returns the length.  Exposed for the parity tests. */
 int bbkio_format_double(double x, char* buf);
 

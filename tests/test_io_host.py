@@ -88,3 +88,77 @@ def test_single_chromosome_shortcut_and_errors(io, tmp_path):
         io.write_significances(str(tmp_path / "nodir" / "x.gz"), ["chr7"], None, [1], None, [2], [3], np.array([0.1]))
     with pytest.raises(io.BbkIoError):
         io.write_significances(path, ["chr7"], np.array([1], np.int32), [1], np.array([0], np.int32), [2], [3], np.array([0.1]))
+
+
+def _ref_parse(path):
+    """fithic.py:243-247, line by line."""
+    rows = []
+    with gzip.open(path, "rt") as fh:
+        for line in fh:
+            ch1, mid1, ch2, mid2, contactCount = line.rstrip().split()
+            rows.append((ch1, int(mid1), ch2, int(mid2), int(contactCount)))
+    return rows
+
+
+@pytest.mark.parametrize("n,threads", [(0, 1), (3, 1), (400000, 3), (400000, 0)])
+def test_reader_matches_the_reference_loop(io, tmp_path, n, threads):
+    rng = np.random.default_rng(n + 7)
+    names = np.array(["chr1", "chr10", "chrX", "scaffold_12"])
+    a = names[rng.integers(0, 4, n)]
+    b = names[rng.integers(0, 4, n)]
+    m1 = rng.integers(-5, 250_000_000, n)
+    m2 = rng.integers(0, 250_000_000, n)
+    cnt = rng.integers(0, 100000, n)
+    seps = ["\t", " ", "  \t "]
+    path = str(tmp_path / "inter.gz")
+    with gzip.open(path, "wt", compresslevel=1) as fh:          # rows of the shapes str.split() accepts
+        chunks = []
+        for i in range(n):
+            s = seps[i % 3]
+            chunks.append("%s%s%s%d%s%s%s%d%s%d%s\n" % ("  " if i % 5 == 0 else "", a[i], s, m1[i], s, b[i], s, m2[i], s, cnt[i],
+                                                        " \r" if i % 7 == 0 else ""))
+        text = "".join(chunks)
+        fh.write(text[:-1] if n == 3 else text)                 # n == 3: last line without a newline
+    got_names, c1, g1, c2, g2, gc = io.read_interactions(path, threads=threads)
+    want = _ref_parse(path)
+    assert len(want) == n == len(g1)
+    if n:
+        gn = np.array(got_names)
+        assert [tuple(r) for r in zip(gn[c1], g1, gn[c2], g2, gc)] == want
+        first = []
+        for r in want:                                          # ids follow first appearance (chr1 before chr2 in a row)
+            for nm in (r[0], r[2]):
+                if nm not in first:
+                    first.append(nm)
+        assert got_names == first
+
+
+def test_reader_accepts_plain_text_and_concatenated_gzip_members(io, tmp_path):
+    rows = "chr1\t10\tchr1\t20\t3\nchr2 5 chr1 7 0\n"
+    plain = tmp_path / "plain.txt"
+    plain.write_text(rows)
+    names, c1, m1, c2, m2, cnt = io.read_interactions(str(plain))
+    assert names == ["chr1", "chr2"] and m1.tolist() == [10, 5] and cnt.tolist() == [3, 0] and c2.tolist() == [0, 0]
+    multi = tmp_path / "multi.gz"
+    with open(multi, "wb") as fh:
+        fh.write(gzip.compress(rows.encode()))
+        fh.write(gzip.compress(b"chrX\t1\tchrX\t2\t9\n"))
+    names, c1, m1, c2, m2, cnt = io.read_interactions(str(multi))
+    assert names == ["chr1", "chr2", "chrX"] and cnt.tolist() == [3, 0, 9]
+
+
+@pytest.mark.parametrize("bad,msg", [("chr1\t1\tchr1\t2\n", "not enough values to unpack (expected 5, got 4)"),
+                                     ("chr1\t1\tchr1\t2\t3\t4\n", "too many values to unpack (expected 5)"),
+                                     ("chr1\t1.5\tchr1\t2\t3\n", "invalid literal for int() with base 10"),
+                                     ("chr1\t1\tchr1\t2\t3\n\nchr1\t1\tchr1\t2\t3\n", "not enough values to unpack (expected 5, got 0)")])
+def test_reader_fails_like_the_reference_on_malformed_rows(io, tmp_path, bad, msg):
+    path = str(tmp_path / "bad.gz")
+    with gzip.open(path, "wt") as fh:
+        fh.write("chr1\t1\tchr1\t2\t3\n" * 10 + bad)
+    with pytest.raises(ValueError) as e:
+        io.read_interactions(path)
+    assert msg in str(e.value)
+    with pytest.raises(ValueError):                             # and so does the reference's loop
+        _ref_parse(path)
+    with pytest.raises(io.BbkIoError):
+        io.read_interactions(str(tmp_path / "missing.gz"))
