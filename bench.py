@@ -237,18 +237,27 @@ def run_ours(args, out_fd):
     p_first = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P] if two_pass else None
     p_outlier = 1.0 / float(world * (nb * (K + 1) - K * (K + 1) // 2 - nb))   # 1 / possibleIntraInRangeCount (d = R..K*R)
 
-    def step():
-        eng.hist([shard])
+    def bh_on(pp, qq):
+        if genome_q:
+            eng.qvalues_global(pp, qq, n_tests=-1, group=group, hist=eng.p_hist, prepared=True)
+        else:
+            eng.qvalues(pp, qq, n_tests=-1, use_hist=True, prepared=True)
+
+    def step_on(sh, pp, qq):
+        eng.hist([sh])
         eng.allreduce_stats(group)
         eng.fit()
         eng.p_hist.zero_()
         if two_pass:
-            eng.pvalues(shard, p_first, with_hist=False)
-            eng.hist_excluding([shard], [p_first], p_outlier)
+            eng.pvalues(sh, p_first, with_hist=False)
+            eng.hist_excluding([sh], [p_first], p_outlier)
             eng.allreduce_stats(group)
             eng.fit()
-        eng.pvalues(shard, p, with_hist=True, q_out=q)
-        bh()
+        eng.pvalues(sh, pp, with_hist=True, q_out=qq)
+        bh_on(pp, qq)
+
+    def step():
+        step_on(shard, p, q)
 
     def barrier():
         if world > 1:
@@ -322,22 +331,11 @@ def run_ours(args, out_fd):
         h.copy_(d)
     h_out = [(torch.empty(P, dtype=torch.float64).pin_memory(), torch.empty(P, dtype=torch.float64).pin_memory()) for _ in range(2)]
     torch.cuda.synchronize()
-    if two_pass or genome_q:      # these step bodies are not a plain eng.run(): one slot, stage by stage
-        pipe, e2e_mode = None, "serial"
-    else:
-        pipe, e2e_mode = HostPipeline(eng, P, chrom=rank, slots=2), "pipelined across steps (2 device slots)"
+    pipe, e2e_mode = HostPipeline(eng, P, chrom=rank, slots=2), "pipelined across steps (2 device slots)"
 
     def e2e_step(k):
         h_p, h_q = h_out[k % 2]
-        if pipe is not None:
-            pipe.submit(h_in[0], h_in[1], h_in[2], h_p, h_q)
-            return
-        mid1.copy_(h_in[0], non_blocking=True)
-        mid2.copy_(h_in[1], non_blocking=True)
-        count.copy_(h_in[2], non_blocking=True)
-        step()
-        h_p.copy_(p, non_blocking=True)
-        h_q.copy_(q, non_blocking=True)
+        pipe.submit(h_in[0], h_in[1], h_in[2], h_p, h_q, run=step_on)
 
     def e2e_drain():
         if pipe is not None:

@@ -342,9 +342,11 @@ class HostPipeline(object):
         self.s_run.wait_stream(torch.cuda.current_stream(dev))      # the engine's tables were filled there
         self.submitted = 0
 
-    def submit(self, h_mid1, h_mid2, h_count, h_p, h_q=None, n_tests=-1):
+    def submit(self, h_mid1, h_mid2, h_count, h_p, h_q=None, n_tests=-1, run=None):
         """Enqueue one pass: pinned int32 host columns in, p (and q when h_q is given) back into pinned float64
-        host buffers.  Returns the event that fires when the outputs are on the host."""
+        host buffers.  Returns the event that fires when the outputs are on the host.
+        run (optional): callable(shard, p, q) that enqueues the pass on the current stream instead of engine.run -
+        e.g. the multi-GPU sequence with its all-reduce and genome-wide q-values."""
         n = int(h_mid1.numel())
         if n > self.max_pairs or h_mid2.numel() != n or h_count.numel() != n or h_p.numel() != n:
             raise ValueError("library larger than the pipeline's slots, or columns differ in length")
@@ -363,7 +365,10 @@ class HostPipeline(object):
         self.s_run.wait_event(s.out_done)       # this slot's previous p/q have left the device
         with torch.cuda.stream(self.s_run):
             sh = Shard(s.mid1[:n], s.mid2[:n], s.count[:n], chrom=self.chrom)
-            self.eng.run([sh], [s.p[:n]], [s.q[:n]] if h_q is not None else None, n_tests=n_tests)
+            if run is not None:
+                run(sh, s.p[:n], s.q[:n] if h_q is not None else None)
+            else:
+                self.eng.run([sh], [s.p[:n]], [s.q[:n]] if h_q is not None else None, n_tests=n_tests)
             s.run_done.record()
         self.s_out.wait_event(s.run_done)
         with torch.cuda.stream(self.s_out):
