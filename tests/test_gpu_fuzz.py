@@ -1,0 +1,83 @@
+"""Randomised differential test: the device pass (through the drop-in array entry point) against the CPU oracle on
+small inputs with varied resolution, n_bins, distance limits, depth, bias presence, zero rows, chromosome mixes and
+row order.  Integer stages and the fit are compared bit for bit, p to 1e-5 in log10 (the oracle's p is scipy's bdtrc,
+which is itself that far from the true tail at large S), q bit for bit on the device's own p."""
+import numpy as np
+import pytest
+
+from helpers import log10_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed):
+    from blueberry_b200 import synth
+    rng = np.random.default_rng(1000 + seed)
+    n_chrom = int(rng.integers(1, 4))
+    bins = [int(rng.integers(60, 700)) for _ in range(n_chrom)]
+    R = int(rng.choice([1000, 5000, 10000, 40000]))
+    span = max(bins) * R
+    max_dist = int(rng.choice([-1, span // 3, span // 2, 10 * span]))
+    min_dist = int(rng.choice([-1, -1, 2 * R, 5 * R]))
+    n_bins = int(rng.choice([20, 50, 100, 100, 200]))
+    depth = float(rng.choice([3.0, 20.0, 150.0, 1500.0]))
+    with_bias = bool(rng.random() < 0.7)
+    keep_zeros = bool(rng.random() < 0.6)
+    bias = synth.make_bias(bins, seed, sigma=float(rng.choice([0.1, 0.25, 0.5]))) if with_bias else None
+    fc, fm = synth.make_fragments(bins, R)
+    c = synth.make_contacts(bins, R, max_dist if max_dist > 0 else 10 ** 9, depth, seed, bias, keep_zeros=keep_zeros)
+    chr1, chr2 = c["chrom"].copy(), c["chrom"].copy()
+    mid1, mid2, cnt = c["mid1"].copy(), c["mid2"].copy(), c["count"].copy()
+    n = len(cnt)
+    if n and rng.random() < 0.5:                               # inter-chromosomal rows, off-grid and negative distances, shuffle
+        k = rng.choice(n, max(n // 50, 1), replace=False)
+        chr2[k] = (chr2[k] + 1) % max(n_chrom, 2)
+        k = rng.choice(n, max(n // 80, 1), replace=False)
+        mid2[k] += 777
+        k = rng.choice(n, max(n // 100, 1), replace=False)
+        mid1[k], mid2[k] = mid2[k].copy(), mid1[k].copy()
+        perm = rng.permutation(n)
+        chr1, chr2, mid1, mid2, cnt = chr1[perm], chr2[perm], mid1[perm], mid2[perm], cnt[perm]
+    barr = None
+    if with_bias:
+        bc = np.concatenate([np.full(b, i, dtype=np.int32) for i, b in enumerate(bins)])
+        barr = (bc, fm.copy(), np.concatenate(bias))
+    return dict(R=R, n_bins=n_bins, min_dist=min_dist, max_dist=max_dist, fc=fc, fm=fm, chr1=chr1, mid1=mid1, chr2=chr2, mid2=mid2,
+                cnt=cnt, bias=barr)
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_pass_against_oracle(seed):
+    import warnings
+    from blueberry_b200.fithic import FitHiC
+    from oracle import fithic_oracle as fo
+    k = _case(seed)
+    model = FitHiC("unused", k["R"], n_bins=k["n_bins"], max_dist=k["max_dist"], min_dist=k["min_dist"])
+    bd = fo.read_bias_arrays(*k["bias"])[0] if k["bias"] is not None else None
+    ref, ref_err = None, None
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            ref = fo.fithic_arrays(k["fc"], k["fm"], k["chr1"], k["mid1"], k["chr2"], k["mid2"], k["cnt"], k["R"], k["n_bins"],
+                                   model.min_dist, model.max_dist, bias=bd)
+        except Exception as e:                                  # what the reference would raise on this input
+            ref_err = e
+    if ref_err is not None:
+        with pytest.raises(type(ref_err)):
+            model.fit_transform_arrays(k["chr1"], k["mid1"], k["chr2"], k["mid2"], k["cnt"], k["fc"], k["fm"], bias=k["bias"], q_values=True)
+        return
+    out = model.fit_transform_arrays(k["chr1"], k["mid1"], k["chr2"], k["mid2"], k["cnt"], k["fc"], k["fm"], bias=k["bias"], q_values=True)
+    assert np.array_equal(out.possible, ref.frag.possible)
+    assert np.array_equal(out.observed, ref.contacts.observed)
+    assert out.totals["observedIntraInRangeSum"] == ref.contacts.S
+    assert np.array_equal(out.bin_of_key, ref.bin_of_key)
+    assert np.array_equal(out.x, np.array(ref.x)) and np.array_equal(out.y, np.array(ref.y))
+    assert out.spline_x[0] == ref.k0 * k["R"] and len(out.spline_y) == len(ref.spline_y)
+    assert np.array_equal(out.spline_y, ref.spline_y)
+    assert np.array_equal(out.keep, ref.keep)
+    sel = ref.keep & (ref.p >= 1e-300)
+    ok, nbad = log10_close(out.p[sel], ref.p[sel], 1e-5)
+    assert ok, "%d p-values differ by more than 1e-5 in log10" % nbad
+    assert (out.p[ref.keep & (ref.p < 1e-300)] <= 1e-299).all()
+    qref = fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum()))
+    assert np.array_equal(out.q[out.keep], qref)
