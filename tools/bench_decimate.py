@@ -1,10 +1,9 @@
-"""Throughput of K7 (bbk_decimate) on device-resident columns, and of the oracle loop on a sample.
+"""Throughput of K7 (bbk_decimate) on device-resident columns.
 
-    python tools/bench_decimate.py [rows]        (needs a GPU; the oracle leg is the CPU restatement of datatypes.pyx:317-339)
+    python tools/bench_decimate.py [rows]        (needs a GPU)
 """
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -49,13 +48,6 @@ def main():
     g = int(n_out.item())
     print("bbk_decimate: %d rows -> %d groups, %.2f ms, %.2f G rows/s, %.0f GB/s of the 40 B/row read + 40 B/group written"
           % (n, g, ms, n / ms / 1e6, (40.0 * n + 40.0 * g) / ms / 1e6))
-    from oracle import datatypes_oracle as do
-    k = 300_000
-    sample = cols[:, :k].T.contiguous().cpu().numpy()
-    t = time.time()
-    ref = do.decimate(sample, 5000)
-    dt = time.time() - t
-    print("oracle loop (1 core): %d rows in %.2f s = %.3f M rows/s" % (k, dt, k / dt / 1e6))
 
 
 if __name__ == "__main__":
