@@ -319,6 +319,7 @@ def run_ours(args, out_fd):
     k4_traffic = 2.6941e9 if (nb == CHR1_BINS and not two_pass) else None
     roofline = {"bound": "hbm", "kernel": "pvalues_kernel (K4)", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                 "frac": k4_gbs / peak, "traffic": k4_traffic, "peak_source": peak_src,
+                "traffic_note": "K4's DRAM bytes include the 8 B/pair of q it writes for K5 (hand-over); its own algorithmic bytes are 20 B/pair, read once and written once",
                 "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * P,
                 "whole_pass_frac": (104 if two_pass else BYTES_PER_PAIR) * P / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stage_gbs": {"hist": 12 * P / (acc["hist"] * 1e-3) / 1e9, "pvalues": k4_gbs,
