@@ -64,7 +64,7 @@ SIGNATURES = {
     "bbk_bh_qvalues_prepared": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "bbk_bh_qvalues": (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bbk_decimate_workspace_bytes": (_sz, [_i64]),
-    "bbk_decimate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bbk_decimate": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "bbk_contact_band_ingest": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "bbk_contact_band_normalize": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bbk_p_hist": (ctypes.c_int, [_vp, _i64, _vp, _vp]),

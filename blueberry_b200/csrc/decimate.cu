@@ -19,13 +19,13 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {    
     return (a % b < 0) ? q - 1 : q;
 }
 
-__global__ void __launch_bounds__(DC_THREADS) dec_keys_kernel(const double* mid1, const double* mid2, long long n, long long r,
+__global__ void __launch_bounds__(DC_THREADS) dec_keys_kernel(const double* map, long long n, long long r,
                                                               unsigned long long* keys, unsigned* idx, unsigned long long* counters,
                                                               int* bad) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = 0;                    // group counter of dec_heads_kernel
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double a = mid1[i], b = mid2[i];
+        const double a = map[5 * i], b = map[5 * i + 1];
         // .astype('int') truncates toward zero; coordinates must be representable (and leave room for + r)
         if (!(a > -1.0 && a < 2147483647.0 && b > -1.0 && b < 2147483647.0)) { *bad = 1; keys[i] = 0; idx[i] = (unsigned)i; continue; }
         const long long ia = (long long)a, ib = (long long)b;
@@ -40,32 +40,37 @@ __global__ void __launch_bounds__(DC_THREADS) dec_keys_kernel(const double* mid1
 // second sort's input
 __global__ void __launch_bounds__(DC_THREADS) dec_heads_kernel(const unsigned long long* keys, const unsigned* idx, long long n,
                                                                unsigned long long* hkeys, unsigned* hpos, unsigned long long* counters) {
+    // one global atomic per CTA step (a warp-aggregated atomic per warp was 1.5e6 same-address atomics on 5e7 rows: 1 ms)
+    __shared__ unsigned s_warp[DC_THREADS / 32];
+    __shared__ unsigned long long s_base;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n_iter = (n + stride - 1) / stride;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long it = 0; it < n_iter; ++it, i += stride) {
         const bool head = i < n && (i == 0 || keys[i - 1] != keys[i]);
         const unsigned vote = __ballot_sync(0xffffffffu, head);
-        if (vote) {
-            unsigned long long base = 0;
-            if (lane == __ffs(vote) - 1) base = atomicAdd(&counters[0], (unsigned long long)__popc(vote));
-            base = __shfl_sync(0xffffffffu, base, __ffs(vote) - 1);
-            if (head) {
-                const unsigned long long pos = base + __popc(vote & ((1u << lane) - 1));
-                hkeys[pos] = (unsigned long long)idx[i];       // the sort is stable: the head is the run's first row in the file
-                hpos[pos] = (unsigned)i;
-            }
+        if (lane == 0) s_warp[warp] = __popc(vote);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int w = 0; w < DC_THREADS / 32; ++w) { unsigned v = s_warp[w]; s_warp[w] = tot; tot += v; }
+            s_base = tot ? atomicAdd(&counters[0], (unsigned long long)tot) : 0ull;
         }
+        __syncthreads();
+        if (head) {
+            const unsigned long long pos = s_base + s_warp[warp] + __popc(vote & ((1u << lane) - 1));
+            hkeys[pos] = (unsigned long long)idx[i];       // the sort is stable: the head is the run's first row in the file
+            hpos[pos] = (unsigned)i;
+        }
+        __syncthreads();
     }
 }
 
 // output row k = the k-th group to appear in the file, folded member by member in file order
 __global__ void __launch_bounds__(DC_THREADS) dec_fold_kernel(const unsigned long long* keys, const unsigned* idx, long long n,
                                                               const unsigned* hpos, const unsigned long long* counters,
-                                                              const double* count, const double* p, const double* q,
-                                                              double* o_mid1, double* o_mid2, double* o_count, double* o_p, double* o_q,
-                                                              long long* n_out) {
+                                                              const double* map, double* out, long long* n_out) {
     const long long groups = (long long)counters[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = groups;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -74,15 +79,16 @@ __global__ void __launch_bounds__(DC_THREADS) dec_fold_kernel(const unsigned lon
         const unsigned long long key = keys[j];
         double c = 0.0, pp = 1.0, qq = 1.0;
         for (; j < n && keys[j] == key; ++j) {
-            const unsigned row = idx[j];
-            c = count[row] + c;                                 // contactCount + contact0      (:335)
-            pp = p[row] * pp;                                   // p * p0
-            const double qv = q[row];
+            const double* row = map + 5ll * idx[j];             // count, p, q of a row sit together: one sector or two per member
+            c = row[2] + c;                                     // contactCount + contact0      (:335)
+            pp = row[3] * pp;                                   // p * p0
+            const double qv = row[4];
             qq = (qq < qv) ? qq : qv;                           // Python's min(q, q0): q0 only when q0 < q
         }
-        o_mid1[k] = (double)(key >> 32);
-        o_mid2[k] = (double)(key & 0xffffffffull);
-        o_count[k] = c; o_p[k] = pp; o_q[k] = qq;
+        double* o = out + 5 * k;
+        o[0] = (double)(key >> 32);
+        o[1] = (double)(key & 0xffffffffull);
+        o[2] = c; o[3] = pp; o[4] = qq;
     }
 }
 
@@ -95,16 +101,13 @@ extern "C" size_t bbk_decimate_workspace_bytes(int64_t n) {
     return 2 * bbk_bh_workspace_bytes(n) + 256;          // one sort workspace per sort (the second must not scratch the first's result)
 }
 
-extern "C" int bbk_decimate(const double* d_mid1, const double* d_mid2, const double* d_count, const double* d_p, const double* d_q,
-                            int64_t n, int64_t resolution, double* d_out_mid1, double* d_out_mid2, double* d_out_count,
-                            double* d_out_p, double* d_out_q, int64_t* d_n_out, void* d_workspace, size_t workspace_bytes,
-                            void* stream) {
+extern "C" int bbk_decimate(const double* d_map, int64_t n, int64_t resolution, double* d_out_map, int64_t* d_n_out,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
     BBK_REQUIRE(n >= 0 && n < (1ll << 32), "bbk_decimate: n must be in [0, 2^32)");
     BBK_REQUIRE(resolution > 0 && resolution <= (1ll << 30), "bbk_decimate: resolution must be in [1, 2^30]");
     BBK_REQUIRE(d_n_out && d_workspace, "bbk_decimate: null pointer");
     BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_decimate: workspace must be 256-byte aligned");
-    BBK_REQUIRE(n == 0 || (d_mid1 && d_mid2 && d_count && d_p && d_q && d_out_mid1 && d_out_mid2 && d_out_count && d_out_p && d_out_q),
-                "bbk_decimate: null column");
+    BBK_REQUIRE(n == 0 || (d_map && d_out_map), "bbk_decimate: null map");
     if (workspace_bytes < bbk_decimate_workspace_bytes(n)) {
         bbk_set_error("bbk_decimate: workspace too small (%zu < %zu bytes)", workspace_bytes, bbk_decimate_workspace_bytes(n));
         return BBK_E_WORKSPACE;
@@ -125,7 +128,7 @@ extern "C" int bbk_decimate(const double* d_mid1, const double* d_mid2, const do
     BBK_CHECK_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
     long long want = (n + DC_THREADS - 1) / DC_THREADS;
     int grid = (int)(want < (long long)bbk_num_sms() * 8 ? want : (long long)bbk_num_sms() * 8);
-    dec_keys_kernel<<<grid, DC_THREADS, 0, st>>>(d_mid1, d_mid2, n, resolution, k0, i0, counters, bad);
+    dec_keys_kernel<<<grid, DC_THREADS, 0, st>>>(d_map, n, resolution, k0, i0, counters, bad);
     BBK_CHECK_LAUNCH("dec_keys_kernel");
     int rc = bbk_sort_pairs(ws_rows, n, n, 0, st);                           // rows by (mid1', mid2'), stable
     if (rc != BBK_OK) return rc;
@@ -133,8 +136,7 @@ extern "C" int bbk_decimate(const double* d_mid1, const double* d_mid2, const do
     BBK_CHECK_LAUNCH("dec_heads_kernel");
     rc = bbk_sort_pairs(ws_heads, n, -1, 0, st);                             // groups by first appearance (count on the device)
     if (rc != BBK_OK) return rc;
-    dec_fold_kernel<<<grid, DC_THREADS, 0, st>>>(k0, i0, n, i1, counters, d_count, d_p, d_q, d_out_mid1, d_out_mid2, d_out_count,
-                                                 d_out_p, d_out_q, (long long*)d_n_out);
+    dec_fold_kernel<<<grid, DC_THREADS, 0, st>>>(k0, i0, n, i1, counters, d_map, d_out_map, (long long*)d_n_out);
     BBK_CHECK_LAUNCH("dec_fold_kernel");
     dec_flag_kernel<<<1, 1, 0, st>>>(bad, (long long*)d_n_out);              // coordinates out of range: *d_n_out = -1
     BBK_CHECK_LAUNCH("dec_flag_kernel");

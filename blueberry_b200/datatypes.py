@@ -46,17 +46,16 @@ class FithicContactMap(object):
         self.resolution = resolution
         if n == 0:
             return
-        cols = torch.from_numpy(np.ascontiguousarray(self.map.T)).to(dev)                 # (5, n): one column per row
-        out = torch.empty((5, n), dtype=torch.float64, device=dev)
+        rows = torch.from_numpy(np.ascontiguousarray(self.map, dtype=np.float64)).to(dev)    # (n, 5) row-major, as the reference holds it
+        out = torch.empty((n, 5), dtype=torch.float64, device=dev)
         n_out = torch.zeros(1, dtype=torch.int64, device=dev)
         ws = torch.empty(int(lib.bbk_decimate_workspace_bytes(n)), dtype=torch.uint8, device=dev)
-        _lib.check(lib.bbk_decimate(_lib.ptr(cols[0]), _lib.ptr(cols[1]), _lib.ptr(cols[2]), _lib.ptr(cols[3]), _lib.ptr(cols[4]),
-                                    n, int(resolution), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
-                                    _lib.ptr(out[4]), _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_decimate")
+        _lib.check(lib.bbk_decimate(_lib.ptr(rows), n, int(resolution), _lib.ptr(out), _lib.ptr(n_out), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr()), "bbk_decimate")
         g = int(n_out.item())
         if g < 0:
             raise ValueError("decimate: a midpoint is outside [0, 2^31)")
-        self.map = np.ascontiguousarray(out[:, :g].T.cpu().numpy())
+        self.map = out[:g].cpu().numpy()
         self.regions = np.union1d(self.map[:, 0], self.map[:, 1])
 
     def contacts(self):

@@ -230,14 +230,14 @@ int bbk_count_band(const double* d_regions, int64_t n, double low, double high, 
  * K7  FithicContactMap.decimate                        replaces datatypes.pyx:317-339  
  *     mid' = (int(mid) + r) / r * r - r/2 (Python-2 integer division) for both midpoints of every row, then rows with
  *     equal (mid1', mid2') are folded in file order: count = count_i + count, p = p_i * p, q = min(q_i, q) from (0, 1, 1).
- * Columns in (the five columns of the reference's (n, 5) float64 map), columns out (capacity n), groups in the order
- * of their first row in the file.  *d_n_out: number of groups, or -1 when a coordinate is outside [0, 2^31).
+ * d_map: the reference's own layout, (n, 5) float64 row-major rows (mid1, mid2, contactCount, p, q); d_out_map: the
+ * decimated map in the same layout (capacity n rows), groups in the order of their first row in the file.
+ * *d_n_out: number of groups, or -1 when a coordinate is outside [0, 2^31).
  * The sum and the product are folded by one thread per group, member by member, so they round like the reference's loop.
  * ------------------------------------------------------------------------------------------- */
 size_t bbk_decimate_workspace_bytes(int64_t n);
-int bbk_decimate(const double* d_mid1, const double* d_mid2, const double* d_count, const double* d_p, const double* d_q,
-                 int64_t n, int64_t resolution, double* d_out_mid1, double* d_out_mid2, double* d_out_count, double* d_out_p,
-                 double* d_out_q, int64_t* d_n_out, void* d_workspace, size_t workspace_bytes, void* stream);
+int bbk_decimate(const double* d_map, int64_t n, int64_t resolution, double* d_out_map, int64_t* d_n_out, void* d_workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K8  ContactMap ingest + normalize on band records    replaces datatypes.pyx:99-120 and :143-171  

@@ -21,19 +21,18 @@ def main():
     i = torch.randint(0, nb, (n,), device=dev, generator=gen)
     i, _ = torch.sort(i)                                         # row-major like a significances file
     d = torch.randint(0, K, (n,), device=dev, generator=gen)
-    cols = torch.empty((5, n), dtype=torch.float64, device=dev)
-    cols[0] = (i * 1000 + 500).double()
-    cols[1] = ((i + d) * 1000 + 500).double()
-    cols[2] = torch.randint(0, 40, (n,), device=dev, generator=gen).double()
-    cols[3] = torch.rand(n, device=dev, generator=gen, dtype=torch.float64) ** 2
-    cols[4] = torch.rand(n, device=dev, generator=gen, dtype=torch.float64)
-    out = torch.empty((5, n), dtype=torch.float64, device=dev)
+    rows = torch.empty((n, 5), dtype=torch.float64, device=dev)
+    rows[:, 0] = (i * 1000 + 500).double()
+    rows[:, 1] = ((i + d) * 1000 + 500).double()
+    rows[:, 2] = torch.randint(0, 40, (n,), device=dev, generator=gen).double()
+    rows[:, 3] = torch.rand(n, device=dev, generator=gen, dtype=torch.float64) ** 2
+    rows[:, 4] = torch.rand(n, device=dev, generator=gen, dtype=torch.float64)
+    out = torch.empty((n, 5), dtype=torch.float64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = torch.empty(int(lib.bbk_decimate_workspace_bytes(n)), dtype=torch.uint8, device=dev)
 
     def run():
-        _lib.check(lib.bbk_decimate(*[_lib.ptr(cols[k]) for k in range(5)], n, 5000, *[_lib.ptr(out[k]) for k in range(5)],
-                                    _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_decimate")
+        _lib.check(lib.bbk_decimate(_lib.ptr(rows), n, 5000, _lib.ptr(out), _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bbk_decimate")
     for _ in range(3):
         run()
     torch.cuda.synchronize()
