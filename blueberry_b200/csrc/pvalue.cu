@@ -147,16 +147,18 @@ struct TailConst {      // per-launch constants (functions of S only)
     double c5_max;      // ... and c^5 < c5_max (= 2e-11 S^4: sum ln(1-i/S) truncated after the cubic term)
 };
 
-// The tail sum as a resumable state.
+// The tail sum as a resumable state.  Always the UPPER tail, P(X >= c) = pmf(c) (1 + r(c+1) + r(c+1) r(c+2) + ...) with
+// r(j) = pmf(j)/pmf(j-1) = (S - j + 1) q / (j (1 - q)): below the mode the terms first rise (by at most pmf(mode)/pmf(c)),
+// the sum comes out as ~1/pmf(c) and p as ~1.  (An earlier version summed the lower tail for c below the mode and returned
+// 1 - sum; the two kinds of lanes then ran two different loops one after the other in every round - 8 % of K4's
+// instructions at 4 of 32 lanes.  One loop for every lane: 1.87 -> 1.70 ms on cfg2.)
 struct TailState {
     double lp;      // ln pmf(c)
     double term;    // last term added, relative to pmf(c)
     double sum;     // sum of the terms so far, relative to pmf(c)
-    double a;       // upper: (S - j + 1) q/(1-q) for the next index j;  lower: j (1-q)/q / S for the next index j
-    double step;    // upper: q/(1-q);  lower: (1-q)/q / S          (a moves by -step per term)
-    double e;       // lower only: (j - 1) / S for the next index j  (moves by -1/S per term)
-    int j;          // next index: upper j = c+1, c+2, ...; lower j = c, c-1, ... (ratio pmf(j-1)/pmf(j))
-    int upper;      // 1 upper tail, 0 lower tail
+    double a;       // (S - j + 1) q/(1-q) for the next index j
+    double step;    // q/(1-q)          (a moves by -step per term)
+    int j;          // next index: c+1, c+2, ...
 };
 
 __device__ __forceinline__ bool fast_ok(int c, const TailConst& K) {
@@ -171,100 +173,63 @@ __device__ __forceinline__ void tail_setup(int c, double q, const TailConst& K, 
     const double A = -s1 * (1.0 + inv_n * ((2.0 * dc - 1.0) * (1.0 / 6.0) + s1 * (1.0 / 3.0)));   // sum_{i<c} ln(1 - i/S)
     const double lnfact = c < LF_TAB ? lfact[c] : lnfact_big(dc);
     T.lp = dc * log(mu) - lnfact + A + (dn - dc) * log1m(q);
-    T.upper = dc >= (dn + 1.0) * q;
+    // More than nine standard deviations below the mean 1 - p is under 1e-19 (the left tail of a binomial is lighter than
+    // the normal's): p rounds to 1.0, which is what the degenerate state produces - and the terms, which would rise by
+    // pmf(mode)/pmf(c), cannot overflow for the rest.
+    const double gap = mu - dc - 2.0;
+    const bool far_below = gap > 0.0 && gap * gap > 81.0 * mu;
     const double qr = q / (1.0 - q);
     T.term = 1.0;
-    if (T.upper) {
-        T.step = qr;
-        T.a = (dn - dc) * qr;
-        T.j = c + 1;
-        T.sum = 1.0;
-        T.e = 0.0;
-    } else {
-        // pmf(j-1)/pmf(j) = j (1-q)/q / (S-j+1);  1/(S-j+1) = (1/S)(1 + e + e^2 + e^3 ...), e = (j-1)/S < 1e-4
-        T.step = inv_n / qr;
-        T.a = dc * T.step;
-        T.e = (dc - 1.0) * inv_n;
-        T.j = c;
-        T.sum = 0.0;
-    }
+    T.sum = 1.0;
+    T.j = c + 1;
+    T.step = qr;
+    T.a = (dn - dc) * qr;
+    if (far_below) { T.lp = 0.0; T.a = 0.0; }                    // exhausted at once: exp(0) * 1
 }
 
 // Up to 16 terms of the state's own series; returns true when the support is exhausted (nothing left to add).
 // The per-term work is kept to the recurrence itself: the table bound and the end of the support are checked
 // once per block (the slow variants handle the blocks that cross them, and stop at the end of the support).
 __device__ __forceinline__ bool tail_terms16(TailState& T, const TailConst& K, const double* __restrict__ rcp) {
-    if (T.upper) {
-        if (T.j + TERM_BLOCK <= RCP_TAB && T.a > (double)TERM_BLOCK * T.step) {
-            const double* r = rcp + T.j;
-#pragma unroll 4
-            for (int u = 0; u < TERM_BLOCK; ++u) {
-                T.term *= T.a * r[u];
-                T.sum += T.term;
-                T.a -= T.step;
-            }
-            T.j += TERM_BLOCK;
-            return false;
-        }
-#pragma unroll 1
-        for (int u = 0; u < TERM_BLOCK; ++u) {
-            if (!(T.a > 0.0)) return true;                       // j > S: pmf is zero from here on
-            double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
-            T.term *= T.a * r;
-            T.sum += T.term;
-            T.a -= T.step;
-            T.j += 1;
-        }
-        return false;
-    }
-    if (T.j > TERM_BLOCK) {
+    if (T.j + TERM_BLOCK <= RCP_TAB && T.a > (double)TERM_BLOCK * T.step) {
+        const double* r = rcp + T.j;
 #pragma unroll 4
         for (int u = 0; u < TERM_BLOCK; ++u) {
-            T.term *= T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e)));
+            T.term *= T.a * r[u];
             T.sum += T.term;
             T.a -= T.step;
-            T.e -= K.inv_n;
         }
-        T.j -= TERM_BLOCK;
+        T.j += TERM_BLOCK;
         return false;
     }
 #pragma unroll 1
-    while (T.j > 0) {                                            // the last (at most 16) terms down to j = 0
-        T.term *= T.a * (1.0 + T.e * (1.0 + T.e * (1.0 + T.e)));
+    for (int u = 0; u < TERM_BLOCK; ++u) {
+        if (!(T.a > 0.0)) return true;                           // j > S: pmf is zero from here on
+        double r = T.j < RCP_TAB ? rcp[T.j] : 1.0 / (double)T.j;
+        T.term *= T.a * r;
         T.sum += T.term;
         T.a -= T.step;
-        T.e -= K.inv_n;
-        T.j -= 1;
+        T.j += 1;
     }
-    return true;
+    return false;
 }
 
 // 8-lane group: every lane of the group holds the SAME state; each takes 8 consecutive terms per step and
 // the group combines them with a prefix product.  All 32 lanes run the same number of steps (shuffles
 // inside); groups that are done or idle pass through.  Returns the finished sum.
-__device__ __noinline__ double tail_group_finish(TailState T, double inv_n, const double* __restrict__ rcp, int sl, bool valid) {
+__device__ __noinline__ double tail_group_finish(TailState T, const double* __restrict__ rcp, int sl, bool valid) {
     constexpr int U = 8;
     bool done = !valid;
     while (!__all_sync(0xffffffffu, done)) {
         double p = 1.0, s = 0.0;
         if (!done) {
             double a = T.a - (double)(sl * U) * T.step;
-            if (T.upper) {
-                int j = T.j + sl * U;
+            int j = T.j + sl * U;
 #pragma unroll 2
-                for (int u = 0; u < U; ++u) {
-                    double r = j < RCP_TAB ? rcp[j] : 1.0 / (double)j;
-                    double f = a > 0.0 ? a * r : 0.0;
-                    p *= f; s += p; a -= T.step; j += 1;
-                }
-            } else {
-                double e = T.e - (double)(sl * U) * inv_n;
-                int j = T.j - sl * U;
-#pragma unroll 2
-                for (int u = 0; u < U; ++u) {
-                    double f = j > 0 ? a * (1.0 + e * (1.0 + e * (1.0 + e))) : 0.0;
-                    p *= f; s += p; a -= T.step; e -= inv_n; j -= 1;
-                }
+            for (int u = 0; u < U; ++u) {
+                double r = j < RCP_TAB ? rcp[j] : 1.0 / (double)j;
+                double f = a > 0.0 ? a * r : 0.0;
+                p *= f; s += p; a -= T.step; j += 1;
             }
         }
         double incl = p;                                         // inclusive prefix product over the group
@@ -283,18 +248,17 @@ __device__ __noinline__ double tail_group_finish(TailState T, double inv_n, cons
             T.sum += T.term * contrib;
             T.term *= prod;
             T.a -= (double)(8 * U) * T.step;
-            if (T.upper) T.j += 8 * U;
-            else { T.j -= 8 * U; T.e -= (double)(8 * U) * inv_n; }
-            done = (T.term < TAIL_EPS * T.sum) || (T.upper ? T.a <= 0.0 : T.j <= 0);
+            T.j += 8 * U;
+            done = (T.term < TAIL_EPS * T.sum) || T.a <= 0.0;
         }
     }
     return T.sum;
 }
 
-__device__ __forceinline__ double tail_finish(double lp, double sum, int upper) {
-    if (upper && lp < -690.0) return exp_deep(lp, sum);          // keep the denormal range reachable
-    double v = exp(lp) * sum;
-    return upper ? v : 1.0 - v;
+__device__ __forceinline__ double tail_finish(double lp, double sum) {
+    if (lp < -690.0) return exp_deep(lp, sum);                   // keep the denormal range reachable
+    const double v = exp(lp) * sum;
+    return v > 1.0 ? 1.0 : v;                                    // c far below the mode: the sum of the whole support, up to rounding
 }
 
 // Everything bdtrc decides without arithmetic.  Returns 0 when *out is final, 1 for count == 1
@@ -526,7 +490,7 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
             const bool active = k < n2;
             const int pos = WT_PAIRS - 1 - (active ? k : 0);
             TailState T;
-            T.lp = 0.0; T.term = 0.0; T.sum = 1.0; T.a = 0.0; T.step = 0.0; T.e = 0.0; T.j = 0; T.upper = 1;
+            T.lp = 0.0; T.term = 0.0; T.sum = 1.0; T.a = 0.0; T.step = 0.0; T.j = 0;
             bool running = false;                    // this lane's sum is set up and not yet converged
             bool fast = false;
             if (active) {
@@ -557,10 +521,8 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
                 G.sum = __shfl_sync(0xffffffffu, T.sum, from);
                 G.a = __shfl_sync(0xffffffffu, T.a, from);
                 G.step = __shfl_sync(0xffffffffu, T.step, from);
-                G.e = __shfl_sync(0xffffffffu, T.e, from);
                 G.j = __shfl_sync(0xffffffffu, T.j, from);
-                G.upper = __shfl_sync(0xffffffffu, T.upper, from);
-                double gsum = tail_group_finish(G, K.inv_n, sh.rcp, sl, valid);
+                double gsum = tail_group_finish(G, sh.rcp, sl, valid);
                 // every lane of group g now holds the finished sum of the g-th straggler: hand it to its owner lane
 #pragma unroll
                 for (int gsel = 0; gsel < 4; ++gsel) {
@@ -571,7 +533,7 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
 #pragma unroll
                 for (int d = 0; d < 4; ++d) rmask &= rmask - 1;      // drop the (up to) 4 lowest set bits
             }
-            if (active && fast) W.res[W.slot[pos]] = tail_finish(T.lp, T.sum, T.upper);
+            if (active && fast) W.res[W.slot[pos]] = tail_finish(T.lp, T.sum);
         }
         __syncwarp();
         // ---- results back to their owners, coalesced 128-bit stores
