@@ -43,9 +43,7 @@ constexpr int PV_WARPS = PV_THREADS / 32;
 constexpr int RCP_TAB = 1024;        // 1/j for j < RCP_TAB
 constexpr int LF_TAB = 256;          // ln j! for j < LF_TAB
 constexpr double TAIL_EPS = 2e-12;
-constexpr int STRAGGLER_MIN = 3;     // a round keeps its lanes summing on their own while at least this many are still running
-                                     // (measured on cfg2: 8 -> 1.94 ms, 3 -> 1.82 ms, 1 -> 1.83 ms)
-constexpr int TERM_BLOCK = 16;       // terms summed between two convergence checks (8 -> 1.89 ms, 16 -> 1.82 ms)
+constexpr int TERM_BLOCK = 16;       // terms summed between two convergence checks (cfg2: 8 -> 1.69 ms, 16 -> 1.64 ms, 32 -> 1.67 ms)
 constexpr double LN_2PI = 1.8378770664093454836;
 
 // mathematical constants, filled once per device (pv_tables_kernel): 1/j and ln j!
@@ -212,47 +210,6 @@ __device__ __forceinline__ bool tail_terms16(TailState& T, const TailConst& K, c
         T.j += 1;
     }
     return false;
-}
-
-// 8-lane group: every lane of the group holds the SAME state; each takes 8 consecutive terms per step and
-// the group combines them with a prefix product.  All 32 lanes run the same number of steps (shuffles
-// inside); groups that are done or idle pass through.  Returns the finished sum.
-__device__ __noinline__ double tail_group_finish(TailState T, const double* __restrict__ rcp, int sl, bool valid) {
-    constexpr int U = 8;
-    bool done = !valid;
-    while (!__all_sync(0xffffffffu, done)) {
-        double p = 1.0, s = 0.0;
-        if (!done) {
-            double a = T.a - (double)(sl * U) * T.step;
-            int j = T.j + sl * U;
-#pragma unroll 2
-            for (int u = 0; u < U; ++u) {
-                double r = j < RCP_TAB ? rcp[j] : 1.0 / (double)j;
-                double f = a > 0.0 ? a * r : 0.0;
-                p *= f; s += p; a -= T.step; j += 1;
-            }
-        }
-        double incl = p;                                         // inclusive prefix product over the group
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            double up = __shfl_up_sync(0xffffffffu, incl, o, 8);
-            if (sl >= o) incl *= up;
-        }
-        double excl = __shfl_up_sync(0xffffffffu, incl, 1, 8);
-        if (sl == 0) excl = 1.0;
-        double contrib = excl * s;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o, 8);
-        double prod = __shfl_sync(0xffffffffu, incl, 7, 8);
-        if (!done) {
-            T.sum += T.term * contrib;
-            T.term *= prod;
-            T.a -= (double)(8 * U) * T.step;
-            T.j += 8 * U;
-            done = (T.term < TAIL_EPS * T.sum) || T.a <= 0.0;
-        }
-    }
-    return T.sum;
 }
 
 __device__ __forceinline__ double tail_finish(double lp, double sum) {
@@ -500,38 +457,16 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
                 if (fast) { tail_setup(c, q, K, sh.lfact, T); running = true; }
                 else W.res[W.slot[pos]] = tail_general(c, S, q);
             }
-            // lanes advance their own sums while the round is still mostly busy ...
+            // every lane advances its own sum, 16 terms between two convergence checks, until the round is done.  (Handing
+            // the last few running sums to 8-lane groups paid while upper- and lower-tail lanes ran separate loops; with
+            // one loop for all lanes it no longer does: 1.72 ms with the groups, 1.64 ms without.)
             unsigned rmask = __ballot_sync(0xffffffffu, running);
-            while (__popc(rmask) >= STRAGGLER_MIN) {
+            while (rmask) {
                 if (running) {
                     const bool exhausted = tail_terms16(T, K, sh.rcp);
                     running = !(exhausted || T.term < TAIL_EPS * T.sum);
                 }
                 rmask = __ballot_sync(0xffffffffu, running);
-            }
-            // ... and groups of 8 lanes finish the stragglers, four at a time
-            const int sub = lane >> 3, sl = lane & 7;
-            while (rmask) {
-                const unsigned src = __fns(rmask, 0, sub + 1);
-                const bool valid = src < 32u;
-                const int from = valid ? (int)src : lane;
-                TailState G;
-                G.lp = 0.0;
-                G.term = __shfl_sync(0xffffffffu, T.term, from);
-                G.sum = __shfl_sync(0xffffffffu, T.sum, from);
-                G.a = __shfl_sync(0xffffffffu, T.a, from);
-                G.step = __shfl_sync(0xffffffffu, T.step, from);
-                G.j = __shfl_sync(0xffffffffu, T.j, from);
-                double gsum = tail_group_finish(G, sh.rcp, sl, valid);
-                // every lane of group g now holds the finished sum of the g-th straggler: hand it to its owner lane
-#pragma unroll
-                for (int gsel = 0; gsel < 4; ++gsel) {
-                    unsigned owner = __fns(rmask, 0, gsel + 1);
-                    double v = __shfl_sync(0xffffffffu, gsum, gsel * 8);
-                    if (owner == (unsigned)lane) { T.sum = v; running = false; }
-                }
-#pragma unroll
-                for (int d = 0; d < 4; ++d) rmask &= rmask - 1;      // drop the (up to) 4 lowest set bits
             }
             if (active && fast) W.res[W.slot[pos]] = tail_finish(T.lp, T.sum);
         }
