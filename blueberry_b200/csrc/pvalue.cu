@@ -403,6 +403,20 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
     // warps are autonomous: no CTA barrier inside the loop
     for (long long wt = (long long)blockIdx.x * PV_WARPS + warp; wt < n_wtiles; wt += (long long)gridDim.x * PV_WARPS) {
         int n1 = 0, n2 = 0;                          // warp-uniform list lengths
+        {   // the records this warp will classify next: pull them into L2 now (their first use stalls on DRAM otherwise)
+            const long long wn = wt + (long long)gridDim.x * PV_WARPS;
+            if (wn < n_wtiles) {
+#pragma unroll
+                for (int it = 0; it < WT_ITERS; ++it) {
+                    const long long g = wn * groups_per_tile + it * 32 + lane;
+                    if (g < n_groups) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(m1v + g));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(m2v + g));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(cv + g));
+                    }
+                }
+            }
+        }
         // ---- phase 1: classify; trivial results to their slots, the rest into the two dense lists
 #pragma unroll 1
         for (int it = 0; it < WT_ITERS; ++it) {
