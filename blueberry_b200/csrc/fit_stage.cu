@@ -47,6 +47,8 @@ struct FitShared {
     double s, min_x, max_x;
     long long t[7];
     long long slice_tot[FIT_THREADS];
+    int s_given;
+    double s_in;
     double cmax[FIT_THREADS], cmin[FIT_THREADS];      // antitonic regression: extrema of each thread's chunk
 };
 
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
     if (tid == 0) {
         for (int i = 0; i < 7; ++i) sh.t[i] = 0;
         sh.t[0] = clock64();
+        sh.s_given = P.result->status == BBK_FIT_S_GIVEN;      // the caller supplies s (include/bbk.h: BbkFitResult.smoothing)
+        sh.s_in = P.result->smoothing;
         sh.status = BBK_FIT_OK;
         sh.n_out = 0; sh.k0 = 0; sh.L = 0;
         sh.S = injected ? 0 : P.totals[0];
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
                 nondecr = nondecr && (xs[j] - xs[j - 1] >= 0.0);
                 strict = strict && (xs[j] - xs[j - 1] > 0.0);
             }
-            sh.s = ymin * ymin;                              // fithic.py:340
+            sh.s = sh.s_given ? sh.s_in : ymin * ymin;       // fithic.py:340
             sh.min_x = xmin;                                 // fithic.py:350
             sh.max_x = xmax;
             if (!(sh.s > 0.0 ? nondecr : strict)) sh.status = BBK_FIT_X_NOT_INCREASING;

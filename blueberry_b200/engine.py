@@ -151,7 +151,14 @@ class PassEngine(object):
         """Sum the distance table and totals over ranks (integers: order-free, bit-exact)."""
         reduce_distance_stats(self.obs_sum, self.totals, group)
 
-    def fit(self):
+    def fit(self, smoothing=None):
+        """K2b + K3.  smoothing: the spline's s when the caller wants to give it (see reference_smoothing); by default the
+        kernel uses min(y) * min(y)."""
+        if smoothing is not None:
+            req = _lib.FitResult()
+            req.status = _lib.FIT_S_GIVEN
+            req.smoothing = float(smoothing)
+            self.fit_result.copy_(torch.frombuffer(bytearray(bytes(req)), dtype=torch.uint8))
         _lib.check(self.lib.bbk_fit(_lib.ptr(self.possible), _lib.ptr(self.obs_sum), self.nkeys, _lib.ptr(self.totals),
                                     self.n_bins, self.R, self.min_dist, self.max_dist, self.max_bins,
                                     _lib.ptr(self.fit_result), _lib.ptr(self.x), _lib.ptr(self.y), _lib.ptr(self.bin_of_key),
@@ -264,6 +271,16 @@ class PassEngine(object):
         return n_all
 
     # ------------------------------------------------------------------ results
+    def reference_smoothing(self, fit):
+        """s exactly as the reference computes it, `min(y)**2` on Python floats (fithic.py:340): that is libm's pow(ymin, 2.0),
+        which is one ulp away from the correctly rounded ymin*ymin the kernel computes for about 0.09 % of inputs (glibc 2.39).
+        Returns None when the kernel's s (fit.smoothing) already equals it, else the value to pass to fit(smoothing=...)."""
+        y = self.y[:fit.n_out].cpu().tolist()
+        if not y:
+            return None
+        s_ref = min(y) ** 2
+        return None if s_ref == fit.smoothing else s_ref
+
     def read_fit(self):
         """Copy the fit status back (synchronises) and raise what the reference would raise."""
         raw = self.fit_result.cpu().numpy().tobytes()
@@ -273,12 +290,12 @@ class PassEngine(object):
             raise err[0](err[1])
         return res
 
-    def run_second_pass(self, shards, p_first, p_outs, p_outlier, q_outs=None, n_tests=-1, group=None):
+    def run_second_pass(self, shards, p_first, p_outs, p_outlier, q_outs=None, n_tests=-1, group=None, smoothing=None):
         """Refit after outlier removal (BASELINE config 4; definition in include/bbk.h): statistics from the records
         with first-pass p > p_outlier, then ALL records are scored again with the refitted S and spline."""
         self.hist_excluding(shards, p_first, p_outlier)
         self.allreduce_stats(group)
-        self.fit()
+        self.fit(smoothing)
         fuse_hist = q_outs is not None and len(shards) == 1
         if fuse_hist:
             self.p_hist.zero_()
@@ -290,7 +307,7 @@ class PassEngine(object):
                 if p.numel():
                     self.qvalues(p, q, n_tests=n_tests, use_hist=fuse_hist, prepared=fuse_hist)
 
-    def run(self, shards, p_outs, q_outs=None, n_tests=-1, group=None):
+    def run(self, shards, p_outs, q_outs=None, n_tests=-1, group=None, smoothing=None):
         """The whole pass over `shards`; p_outs[i] (float64, len shards[i].n) receives the p-values.
 
         q_outs (optional): per-shard q buffers.  q-values are computed per call over ALL shards
@@ -298,7 +315,7 @@ class PassEngine(object):
         """
         self.hist(shards)
         self.allreduce_stats(group)
-        self.fit()
+        self.fit(smoothing)
         fuse_hist = q_outs is not None and len(shards) == 1
         if fuse_hist:
             self.p_hist.zero_()

@@ -210,18 +210,29 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
     q = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n] if want_q else None
     nt = -1 if n_tests is None else int(n_tests)
     first = None
+    # The kernel takes s = min(y) * min(y); the reference's `min(y)**2` is libm's pow, one ulp off for ~0.09 % of inputs.
+    # When the two differ (checked on the host once the pass is through) the pass is run again with the reference's s.
     if not refit:
         eng.run([shard], [p], [q] if want_q else None, n_tests=nt)
+        s_ref = eng.reference_smoothing(eng.read_fit())
+        if s_ref is not None:
+            eng.run([shard], [p], [q] if want_q else None, n_tests=nt, smoothing=s_ref)
     else:
         # pass 1 without q-values, then the refit on the non-outliers scores every record again
         eng.run([shard], [p], None)
-        eng.read_fit()
+        s_ref = eng.reference_smoothing(eng.read_fit())
+        if s_ref is not None:
+            eng.run([shard], [p], None, smoothing=s_ref)
+            eng.read_fit()
         possible_host = eng.possible.cpu().numpy()
         in_rng = sum(int(v) for k, v in enumerate(possible_host) if in_range_check(k * int(resolution), min_dist, max_dist))
         if in_rng <= 0:
             raise ZeroDivisionError("float division by zero (possibleIntraInRangeCount == 0)")
         first = p.clone()
         eng.run_second_pass([shard], [first], [p], 1.0 / in_rng, [q] if want_q else None, n_tests=nt)
+        s_ref = eng.reference_smoothing(eng.read_fit())
+        if s_ref is not None:
+            eng.run_second_pass([shard], [first], [p], 1.0 / in_rng, [q] if want_q else None, n_tests=nt, smoothing=s_ref)
     fit = eng.read_fit()                                        # raises what the reference would raise
 
     out = PassOutput()
@@ -472,6 +483,10 @@ def fit_spline(mainDic, x, y, yerr, infilename, outfilename, biasDic, resolution
     ys = torch.tensor(list(y), dtype=torch.float64, device=dev)
     ws_bytes = int(lib.bbk_fit_workspace_bytes(max(m, 4), nkeys)) + 16 * m + 64
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    req = _lib.FitResult()                                      # s exactly as fithic.py:340 computes it, on Python floats
+    req.status = _lib.FIT_S_GIVEN
+    req.smoothing = float(min(list(y)) ** 2)
+    eng.fit_result.copy_(torch.frombuffer(bytearray(bytes(req)), dtype=torch.uint8))
     _lib.check(lib.bbk_fit_from_bins(_lib.ptr(xs), _lib.ptr(ys), m, nkeys, int(resolution), _lib.ptr(eng.fit_result),
                                      _lib.ptr(eng.spline_y), _lib.ptr(eng.spline_raw), _lib.ptr(eng.knots),
                                      _lib.ptr(eng.coefs), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "bbk_fit_from_bins")

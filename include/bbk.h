@@ -43,6 +43,7 @@ extern "C" {
 #define BBK_FIT_S_ZERO (-14)           /* reference: ZeroDivisionError at fithic.py:216 */
 #define BBK_FIT_X_NOT_INCREASING (-15)
 #define BBK_FIT_EMPTY_GRID (-16)       /* no distance key inside [min(x), max(x)] */
+#define BBK_FIT_S_GIVEN 7777            /* INPUT value of BbkFitResult.status: use BbkFitResult.smoothing as s (see bbk_fit) */
 
 int bbk_version(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
@@ -103,7 +104,10 @@ typedef struct BbkFitResult {
     double min_x, max_x; /* min(x), max(x) */
     double residual;     /* sum((y - ius(x))**2), fithic.py:374 */
     double fp;           /* weighted sum of squared residuals of the smoothing spline */
-    double smoothing;    /* s = min(y)**2 */
+    double smoothing;    /* s.  The reference passes s = min(y)**2 on Python floats, i.e. libm's pow(ymin, 2.0), which is NOT always
+                            the correctly rounded ymin*ymin (glibc 2.39: one ulp off for ~0.09 % of inputs); the kernel computes
+                            ymin*ymin.  A host that wants the reference's bits checks this field against its own min(y)**2 and, when
+                            they differ, calls bbk_fit again with status = BBK_FIT_S_GIVEN and smoothing = its value on input. */
     int64_t phase_cycles[6]; /* SM clock cycles: staging+binning, bin stats, spline search, grid evaluation,
                                 antitonic regression + residual, total */
     int64_t spline_diag[8];  /* LSQ fits, smoothing iterations, then SM cycles: B-spline rows, row QR + back

@@ -46,7 +46,7 @@ def _case(seed):
                 cnt=cnt, bias=barr)
 
 
-@pytest.mark.parametrize("seed", range(36))
+@pytest.mark.parametrize("seed", list(range(36)) + [241])      # 241: libm pow(ymin, 2.0) != ymin * ymin, the pass is re-run with the reference's s
 def test_random_pass_against_oracle(seed):
     import warnings
     from blueberry_b200.fithic import FitHiC
