@@ -294,6 +294,48 @@ __device__ __forceinline__ double bias_lookup(const PvParams& P, const BiasRow& 
     return isnan(v) ? 1.0 : v;
 }
 
+// The same lookup in two steps, so that the loads of several records can be issued together: where the entry is (and
+// whether there is one), then what the loaded value means.  The load itself is unconditional (entry 0 stands in when there
+// is no entry) so that nothing but arithmetic separates the loads of a group.
+template <bool FAST>
+__device__ __forceinline__ bool bias_index(const PvParams& P, const BiasRow& row, int mid, long long* at) {
+    const long long off = (long long)mid - row.mid0;
+    bool ok = (unsigned long long)off < row.span;
+    unsigned idx;
+    if (FAST) {
+        ok = ok && off < (1ll << 31);
+        idx = fastdiv31((unsigned)off, P.div);
+    } else {
+        ok = ok && off < (1ll << 32);
+        idx = fastdiv((unsigned)off, P.div);
+    }
+    ok = ok && idx * P.div.R == (unsigned)off;
+    *at = ok ? row.base + (long long)idx : 0ll;
+    return ok;
+}
+__device__ __forceinline__ double bias_value(double v, bool ok) { return (ok && !isnan(v)) ? v : 1.0; }
+
+// i = min(bisect_left(splineX, clamp(d, min_x, max_x)), L-1) == clamp(ceil((d - splineX[0]) / R), 0, L-1), for an in-range d
+template <bool FAST>
+__device__ __forceinline__ int spline_index(const PvParams& P, long long d, int k0, int L) {
+    int i = 0;
+    if (FAST) {
+        const int t = (int)d - k0 * (int)P.div.R;                        // k0 * R <= max_dist
+        if (t > 0) {
+            unsigned qd = fastdiv31((unsigned)t + P.div.R - 1u, P.div);
+            i = qd > (unsigned)(L - 1) ? L - 1 : (int)qd;
+        }
+    } else {
+        const long long t = d - (long long)k0 * P.R;
+        if (t > 0) {
+            long long tt = t + P.R - 1;
+            long long qd = tt < (1ll << 32) ? (long long)fastdiv((unsigned)tt, P.div) : tt / P.R;
+            i = qd > (long long)(L - 1) ? L - 1 : (int)qd;
+        }
+    }
+    return i;
+}
+
 // prior of one record; returns false when the reference does not score it (fithic.py:427).
 // FAST: 0 <= min_dist, max_dist + R < 2^31, so every in-range quantity fits 31 bits.
 template <bool HAS_CHR, bool HAS_BIAS, bool FAST>
@@ -417,45 +459,109 @@ __global__ void __launch_bounds__(PV_THREADS, 3) pvalues_kernel(PvParams P) {
                 }
             }
         }
-        // ---- phase 1: classify; trivial results to their slots, the rest into the two dense lists
-#pragma unroll 1
-        for (int it = 0; it < WT_ITERS; ++it) {
-            const long long g = wt * groups_per_tile + it * 32 + lane;
-            const bool live = g < n_groups;
-            int4 z4 = make_int4(0, 0, 0, 0);
-            int4 a1 = z4, a2 = z4, ac = z4, x1 = z4, x2 = z4;
-            if (live) {
-                a1 = ld_stream_int4(m1v + g); a2 = ld_stream_int4(m2v + g); ac = ld_stream_int4(cv + g);
-                if (HAS_CHR) { x1 = ld_stream_int4(c1v + g); x2 = ld_stream_int4(c2v + g); }
-            }
-            const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
-            const int c1s[4] = {x1.x, x1.y, x1.z, x1.w}, c2s[4] = {x2.x, x2.y, x2.z, x2.w};
-            // records that are neighbours in memory usually share their first locus (row-major input): one bias
-            // gather serves the group then (any other order just takes the per-record path)
-            bool same1 = false;
-            double b1g = 1.0;
-            if (HAS_BIAS && !HAS_CHR) {
-                same1 = (a1.x == a1.y) & (a1.y == a1.z) & (a1.z == a1.w);
-                if (same1 && live && fit_ok) b1g = bias_lookup<FAST>(P, shard_row, a1.x);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                int cls = 0;                               // 0 final, 1 count == 1, 2 tail sum
-                double prior = 0.0, out = __longlong_as_double(0x7ff8000000000000ll);
-                if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS, FAST>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, same1, b1g, &prior))
-                    cls = bdtrc_class(cs[e], s_cap, s_fits, prior, &out);
-                const int slot = it * 128 + lane * 4 + e;
-                unsigned b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
-                if (cls) {
-                    int pos = cls == 1 ? n1 + __popc(b1 & lt) : WT_PAIRS - 1 - (n2 + __popc(b2 & lt));
-                    W.q[pos] = prior;
-                    W.c[pos] = cs[e];
-                    W.slot[pos] = (unsigned char)slot;
-                } else {
-                    W.res[slot] = out;
+        if (HAS_CHR) {
+            // ---- phase 1: classify; trivial results to their slots, the rest into the two dense lists
+    #pragma unroll 1
+            for (int it = 0; it < WT_ITERS; ++it) {
+                const long long g = wt * groups_per_tile + it * 32 + lane;
+                const bool live = g < n_groups;
+                int4 z4 = make_int4(0, 0, 0, 0);
+                int4 a1 = z4, a2 = z4, ac = z4, x1 = z4, x2 = z4;
+                if (live) {
+                    a1 = ld_stream_int4(m1v + g); a2 = ld_stream_int4(m2v + g); ac = ld_stream_int4(cv + g);
+                    if (HAS_CHR) { x1 = ld_stream_int4(c1v + g); x2 = ld_stream_int4(c2v + g); }
                 }
-                n1 += __popc(b1);
-                n2 += __popc(b2);
+                const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
+                const int c1s[4] = {x1.x, x1.y, x1.z, x1.w}, c2s[4] = {x2.x, x2.y, x2.z, x2.w};
+                // records that are neighbours in memory usually share their first locus (row-major input): one bias
+                // gather serves the group then (any other order just takes the per-record path)
+                bool same1 = false;
+                double b1g = 1.0;
+                if (HAS_BIAS && !HAS_CHR) {
+                    same1 = (a1.x == a1.y) & (a1.y == a1.z) & (a1.z == a1.w);
+                    if (same1 && live && fit_ok) b1g = bias_lookup<FAST>(P, shard_row, a1.x);
+                }
+    #pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int cls = 0;                               // 0 final, 1 count == 1, 2 tail sum
+                    double prior = 0.0, out = __longlong_as_double(0x7ff8000000000000ll);
+                    if (live && fit_ok && record_prior<HAS_CHR, HAS_BIAS, FAST>(P, m1s[e], m2s[e], c1s[e], c2s[e], k0, L, shard_row, same1, b1g, &prior))
+                        cls = bdtrc_class(cs[e], s_cap, s_fits, prior, &out);
+                    const int slot = it * 128 + lane * 4 + e;
+                    unsigned b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
+                    if (cls) {
+                        int pos = cls == 1 ? n1 + __popc(b1 & lt) : WT_PAIRS - 1 - (n2 + __popc(b2 & lt));
+                        W.q[pos] = prior;
+                        W.c[pos] = cs[e];
+                        W.slot[pos] = (unsigned char)slot;
+                    } else {
+                        W.res[slot] = out;
+                    }
+                    n1 += __popc(b1);
+                    n2 += __popc(b2);
+                }
+            }
+        } else {
+            // ---- phase 1: classify; trivial results to their slots, the rest into the two dense lists.  The four records of
+            // a lane's group go through the steps together - where their spline and bias entries are, then all the loads,
+            // unconditionally, then the products - so that the gathers of a group are in flight at once: as four lookups,
+            // each behind its own early returns, they were four L2 latencies in a row (a quarter of the stall samples on the
+            // 1 kb workload sat on the first use of a bias value).
+#pragma unroll 1
+            for (int it = 0; it < WT_ITERS; ++it) {
+                const long long g = wt * groups_per_tile + it * 32 + lane;
+                const bool live = g < n_groups && fit_ok;
+                int4 z4 = make_int4(0, 0, 0, 0);
+                int4 a1 = z4, a2 = z4, ac = z4;
+                if (g < n_groups) { a1 = ld_stream_int4(m1v + g); a2 = ld_stream_int4(m2v + g); ac = ld_stream_int4(cv + g); }
+                const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
+                const bool same1 = (a1.x == a1.y) & (a1.y == a1.z) & (a1.z == a1.w);
+                bool inr[4], ok1[4], ok2[4];
+                long long at1[4], at2[4];
+                int si[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const long long d = (long long)m2s[e] - (long long)m1s[e];               // fithic.py:416
+                    inr[e] = live && P.min_dist <= d && d <= P.max_dist;                      // fithic.py:427
+                    si[e] = inr[e] ? spline_index<FAST>(P, d, k0, L) : 0;
+                    ok1[e] = false; ok2[e] = false; at1[e] = 0; at2[e] = 0;
+                    if (HAS_BIAS) {
+                        if (e == 0 || !same1) ok1[e] = bias_index<FAST>(P, shard_row, m1s[e], &at1[e]);
+                        ok2[e] = bias_index<FAST>(P, shard_row, m2s[e], &at2[e]);
+                    }
+                }
+                double sv[4], v1[4], v2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sv[e] = live ? __ldg(&P.spline_y[si[e]]) : 0.0;
+                    v1[e] = 1.0; v2[e] = 1.0;
+                    if (HAS_BIAS) {
+                        if (e == 0 || !same1) v1[e] = __ldg(&P.bias[at1[e]]);
+                        v2[e] = __ldg(&P.bias[at2[e]]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int cls = 0;                               // 0 final, 1 count == 1, 2 tail sum
+                    double prior = sv[e], out = __longlong_as_double(0x7ff8000000000000ll);
+                    if (HAS_BIAS) {
+                        const double b1 = same1 ? bias_value(v1[0], ok1[0]) : bias_value(v1[e], ok1[e]);
+                        prior = prior * (b1 * bias_value(v2[e], ok2[e]));                     // :431
+                    }
+                    if (inr[e]) cls = bdtrc_class(cs[e], s_cap, s_fits, prior, &out);
+                    const int slot = it * 128 + lane * 4 + e;
+                    unsigned b1m = __ballot_sync(0xffffffffu, cls == 1), b2m = __ballot_sync(0xffffffffu, cls == 2);
+                    if (cls) {
+                        int pos = cls == 1 ? n1 + __popc(b1m & lt) : WT_PAIRS - 1 - (n2 + __popc(b2m & lt));
+                        W.q[pos] = prior;
+                        W.c[pos] = cs[e];
+                        W.slot[pos] = (unsigned char)slot;
+                    } else {
+                        W.res[slot] = out;
+                    }
+                    n1 += __popc(b1m);
+                    n2 += __popc(b2m);
+                }
             }
         }
         __syncwarp();
