@@ -81,3 +81,40 @@ def test_random_pass_against_oracle(seed):
     assert (out.p[ref.keep & (ref.p < 1e-300)] <= 1e-299).all()
     qref = fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum()))
     assert np.array_equal(out.q[out.keep], qref)
+
+
+@pytest.mark.parametrize("seed", [0, 2, 5, 10, 12, 13, 20, 24, 29, 31])
+def test_random_two_pass_against_oracle(seed):
+    """refit=True (BASELINE config 4's second pass) on the same random cases, against the oracle's composition of the
+    reference's own functions.  The outlier set is decided by p <= 1/possibleIntraInRangeCount; a record
+    whose p sits within 1e-9 (relative) of that threshold could fall either way and is not allowed to exist here."""
+    import warnings
+    from blueberry_b200.fithic import FitHiC
+    from oracle import fithic_oracle as fo
+    k = _case(seed)
+    model = FitHiC("unused", k["R"], n_bins=k["n_bins"], max_dist=k["max_dist"], min_dist=k["min_dist"])
+    bd = fo.read_bias_arrays(*k["bias"])[0] if k["bias"] is not None else None
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            r1, r2, outlier, thr = fo.fithic_two_pass_arrays(k["fc"], k["fm"], k["chr1"], k["mid1"], k["chr2"], k["mid2"], k["cnt"], k["R"],
+                                                             k["n_bins"], model.min_dist, model.max_dist, bias=bd)
+        except Exception as e:
+            with pytest.raises(type(e)):
+                model.fit_transform_arrays(k["chr1"], k["mid1"], k["chr2"], k["mid2"], k["cnt"], k["fc"], k["fm"], bias=k["bias"], refit=True)
+            return
+    with np.errstate(invalid="ignore", divide="ignore"):
+        assert not (r1.keep & (np.abs(r1.p / thr - 1.0) < 1e-9)).any()
+    out = model.fit_transform_arrays(k["chr1"], k["mid1"], k["chr2"], k["mid2"], k["cnt"], k["fc"], k["fm"], bias=k["bias"], refit=True,
+                                     q_values=True)
+    assert np.array_equal(out.observed, r2.contacts.observed)
+    assert out.totals["observedIntraInRangeSum"] == r2.contacts.S
+    assert np.array_equal(out.x, np.array(r2.x)) and np.array_equal(out.y, np.array(r2.y))
+    assert np.array_equal(out.spline_y, r2.spline_y)
+    assert np.array_equal(out.keep, r2.keep)
+    sel = r2.keep & (r2.p >= 1e-300)
+    ok, nbad = log10_close(out.p[sel], r2.p[sel], 1e-5)
+    assert ok, "%d p-values differ by more than 1e-5 in log10" % nbad
+    qref = fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum()))
+    assert np.array_equal(out.q[out.keep], qref)
+    assert int(outlier.sum()) >= 0
