@@ -14,17 +14,16 @@
 //      tile's result slots in shared memory, records that need arithmetic are appended to two dense
 //      warp-private work lists (count == 1 from the front, count >= 2 from the back; ballot + popc);
 //   2. solve: the warp runs down each list with all lanes on the same branch.  A tail sum is a small
-//      resumable state: a lane advances it 16 terms at a time while at least 8 lanes of the round
-//      are still going (neighbouring records have similar lengths, so rounds are homogeneous);
-//      the stragglers are then finished by groups of 8 lanes that take 8 consecutive terms each
-//      per step and combine them with a prefix product;
+//      resumable state: every lane advances its own sum 16 terms between two convergence checks
+//      until the whole round of 32 records is done (neighbouring records have similar lengths, so
+//      rounds are homogeneous);
 //   3. each lane reads its 8 results back and issues coalesced 128-bit streaming stores.
 // The hot loop is kept small (tables and rare branches live in separate functions/kernels): with
 // autonomous warps the instruction cache is the first thing to overflow.
 //
 // The tail P(X >= c), X ~ Binomial(S, q), is the regularised incomplete beta I_q(c, S-c+1) that
-// cephes' bdtrc evaluates.  Here: pmf(c) * (1 + r_c + r_c r_{c+1} + ...) from the mode outwards (upper
-// tail when c >= (S+1)q, else 1 - lower tail).  ln pmf(c) = c ln(Sq) - ln c! + sum_{i<c} ln(1-i/S)
+// cephes' bdtrc evaluates.  Here: pmf(c) * (1 + r_{c+1} + r_{c+1} r_{c+2} + ...), always the upper tail
+// (a count more than 9 sigma below the mean gives p = 1.0 directly).  ln pmf(c) = c ln(Sq) - ln c! + sum_{i<c} ln(1-i/S)
 // + (S-c) ln(1-q), with the two small logarithms expanded in series (exact to < 1e-12 for the c/S the
 // fast path admits) and ln c!, 1/j from shared-memory tables; outside that range the saddle-point
 // form (Stirling error + deviance terms; C. Loader, "Fast and accurate computation of binomial
