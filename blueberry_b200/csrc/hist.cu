@@ -30,6 +30,7 @@ struct HistParams {
     long long n_pairs;
     long long min_dist, max_dist;
     long long lo_excl, hi_incl;   // in range  <=>  lo_excl < d <= hi_incl   (the -1 sentinels folded in)
+    unsigned lo_u, span_u;        // FAST path: in range  <=>  m2 >= m1  &&  (u32)(m2 - m1) - lo_u <= span_u
     FastDiv div;
     int nkeys;        // len(mainDic)
     int nkeys_s;      // bins kept in shared memory (prefix of the table), 0 = none
@@ -93,24 +94,27 @@ __device__ __forceinline__ void process_record(const HistParams& P, unsigned* sh
 }
 
 // FAST path (0 <= d <= max_dist < 2^31 for every in-range record, no chromosome columns): one int4 group = 4
-// consecutive records of a lane.  32-bit arithmetic throughout; the warp-uniform test (diagonal-major input:
-// all 128 records of the warp step on one distance) is made once per group, otherwise plain shared atomics.
+// consecutive records of a lane.  32-bit arithmetic throughout: with m2 >= m1 (signed) the difference is in [0, 2^32) and
+// equal to the wrapped 32-bit subtraction, so "lo_excl < d <= hi_incl" is one unsigned span test; without it d < 0 is out of
+// range anyway.  The warp-uniform test (diagonal-major input: all 128 records of the warp step on one distance) is made once
+// per group, otherwise plain shared atomics (ptxas turns a predicated red.shared back into a branch, so there is no
+// cheaper form of those).
 struct FastAcc {
     long long S, intra_sum;
     int in_range, intra_cnt, dmin, dmax;
 };
 
+template <bool FULL>
 __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, bool live_group, unsigned excl, FastAcc& a) {
     const int m1s[4] = {m1.x, m1.y, m1.z, m1.w}, m2s[4] = {m2.x, m2.y, m2.z, m2.w}, cs[4] = {c.x, c.y, c.z, c.w};
     unsigned key[4];
     bool ok[4];
-    int csum = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const bool live = live_group && !((excl >> e) & 1u);
-        const long long d64 = (long long)m2s[e] - (long long)m1s[e];                 // fithic.py:247
-        const bool in_range = live && d64 > P.lo_excl && d64 <= P.hi_incl;            // fithic.py:256-257
-        const int d = (int)d64;                                                       // valid when in_range
+        const bool live = (FULL || live_group) && !((excl >> e) & 1u);
+        const unsigned ud = (unsigned)m2s[e] - (unsigned)m1s[e];                      // fithic.py:247
+        const bool in_range = live && m2s[e] >= m1s[e] && (ud - P.lo_u) <= P.span_u;  // fithic.py:256-257
+        const int d = (int)ud;                                                        // < 2^31 when in_range
         a.intra_sum += live ? cs[e] : 0;
         a.intra_cnt += live ? 1 : 0;
         if (in_range) {
@@ -119,19 +123,16 @@ __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned
             a.S += cs[e];                                                             // fithic.py:262
             a.in_range += 1;                                                          // fithic.py:263
         }
-        const unsigned k = fastdiv31((unsigned)d, P.div);
+        const unsigned k = fastdiv31(ud, P.div);
         key[e] = k;
-        ok[e] = in_range && cs[e] != 0 && k * P.div.R == (unsigned)d && k < (unsigned)P.nkeys;   // "distance in mainDic" (:260)
-        csum += ok[e] ? cs[e] : 0;
+        ok[e] = in_range && cs[e] != 0 && k * P.div.R == ud && k < (unsigned)P.nkeys;  // "distance in mainDic" (:260)
     }
     // big counts / keys beyond the shared table go straight to the global table
     bool small[4];
-    bool any_small = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         small[e] = ok[e] && (unsigned)cs[e] < (unsigned)SMALL_COUNT_LIMIT && key[e] < (unsigned)P.nkeys_s;
         if (ok[e] && !small[e]) atomicAdd((unsigned long long*)&P.obs_sum[key[e]], (unsigned long long)(long long)cs[e]);
-        any_small |= small[e];
     }
     // warp-uniform distance?  (every lane's 4 keys equal lane 0's first key, all of them "small" or zero-count)
     const unsigned kref = __shfl_sync(0xffffffffu, key[0], 0);
@@ -145,7 +146,7 @@ __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned
     if (__all_sync(0xffffffffu, mine_uniform)) {
         unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)ssum);
         if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&sh[phys_bin((int)kref, P.quarter)], tot);
-    } else if (any_small) {
+    } else {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (small[e]) atomicAdd(&sh[phys_bin((int)key[e], P.quarter)], (unsigned)cs[e]);
@@ -185,7 +186,34 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
     // flush_hist and the warp collectives in process_record are reached by every thread
     const long long tile_groups = 2ll * blockDim.x;
     const long long n_tiles = (n_groups + tile_groups - 1) / tile_groups;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    long long tile = blockIdx.x;
+    if (FAST && !HAS_CHR) {
+        // full tiles: no bounds predicates, the six loads of a thread go out back to back
+        const long long full_tiles = n_groups / tile_groups;
+        const double2* pe = reinterpret_cast<const double2*>(P.p_excl);
+        for (; tile < full_tiles; tile += gridDim.x) {
+            const long long g0 = tile * tile_groups + threadIdx.x;
+            const long long g1 = g0 + blockDim.x;
+            const int4 a1 = ld_stream_int4(m1v + g0), a2 = ld_stream_int4(m2v + g0), ac = ld_stream_int4(cv + g0);
+            const int4 b1 = ld_stream_int4(m1v + g1), b2 = ld_stream_int4(m2v + g1), bc = ld_stream_int4(cv + g1);
+            unsigned xa = 0, xb = 0;
+            if (pe) {
+                const double2 u0 = ld_stream_double2(pe + 2 * g0), v0 = ld_stream_double2(pe + 2 * g0 + 1);
+                const double2 u1 = ld_stream_double2(pe + 2 * g1), v1 = ld_stream_double2(pe + 2 * g1 + 1);
+                xa = (u0.x <= P.p_thr ? 1u : 0u) | (u0.y <= P.p_thr ? 2u : 0u) | (v0.x <= P.p_thr ? 4u : 0u) | (v0.y <= P.p_thr ? 8u : 0u);
+                xb = (u1.x <= P.p_thr ? 1u : 0u) | (u1.y <= P.p_thr ? 2u : 0u) | (v1.x <= P.p_thr ? 4u : 0u) | (v1.y <= P.p_thr ? 8u : 0u);
+            }
+            process_group_fast<true>(P, sh, a1, a2, ac, true, xa, fa);
+            process_group_fast<true>(P, sh, b1, b2, bc, true, xb, fa);
+            since_flush += 4 * tile_groups;
+            if (since_flush >= FLUSH_PAIRS) {      // uniform across the CTA
+                flush_hist(P, sh);
+                since_flush = 0;
+            }
+        }
+        // at most one partial tile is left, and exactly one CTA arrives at it; it goes through the general loop below
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
         long long g0 = tile * tile_groups + threadIdx.x;
         long long g1 = g0 + blockDim.x;
         bool l0 = g0 < n_groups, l1 = g1 < n_groups;
@@ -207,8 +235,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
                       xb = (u.x <= P.p_thr ? 1u : 0u) | (u.y <= P.p_thr ? 2u : 0u) | (v.x <= P.p_thr ? 4u : 0u) | (v.y <= P.p_thr ? 8u : 0u); }
         }
         if (FAST && !HAS_CHR) {
-            process_group_fast(P, sh, a1, a2, ac, l0, xa, fa);
-            process_group_fast(P, sh, b1, b2, bc, l1, xb, fa);
+            process_group_fast<false>(P, sh, a1, a2, ac, l0, xa, fa);
+            process_group_fast<false>(P, sh, b1, b2, bc, l1, xb, fa);
         } else {
             process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0 && !(xa & 1u), a);
             process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0 && !(xa & 2u), a);
@@ -300,7 +328,11 @@ static int hist_pairs_impl(const int32_t* d_chr1, const int32_t* d_chr2, const i
     P.lo_excl = (min_dist == -1) ? (-0x7fffffffffffffffll - 1) : (min_dist > -1 ? min_dist : 0x7fffffffffffffffll);
     P.hi_incl = (max_dist == -1) ? 0x7fffffffffffffffll : (max_dist > -1 ? max_dist : (-0x7fffffffffffffffll - 1));
     // 31-bit fast path: every in-range distance is in [0, 2^31)
-    const bool fast = d_chr1 == nullptr && min_dist >= -1 && max_dist >= 0 && max_dist < (1ll << 31) && P.lo_excl >= -1;
+    // (and a non-empty range, so that it is one unsigned span: lo_u <= d <= lo_u + span_u)
+    const bool fast = d_chr1 == nullptr && min_dist >= -1 && max_dist >= 0 && max_dist < (1ll << 31) && P.lo_excl >= -1 &&
+                      P.lo_excl < P.hi_incl;
+    P.lo_u = fast ? (unsigned)(P.lo_excl + 1) : 0u;
+    P.span_u = fast ? (unsigned)(P.hi_incl - (P.lo_excl + 1)) : 0u;
     P.nkeys = nkeys;
     // only keys that can be in range need a shared bin: k*R <= max_dist
     long long want = nkeys;
