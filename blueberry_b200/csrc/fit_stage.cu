@@ -92,23 +92,48 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         long long* pre_s = pos_s + nk;
         int* bstart = (int*)(pre_s + nk);
         int* bend = bstart + P.max_bins;
-        for (int k = tid; k < nk; k += FIT_THREADS) { obs_s[k] = P.observed[k]; pos_s[k] = P.possible[k]; }
-        __syncthreads();
-        // inclusive prefix sums of observed (the reference's totalInteractionCountSoFar, fithic.py:183):
-        // every thread scans a contiguous slice, thread 0 chains the slice totals
-        {
-            const int per = (nk + FIT_THREADS - 1) / FIT_THREADS;
-            const int lo = tid * per, hi = min(lo + per, nk);
-            long long run = 0;
-            for (int k = lo; k < hi; ++k) { run += obs_s[k]; pre_s[k] = run; }
-            sh.slice_tot[tid] = run;
-            __syncthreads();
-            if (tid == 0) { long long c = 0; for (int t = 0; t < FIT_THREADS; ++t) { long long v = sh.slice_tot[t]; sh.slice_tot[t] = c; c += v; } }
-            __syncthreads();
-            const long long add = sh.slice_tot[tid];
-            for (int k = lo; k < hi; ++k) pre_s[k] += add;
+        for (int k0 = tid; k0 < nk; k0 += 4 * FIT_THREADS) {     // eight loads in flight per thread: one round trip per 512 keys
+            long long o[4], q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * FIT_THREADS;
+                o[u] = k < nk ? __ldg(P.observed + k) : 0;
+                q[u] = k < nk ? __ldg(P.possible + k) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * FIT_THREADS;
+                if (k < nk) { obs_s[k] = o[u]; pos_s[k] = q[u]; }
+            }
         }
         __syncthreads();
+        // inclusive prefix sums of observed (the reference's totalInteractionCountSoFar, fithic.py:183): FIT_THREADS keys at
+        // a time, a shuffle scan per warp, the warp totals and the running carry through shared memory
+        {
+            const int lane = tid & 31, warp = tid >> 5;
+            long long carry = 0;
+            for (int c0 = 0; c0 < nk; c0 += FIT_THREADS) {
+                const int k = c0 + tid;
+                long long v = k < nk ? obs_s[k] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                if (lane == 31) sh.slice_tot[warp] = v;
+                __syncthreads();
+                long long add = carry, tot = 0;
+#pragma unroll
+                for (int w = 0; w < FIT_THREADS / 32; ++w) {
+                    const long long wt = sh.slice_tot[w];
+                    add += w < warp ? wt : 0;
+                    tot += wt;
+                }
+                if (k < nk) pre_s[k] = v + add;
+                carry += tot;
+                __syncthreads();
+            }
+        }
         if (tid < 32) {
             // Bin boundaries by warp 0.  A bin that starts at key s closes at the first key k >= s with
             //   observed[k] >= desired  or  (sum of observed[s..k]) >= desired        (fithic.py:188-197)
