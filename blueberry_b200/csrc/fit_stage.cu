@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int FIT_THREADS = 128;
+constexpr int FIT_THREADS = 256;
 
 struct FitParams {
     const long long* possible;
@@ -185,12 +185,35 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         m = sh.n_out;
         if (tid == 0) sh.t[1] = clock64();
         if (sh.status == BBK_FIT_OK) {
+            // bin statistics (fithic.py:211-217): the per-key operands - two int64 -> double conversions and the distance
+            // term with its division - are formed by all threads in place (the integer tables and the prefix sums are not
+            // needed any more), so that the serial part, one thread per bin adding its keys in the reference's order, is
+            // three additions per key
+            double* dpos = (double*)pos_s;
+            double* dobs = (double*)obs_s;
+            double* term = (double*)pre_s;
+            for (int k = tid; k < nk; k += FIT_THREADS) {
+                const double pv = (double)pos_s[k], ov = (double)obs_s[k];
+                term[k] = 1.0 * pv * ((double)((long long)k * P.R) / 10000.0);
+                dpos[k] = pv;
+                dobs[k] = ov;
+            }
+            __syncthreads();
             for (int j = tid; j < m; j += FIT_THREADS) {
-                double xv = 0.0, yv = 0.0;
-                int stc = bbk_eo_bin_stats((const int64_t*)pos_s, (const int64_t*)obs_s, bstart[j], bend[j], S, P.R, &xv, &yv);
-                P.x[j] = xv;
-                P.y[j] = yv;
-                if (stc != BBK_FIT_OK) atomicMin(&sh.status, stc);
+                double n_pairs = 0.0, n_inter = 0.0, avg = 0.0;
+                for (int b = bstart[j]; b <= bend[j]; ++b) {
+                    n_pairs += dpos[b];
+                    n_inter += dobs[b];
+                    avg += term[b];
+                }
+                if (n_pairs == 0.0 || S == 0) {
+                    atomicMin(&sh.status, n_pairs == 0.0 ? BBK_FIT_ZERO_PAIRS_BIN : BBK_FIT_S_ZERO);
+                    P.x[j] = 0.0;
+                    P.y[j] = 0.0;
+                } else {
+                    P.y[j] = (n_inter / n_pairs) / (double)S;        // :216
+                    P.x[j] = 10000.0 * (avg / n_pairs);              // :217
+                }
                 if (P.bin_of_key) for (int k = bstart[j]; k <= bend[j]; ++k) P.bin_of_key[k] = j;
             }
         }
