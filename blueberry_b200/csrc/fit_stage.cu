@@ -156,27 +156,43 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
                 }
                 long long D = 0;
                 if (P.n_bins != 0) D = (S >= 0 || S % P.n_bins == 0) ? S / P.n_bins : S / P.n_bins - 1;   // floor (:167)
+                // The serial chain per bin is: threshold test -> ballot -> next `desired` (an FP64 division).  The prefix sum at
+                // the closing key serves both the division and, as `base`, the next bin, and the next bin's first 32 keys are
+                // loaded before the division is started, so nothing but the division and the test is left on that chain.
                 int n = 0, s0 = klo;
+                long long base = (s0 > 0 && s0 <= khi) ? pre_s[s0 - 1] : 0;
+                long long po = 0, pp = 0;                            // first chunk of the current bin
+                if (s0 + lane <= khi) { po = obs_s[s0 + lane]; pp = pre_s[s0 + lane]; }
                 while (s0 <= khi) {
-                    const long long base = s0 > 0 ? pre_s[s0 - 1] : 0;
                     int kk = -1;
+                    long long pk = 0;                                // prefix sum at the closing key
                     for (int k0w = s0; k0w <= khi; k0w += 32) {
                         const int k = k0w + lane;
-                        bool hit = k <= khi && (obs_s[k] >= D || pre_s[k] - base >= D);
+                        long long o = po, q = pp;
+                        if (k0w != s0) { o = 0; q = 0; if (k <= khi) { o = obs_s[k]; q = pre_s[k]; } }
+                        bool hit = k <= khi && (o >= D || q - base >= D);
                         unsigned bal = __ballot_sync(0xffffffffu, hit);
-                        if (bal) { kk = k0w + __ffs(bal) - 1; break; }
+                        if (bal) {
+                            const int src = __ffs(bal) - 1;
+                            kk = k0w + src;
+                            pk = __shfl_sync(0xffffffffu, q, src);
+                            break;
+                        }
                     }
                     if (kk < 0) break;                               // the trailing, unfilled bin is dropped
                     if (nout >= P.max_bins) { stc = BBK_FIT_TOO_MANY_BINS; break; }
                     if (lane == 0) { bstart[nout] = s0; bend[nout] = kk; }
                     nout += 1;
                     n += 1;                                          // :206
+                    s0 = kk + 1;
+                    po = 0; pp = 0;
+                    if (s0 + lane <= khi) { po = obs_s[s0 + lane]; pp = pre_s[s0 + lane]; }
                     if (n < P.n_bins) {                              // :208-209
-                        double dd = 1.0 * (double)(S - pre_s[kk]) / (double)(P.n_bins - n);
+                        double dd = 1.0 * (double)(S - pk) / (double)(P.n_bins - n);
                         double cd = ceil(dd);
                         D = cd >= 9.2e18 ? 0x7fffffffffffffffll : (cd <= -9.2e18 ? -0x7fffffffffffffffll : (long long)cd);
                     }
-                    s0 = kk + 1;
+                    base = pk;
                 }
             }
             if (lane == 0) { sh.status = stc; sh.n_out = stc == BBK_FIT_OK ? nout : 0; }
