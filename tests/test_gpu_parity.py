@@ -388,3 +388,60 @@ def test_second_pass_against_composed_reference_golden(torch_cuda):
     assert np.array_equal(g["mid1"][keep], g2["ref2_out_mid1"]) and np.array_equal(g["count"][keep], g2["ref2_out_count"])
     ok, nbad = log10_close(out.p[keep], g2["ref2_out_p"], P_TOL_GOLDEN)
     assert ok, nbad
+
+
+# K1 works on tiles of 4096 records (two groups of four per thread, 512 threads); sizes on either side of the tile and
+# group boundaries, all three kernel variants (32-bit fast path, general, with chromosome columns), coordinates that
+# wrap a 32-bit subtraction, off-grid and negative distances, counts above the shared-histogram limit and below zero.
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 4093, 4095, 4096, 4097, 4099, 8192, 8195, 12288 + 7, 100003, 1_300_001])
+@pytest.mark.parametrize("variant", ["fast", "general", "chrom"])
+def test_hist_kernel_edge_sizes_against_oracle(n, variant, torch_cuda):
+    torch = torch_cuda
+    from blueberry_b200.engine import PassEngine, Shard
+    from oracle import fithic_oracle as fo
+    rng = np.random.default_rng(n * 3 + len(variant))
+    R, nkeys = 5000, 700
+    bins = rng.integers(0, 900, size=(2, n))
+    mid1 = (2500 + R * bins.min(axis=0)).astype(np.int64)
+    mid2 = (2500 + R * bins.max(axis=0)).astype(np.int64)
+    k = rng.choice(n, max(n // 40, 1), replace=False)
+    mid2[k] += rng.integers(1, R, size=len(k))                       # off the grid
+    k = rng.choice(n, max(n // 60, 1), replace=False)
+    mid1[k], mid2[k] = mid2[k].copy(), mid1[k].copy()                # negative distances
+    k = rng.choice(n, max(n // 90, 1), replace=False)
+    mid1[k] = rng.choice([-2**31, -2**31 + 1, -5, 2**31 - 1], size=len(k))
+    k = rng.choice(n, max(n // 90, 1), replace=False)
+    mid2[k] = rng.choice([-2**31, 2**31 - 1, 2**31 - 2, -1], size=len(k))
+    count = rng.poisson(0.7, size=n).astype(np.int64)
+    k = rng.choice(n, max(n // 70, 1), replace=False)
+    count[k] = rng.choice([4095, 4096, 4097, 2**31 - 1, -3, 100000], size=len(k))
+    chr1 = chr2 = None
+    if variant == "chrom":
+        chr1 = rng.integers(0, 3, size=n).astype(np.int32)
+        chr2 = np.where(rng.random(n) < 0.9, chr1, (chr1 + 1) % 3).astype(np.int32)
+    min_dist, max_dist = (2 * R, 600 * R) if variant == "fast" else (-1, -1) if variant == "general" else (R, 800 * R)
+    ref = fo.read_interactions(nkeys, R, chr1, mid1, chr2, mid2, count, min_dist, max_dist)
+
+    dev = torch.device("cuda:0")
+    to = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    sh = Shard(to(mid1), to(mid2), to(count), to(chr1), to(chr2))
+    eng = PassEngine(R, 100, min_dist, max_dist, nkeys, device=dev)
+    eng.hist([sh])
+    torch.cuda.synchronize()
+    t = eng.totals.cpu().numpy()
+    assert np.array_equal(eng.obs_sum.cpu().numpy(), ref.observed)
+    assert [int(v) for v in t] == [ref.S, ref.intra_in_range_count, ref.intra_all_sum, ref.intra_all_count,
+                                   ref.inter_all_sum, ref.inter_all_count, ref.min_obs_dist, ref.max_obs_dist]
+
+    # the second pass' histogram: the records with p <= threshold left out (fithic.py:413-435 feeding :229-270)
+    p = rng.random(n)
+    p[rng.choice(n, max(n // 10, 1), replace=False)] = 0.25
+    keep = ~(p <= 0.25)
+    ref2 = fo.read_interactions(nkeys, R, None if chr1 is None else chr1[keep], mid1[keep], None if chr2 is None else chr2[keep],
+                                mid2[keep], count[keep], min_dist, max_dist)
+    eng.hist_excluding([sh], [torch.from_numpy(p).to(dev)], 0.25)
+    torch.cuda.synchronize()
+    t = eng.totals.cpu().numpy()
+    assert np.array_equal(eng.obs_sum.cpu().numpy(), ref2.observed)
+    assert [int(v) for v in t] == [ref2.S, ref2.intra_in_range_count, ref2.intra_all_sum, ref2.intra_all_count,
+                                   ref2.inter_all_sum, ref2.inter_all_count, ref2.min_obs_dist, ref2.max_obs_dist]
