@@ -93,20 +93,22 @@ __device__ __forceinline__ void process_record(const HistParams& P, unsigned* sh
     }
 }
 
-// FAST path (0 <= d <= max_dist < 2^31 for every in-range record, no chromosome columns): one int4 group = 4
+// FAST path (0 <= d <= max_dist < 2^31 for every in-range record): one int4 group = 4
 // consecutive records of a lane.  32-bit arithmetic throughout: with m2 >= m1 (signed) the difference is in [0, 2^32) and
 // equal to the wrapped 32-bit subtraction, so "lo_excl < d <= hi_incl" is one unsigned span test; without it d < 0 is out of
 // range anyway.  The warp-uniform test (diagonal-major input: all 128 records of the warp step on one distance) is made once
 // per group, otherwise plain shared atomics (ptxas turns a predicated red.shared back into a branch, so there is no
 // cheaper form of those).
 struct FastAcc {
-    long long S, intra_sum;
-    int in_range, intra_cnt, dmin, dmax;
+    long long S, intra_sum, inter_sum;
+    int in_range, intra_cnt, inter_cnt, dmin, dmax;
 };
 
-template <bool FULL>
-__device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, bool live_group, unsigned excl, FastAcc& a) {
+template <bool FULL, bool HAS_CHR>
+__device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, int4 x1, int4 x2,
+                                                   bool live_group, unsigned excl, FastAcc& a) {
     const int m1s[4] = {m1.x, m1.y, m1.z, m1.w}, m2s[4] = {m2.x, m2.y, m2.z, m2.w}, cs[4] = {c.x, c.y, c.z, c.w};
+    const int x1s[4] = {x1.x, x1.y, x1.z, x1.w}, x2s[4] = {x2.x, x2.y, x2.z, x2.w};
     unsigned key[4];
     bool ok[4];
 #pragma unroll
@@ -115,8 +117,16 @@ __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned
         const unsigned ud = (unsigned)m2s[e] - (unsigned)m1s[e];                      // fithic.py:247
         const bool in_range = live && m2s[e] >= m1s[e] && (ud - P.lo_u) <= P.span_u;  // fithic.py:256-257
         const int d = (int)ud;                                                        // < 2^31 when in_range
-        a.intra_sum += live ? cs[e] : 0;
-        a.intra_cnt += live ? 1 : 0;
+        if (HAS_CHR) {                                                                // fithic.py:249-254
+            const bool inter = live && x1s[e] != x2s[e], intra = live && x1s[e] == x2s[e];
+            a.inter_sum += inter ? cs[e] : 0;
+            a.inter_cnt += inter ? 1 : 0;
+            a.intra_sum += intra ? cs[e] : 0;
+            a.intra_cnt += intra ? 1 : 0;
+        } else {
+            a.intra_sum += live ? cs[e] : 0;
+            a.intra_cnt += live ? 1 : 0;
+        }
         if (in_range) {
             a.dmin = min(a.dmin, d);                                                  // fithic.py:258-259
             a.dmax = max(a.dmax, d);
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
     __syncthreads();
 
     Acc a = {0, 0, 0, 0, 0, 0, 500000000ll, 0ll};                      // fithic.py:40-41 initial min / max
-    FastAcc fa = {0, 0, 0, 0, 500000000, 0};
+    FastAcc fa = {0, 0, 0, 0, 0, 0, 500000000, 0};
     const long long n_groups = P.n_pairs >> 2;                         // groups of 4 records (one int4 per column)
     const int4* m1v = reinterpret_cast<const int4*>(P.mid1);
     const int4* m2v = reinterpret_cast<const int4*>(P.mid2);
@@ -187,8 +197,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
     const long long tile_groups = 2ll * blockDim.x;
     const long long n_tiles = (n_groups + tile_groups - 1) / tile_groups;
     long long tile = blockIdx.x;
-    if (FAST && !HAS_CHR) {
-        // full tiles: no bounds predicates, the six loads of a thread go out back to back
+    if (FAST) {
+        // full tiles: no bounds predicates, the loads of a thread go out back to back
         const long long full_tiles = n_groups / tile_groups;
         const double2* pe = reinterpret_cast<const double2*>(P.p_excl);
         for (; tile < full_tiles; tile += gridDim.x) {
@@ -196,6 +206,11 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
             const long long g1 = g0 + blockDim.x;
             const int4 a1 = ld_stream_int4(m1v + g0), a2 = ld_stream_int4(m2v + g0), ac = ld_stream_int4(cv + g0);
             const int4 b1 = ld_stream_int4(m1v + g1), b2 = ld_stream_int4(m2v + g1), bc = ld_stream_int4(cv + g1);
+            int4 ax = make_int4(0, 0, 0, 0), ay = ax, bx = ax, by = ax;
+            if (HAS_CHR) {
+                ax = ld_stream_int4(c1v + g0); ay = ld_stream_int4(c2v + g0);
+                bx = ld_stream_int4(c1v + g1); by = ld_stream_int4(c2v + g1);
+            }
             unsigned xa = 0, xb = 0;
             if (pe) {
                 const double2 u0 = ld_stream_double2(pe + 2 * g0), v0 = ld_stream_double2(pe + 2 * g0 + 1);
@@ -203,8 +218,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
                 xa = (u0.x <= P.p_thr ? 1u : 0u) | (u0.y <= P.p_thr ? 2u : 0u) | (v0.x <= P.p_thr ? 4u : 0u) | (v0.y <= P.p_thr ? 8u : 0u);
                 xb = (u1.x <= P.p_thr ? 1u : 0u) | (u1.y <= P.p_thr ? 2u : 0u) | (v1.x <= P.p_thr ? 4u : 0u) | (v1.y <= P.p_thr ? 8u : 0u);
             }
-            process_group_fast<true>(P, sh, a1, a2, ac, true, xa, fa);
-            process_group_fast<true>(P, sh, b1, b2, bc, true, xb, fa);
+            process_group_fast<true, HAS_CHR>(P, sh, a1, a2, ac, ax, ay, true, xa, fa);
+            process_group_fast<true, HAS_CHR>(P, sh, b1, b2, bc, bx, by, true, xb, fa);
             since_flush += 4 * tile_groups;
             if (since_flush >= FLUSH_PAIRS) {      // uniform across the CTA
                 flush_hist(P, sh);
@@ -234,9 +249,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
             if (l1) { double2 u = ld_stream_double2(pe + 2 * g1), v = ld_stream_double2(pe + 2 * g1 + 1);
                       xb = (u.x <= P.p_thr ? 1u : 0u) | (u.y <= P.p_thr ? 2u : 0u) | (v.x <= P.p_thr ? 4u : 0u) | (v.y <= P.p_thr ? 8u : 0u); }
         }
-        if (FAST && !HAS_CHR) {
-            process_group_fast<false>(P, sh, a1, a2, ac, l0, xa, fa);
-            process_group_fast<false>(P, sh, b1, b2, bc, l1, xb, fa);
+        if (FAST) {
+            process_group_fast<false, HAS_CHR>(P, sh, a1, a2, ac, ax, ay, l0, xa, fa);
+            process_group_fast<false, HAS_CHR>(P, sh, b1, b2, bc, bx, by, l1, xb, fa);
         } else {
             process_record<HAS_CHR>(P, sh, a1.x, a2.x, ac.x, ax.x, ay.x, l0 && !(xa & 1u), a);
             process_record<HAS_CHR>(P, sh, a1.y, a2.y, ac.y, ax.y, ay.y, l0 && !(xa & 2u), a);
@@ -264,8 +279,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
         process_record<HAS_CHR>(P, sh, m1, m2, c, c1, c2, live, a);
     }
     flush_hist(P, sh);
-    if (FAST && !HAS_CHR) {
+    if (FAST) {
         a.S += fa.S; a.in_range += fa.in_range; a.intra_sum += fa.intra_sum; a.intra_cnt += fa.intra_cnt;
+        a.inter_sum += fa.inter_sum; a.inter_cnt += fa.inter_cnt;
         a.dmin = fa.dmin < a.dmin ? fa.dmin : a.dmin;
         a.dmax = fa.dmax > a.dmax ? fa.dmax : a.dmax;
     }
@@ -329,8 +345,7 @@ static int hist_pairs_impl(const int32_t* d_chr1, const int32_t* d_chr2, const i
     P.hi_incl = (max_dist == -1) ? 0x7fffffffffffffffll : (max_dist > -1 ? max_dist : (-0x7fffffffffffffffll - 1));
     // 31-bit fast path: every in-range distance is in [0, 2^31)
     // (and a non-empty range, so that it is one unsigned span: lo_u <= d <= lo_u + span_u)
-    const bool fast = d_chr1 == nullptr && min_dist >= -1 && max_dist >= 0 && max_dist < (1ll << 31) && P.lo_excl >= -1 &&
-                      P.lo_excl < P.hi_incl;
+    const bool fast = min_dist >= -1 && max_dist >= 0 && max_dist < (1ll << 31) && P.lo_excl >= -1 && P.lo_excl < P.hi_incl;
     P.lo_u = fast ? (unsigned)(P.lo_excl + 1) : 0u;
     P.span_u = fast ? (unsigned)(P.hi_incl - (P.lo_excl + 1)) : 0u;
     P.nkeys = nkeys;
@@ -351,16 +366,14 @@ static int hist_pairs_impl(const int32_t* d_chr1, const int32_t* d_chr2, const i
     long long grid = (long long)sms * per_sm;
     if (need < grid) grid = need > 0 ? need : 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_chr1) {
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hist_pairs_kernel<true, false><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
-    } else if (fast) {
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hist_pairs_kernel<false, true><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
-    } else {
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hist_pairs_kernel<false, false><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);
-    }
+#define BBK_HIST_LAUNCH(C, F)                                                                                                   \
+    do {                                                                                                                         \
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        hist_pairs_kernel<C, F><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);                                                  \
+    } while (0)
+    if (d_chr1) { if (fast) BBK_HIST_LAUNCH(true, true); else BBK_HIST_LAUNCH(true, false); }
+    else        { if (fast) BBK_HIST_LAUNCH(false, true); else BBK_HIST_LAUNCH(false, false); }
+#undef BBK_HIST_LAUNCH
     BBK_CHECK_LAUNCH("hist_pairs_kernel");
     return BBK_OK;
 }

@@ -391,10 +391,10 @@ def test_second_pass_against_composed_reference_golden(torch_cuda):
 
 
 # K1 works on tiles of 4096 records (two groups of four per thread, 512 threads); sizes on either side of the tile and
-# group boundaries, all three kernel variants (32-bit fast path, general, with chromosome columns), coordinates that
+# group boundaries, all four kernel variants (32-bit fast path / general, without / with chromosome columns), coordinates that
 # wrap a 32-bit subtraction, off-grid and negative distances, counts above the shared-histogram limit and below zero.
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 4093, 4095, 4096, 4097, 4099, 8192, 8195, 12288 + 7, 100003, 1_300_001])
-@pytest.mark.parametrize("variant", ["fast", "general", "chrom"])
+@pytest.mark.parametrize("variant", ["fast", "general", "chrom", "chrom_general"])
 def test_hist_kernel_edge_sizes_against_oracle(n, variant, torch_cuda):
     torch = torch_cuda
     from blueberry_b200.engine import PassEngine, Shard
@@ -416,10 +416,10 @@ def test_hist_kernel_edge_sizes_against_oracle(n, variant, torch_cuda):
     k = rng.choice(n, max(n // 70, 1), replace=False)
     count[k] = rng.choice([4095, 4096, 4097, 2**31 - 1, -3, 100000], size=len(k))
     chr1 = chr2 = None
-    if variant == "chrom":
+    if variant.startswith("chrom"):
         chr1 = rng.integers(0, 3, size=n).astype(np.int32)
         chr2 = np.where(rng.random(n) < 0.9, chr1, (chr1 + 1) % 3).astype(np.int32)
-    min_dist, max_dist = (2 * R, 600 * R) if variant == "fast" else (-1, -1) if variant == "general" else (R, 800 * R)
+    min_dist, max_dist = {"fast": (2 * R, 600 * R), "general": (-1, -1), "chrom": (R, 800 * R), "chrom_general": (-1, 650 * R)}[variant]
     ref = fo.read_interactions(nkeys, R, chr1, mid1, chr2, mid2, count, min_dist, max_dist)
 
     dev = torch.device("cuda:0")
