@@ -33,7 +33,7 @@ class FitResult(ctypes.Structure):
         ("n_knots", ctypes.c_int32), ("ier", ctypes.c_int32), ("S", ctypes.c_int64),
         ("min_x", ctypes.c_double), ("max_x", ctypes.c_double), ("residual", ctypes.c_double),
         ("fp", ctypes.c_double), ("smoothing", ctypes.c_double), ("phase_cycles", ctypes.c_int64 * 6),
-        ("spline_diag", ctypes.c_int64 * 8),
+        ("spline_diag", ctypes.c_int64 * 8), ("y_min", ctypes.c_double),
     ]
 
 

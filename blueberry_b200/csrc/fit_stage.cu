@@ -49,6 +49,7 @@ struct FitShared {
     long long slice_tot[FIT_THREADS];
     int s_given;
     double s_in;
+    double y_min;
     double cmax[FIT_THREADS], cmin[FIT_THREADS];      // antitonic regression: extrema of each thread's chunk
 };
 
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         sh.s_given = P.result->status == BBK_FIT_S_GIVEN;      // the caller supplies s (include/bbk.h: BbkFitResult.smoothing)
         sh.s_in = P.result->smoothing;
         sh.status = BBK_FIT_OK;
-        sh.n_out = 0; sh.k0 = 0; sh.L = 0;
+        sh.n_out = 0; sh.k0 = 0; sh.L = 0; sh.y_min = 0.0; sh.s = 0.0;
         sh.S = injected ? 0 : P.totals[0];
         long long eff = P.nkeys;
         if (P.max_dist > -1) { long long lim = P.max_dist / P.R + 1; if (lim < eff) eff = lim; }
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
                 nondecr = nondecr && (xs[j] - xs[j - 1] >= 0.0);
                 strict = strict && (xs[j] - xs[j - 1] > 0.0);
             }
+            sh.y_min = ymin;
             sh.s = sh.s_given ? sh.s_in : ymin * ymin;       // fithic.py:340
             sh.min_x = xmin;                                 // fithic.py:350
             sh.max_x = xmax;
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) fit_kernel(FitParams P) {
         r->max_x = sh.max_x;
         r->fp = sh.st.fp;
         r->smoothing = sh.s;
+        r->y_min = sh.y_min;
         sh.t[5] = clock64();
         for (int i = 0; i < 5; ++i) r->phase_cycles[i] = (sh.t[i + 1] && sh.t[i]) ? sh.t[i + 1] - sh.t[i] : 0;
         r->phase_cycles[5] = sh.t[5] - sh.t[0];

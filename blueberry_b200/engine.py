@@ -271,24 +271,29 @@ class PassEngine(object):
         return n_all
 
     # ------------------------------------------------------------------ results
-    def reference_smoothing(self, fit):
+    @staticmethod
+    def reference_smoothing(fit):
         """s exactly as the reference computes it, `min(y)**2` on Python floats (fithic.py:340): that is libm's pow(ymin, 2.0),
         which is one ulp away from the correctly rounded ymin*ymin the kernel computes for about 0.09 % of inputs (glibc 2.39).
-        Returns None when the kernel's s (fit.smoothing) already equals it, else the value to pass to fit(smoothing=...)."""
-        y = self.y[:fit.n_out].cpu().tolist()
-        if not y:
+        Returns None when the kernel's s (fit.smoothing) already equals it, else the value to pass to fit(smoothing=...).
+        min(y) comes back inside the fit result (BbkFitResult.y_min)."""
+        if fit.n_out <= 0:
             return None
-        s_ref = min(y) ** 2
+        s_ref = float(fit.y_min) ** 2
         return None if s_ref == fit.smoothing else s_ref
 
-    def read_fit(self):
-        """Copy the fit status back (synchronises) and raise what the reference would raise."""
-        raw = self.fit_result.cpu().numpy().tobytes()
+    @staticmethod
+    def decode_fit(raw):
+        """BbkFitResult bytes -> FitResult; raises what the reference would raise for a failed fit."""
         res = _lib.FitResult.from_buffer_copy(raw)
         err = _lib.FIT_STATUS.get(res.status, (RuntimeError, "fit stage failed with status %d" % res.status))
         if err is not None:
             raise err[0](err[1])
         return res
+
+    def read_fit(self):
+        """Copy the fit status back (synchronises) and raise what the reference would raise."""
+        return self.decode_fit(self.fit_result.cpu().numpy().tobytes())
 
     def run_second_pass(self, shards, p_first, p_outs, p_outlier, q_outs=None, n_tests=-1, group=None, smoothing=None):
         """Refit after outlier removal (BASELINE config 4; definition in include/bbk.h): statistics from the records
@@ -354,6 +359,9 @@ class HostPipeline(object):
             s.mid1, s.mid2, s.count = (torch.empty(self.max_pairs, dtype=torch.int32, device=dev) for _ in range(3))
             s.p, s.q = (torch.empty(padded, dtype=torch.float64, device=dev) for _ in range(2))
             s.in_ready, s.run_done, s.out_done = (torch.cuda.Event() for _ in range(3))
+            s.fit = torch.zeros_like(engine.fit_result)                      # this pass' BbkFitResult (the engine's is overwritten by the next pass)
+            s.h_fit = torch.zeros(engine.fit_result.numel(), dtype=torch.uint8).pin_memory()
+            s.index = -1
             self.slots.append(s)
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.s_run.wait_stream(torch.cuda.current_stream(dev))      # the engine's tables were filled there
@@ -386,14 +394,28 @@ class HostPipeline(object):
                 run(sh, s.p[:n], s.q[:n] if h_q is not None else None)
             else:
                 self.eng.run([sh], [s.p[:n]], [s.q[:n]] if h_q is not None else None, n_tests=n_tests)
+            s.fit.copy_(self.eng.fit_result, non_blocking=True)
             s.run_done.record()
         self.s_out.wait_event(s.run_done)
         with torch.cuda.stream(self.s_out):
             h_p.copy_(s.p[:n], non_blocking=True)
             if h_q is not None:
                 h_q.copy_(s.q[:n], non_blocking=True)
+            s.h_fit.copy_(s.fit, non_blocking=True)
             s.out_done.record()
+        s.index = self.submitted - 1
         return s.out_done
+
+    def fit_of(self, index):
+        """Fit result of submission `index` (0-based), once its outputs are on the host: raises what the reference would
+        raise for that library (ZeroDivisionError, ...), else returns the FitResult - PassEngine.reference_smoothing(result)
+        then tells whether the pass has to be submitted again with the reference's own s.  Only the last `slots`
+        submissions are kept."""
+        s = self.slots[int(index) % len(self.slots)]
+        if s.index != int(index):
+            raise KeyError("submission %d is no longer (or not yet) held by the pipeline" % int(index))
+        s.out_done.synchronize()
+        return PassEngine.decode_fit(s.h_fit.numpy().tobytes())
 
     def drain(self):
         self.s_out.synchronize()

@@ -112,6 +112,7 @@ typedef struct BbkFitResult {
                                 antitonic regression + residual, total */
     int64_t spline_diag[8];  /* LSQ fits, smoothing iterations, then SM cycles: B-spline rows, row QR + back
                                 substitution, residuals + knot insertion, Givens sweep, f(p) evaluation */
+    double y_min;            /* min(y): what the host needs to form the reference's own s = min(y)**2 for the check above */
 } BbkFitResult;
 
 /* bytes of scratch bbk_fit needs for up to max_bins bins and nkeys distances */

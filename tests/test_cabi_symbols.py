@@ -52,7 +52,7 @@ def test_fit_result_struct_matches_header():
         for part in f.split(","):
             flat.append(re.sub(r"\[.*\]", "", part).strip())
     assert flat == [n for n, _ in _lib.FitResult._fields_]
-    assert ctypes.sizeof(_lib.FitResult) == 6 * 4 + 8 + 5 * 8 + 6 * 8 + 8 * 8
+    assert ctypes.sizeof(_lib.FitResult) == 6 * 4 + 8 + 5 * 8 + 6 * 8 + 8 * 8 + 8
 
 
 def test_workspace_queries_run_without_a_gpu(lib):

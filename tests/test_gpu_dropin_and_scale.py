@@ -233,7 +233,8 @@ def test_host_pipeline_matches_serial_passes():
         p = torch.empty(n + 1, dtype=torch.float64, device=dev)[:n]
         q = torch.empty(n + 1, dtype=torch.float64, device=dev)[:n]
         eng.run([Shard(*cols)], [p], [q])
-        want.append((p.cpu(), q.cpu()))
+        fit = eng.read_fit()
+        want.append((p.cpu(), q.cpu(), (fit.S, fit.n_knots, fit.smoothing, fit.y_min)))
         libs.append([c.cpu().pin_memory() for c in cols])
     torch.cuda.synchronize()
     pipe = HostPipeline(eng, P, slots=2)
@@ -245,10 +246,26 @@ def test_host_pipeline_matches_serial_passes():
     outs[0][2].synchronize()                          # the event of the first library alone makes its outputs readable
     assert torch.equal(outs[0][0].view(torch.int64), want[0][0].view(torch.int64))
     pipe.drain()
-    for (h_p, h_q, _), (p, q) in zip(outs, want):
+    for (h_p, h_q, _), (p, q, _fit) in zip(outs, want):
         assert torch.equal(h_p.view(torch.int64), p.view(torch.int64))
         assert torch.equal(h_q.view(torch.int64), q.view(torch.int64))
     assert (want[0][0][:100000] != want[1][0][:100000]).any()
+    # every pass leaves its own fit result (the engine's is overwritten by the next pass); the last `slots` are held
+    for k in (3, 4):
+        fit = pipe.fit_of(k)
+        assert (fit.S, fit.n_knots, fit.smoothing, fit.y_min) == want[k][2]
+        assert fit.y_min > 0 and PassEngine.reference_smoothing(fit) in (None, fit.y_min ** 2)
+    with pytest.raises(KeyError):
+        pipe.fit_of(0)
+    # a library without a single contact: the reference divides by S == 0 (fithic.py:216); the pipeline reports it per pass
+    zero = torch.zeros(libs[0][2].numel(), dtype=torch.int32).pin_memory()
+    h_p = torch.empty(zero.numel(), dtype=torch.float64).pin_memory()
+    pipe.submit(libs[0][0], libs[0][1], zero, h_p)
+    with pytest.raises(ZeroDivisionError):
+        pipe.fit_of(5)
+    pipe.submit(libs[1][0], libs[1][1], libs[1][2], outs[1][0], outs[1][1])      # and the next pass is not affected
+    assert pipe.fit_of(6).S == want[1][2][0]
+    assert torch.equal(outs[1][0].view(torch.int64), want[1][0].view(torch.int64))
     with pytest.raises(ValueError):
         pipe.submit(libs[0][0], libs[0][1], libs[0][2], torch.empty(libs[0][0].numel(), dtype=torch.float64))
 
