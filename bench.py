@@ -5,16 +5,19 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
 
-Workload (config.workload): BASELINE config 2 - chr1 at 5 kb (49,851 bins), every pair within 10 Mb
-(97,750,851 records, zeros kept), ICE-style biases, synthetic counts generated on the device.
-At N > 1 every rank holds one such chromosome-sized shard (weak scaling): the per-distance table and
-totals are all-reduced over NCCL (S, the bins and the spline are genome-wide, identical on all ranks),
-p-values are per shard; q-values are ranked genome-wide across the ranks (all-reduce of the coarse p histogram
-+ all-gather of the few candidate keys; `--q-scope shard` ranks per chromosome instead).
-A "step" is one whole pass over the resident records: K1 histogram -> [allreduce] -> K2/K3 fit ->
-K4 p-values (+ coarse p histogram) -> K5 Benjamini-Hochberg q-values.
+Default workload (config.workload): BASELINE config 3 - the 23 hg19 chromosomes at 5 kb (607,271 bins), every pair within
+10 Mb (1,169,126,271 records, zeros kept), ICE-style biases, synthetic counts generated on the device - the configuration
+the metric is quoted on ("at 1/2/4/8 B200").  The SAME genome is scored at every N (strong scaling): the records are
+cut into N equal pieces along the chromosomes (distributed.plan_shards: whole chromosomes, a chromosome that straddles
+a cut is split into row blocks), through the public multi-GPU entry point distributed.GenomePass: K1 per shard ->
+all-reduce of the distance table (NCCL) -> fit -> K4 (classification overlapped with the fit, then the dense work
+lists) -> genome-wide Benjamini-Hochberg q-values (histogram all-reduce + one fixed-capacity all-gather).
+With --gpus 8 the line also carries BASELINE config 5 (genome-wide 1 kb, 2 Mb cap, 6,029,643,315 records) as
+cfg5_ms_per_step / cfg5_frac.  Other workloads: --workload cfg2 (chr1 @ 5 kb), cfg4 (chr1 @ 1 kb, two passes), cfg5.
+A "step" is one whole pass over the resident records.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -27,15 +30,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-RESOLUTION = 5000
-CHR1_BINS = 49851            # ceil(249,250,621 / 5000)
-MAX_DIST = 10_000_000
 N_BINS = 100
-DEPTH = 600.0                # Poisson mean of a d=0 pair with unit bias -> S ~ 2e8 per shard (8 shards stay < 2^31)
 DECAY = 1.08
 SEED = 20161108
 BYTES_PER_PAIR = 48          # 12 (K1 read) + 20 (K4 read+write) + 16 (K5 read+write), BASELINE.md section 2
 K4_BYTES_PER_PAIR = 20
+
+HG19 = [249250621, 243199373, 198022430, 191154276, 180915260, 171115067, 159138663, 146364022, 141213431, 135534747,
+        135006516, 133851895, 115169878, 107349540, 102531392, 90354753, 81195210, 78077248, 59128983, 63025520, 48129895,
+        51304566, 155270560]
+
+# depth = Poisson mean of a d = 0 pair with unit bias, chosen so that S stays below 2^31 (the reference's bdtrc takes a C int)
+WORKLOADS = {
+    "cfg2": dict(R=5000, max_dist=10_000_000, depth=600.0, chroms=[0], two_pass=False,
+                 name="cfg2: chr1@5kb, all pairs within 10 Mb"),
+    "cfg3": dict(R=5000, max_dist=10_000_000, depth=450.0, chroms=list(range(23)), two_pass=False,
+                 name="cfg3: 23 hg19 chromosomes @5kb, all intra-chromosomal pairs within 10 Mb, sharded by chromosome"),
+    "cfg4": dict(R=1000, max_dist=2_000_000, depth=60.0, chroms=[0], two_pass=True,
+                 name="cfg4: chr1@1kb, all pairs within 2 Mb, two passes (refit after outlier removal)"),
+    "cfg5": dict(R=1000, max_dist=2_000_000, depth=25.0, chroms=list(range(23)), two_pass=False,
+                 name="cfg5: 23 hg19 chromosomes @1kb, all intra-chromosomal pairs within 2 Mb, band-sharded"),
+}
 
 
 def _peaks():
@@ -44,6 +59,30 @@ def _peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _k4_sources_sha():
+    h = hashlib.sha256()
+    for f in ("pvalue.cu", "pvalue_lists.inl"):
+        with open(os.path.join(ROOT, "blueberry_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def _k4_traffic(workload, n_gpus):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the K4 kernels from the committed ncu --set full capture of THIS
+    workload and THESE kernel sources (profiles/k4_traffic.json); None when there is no capture or the sources changed."""
+    path = os.path.join(ROOT, "profiles", "k4_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path) as fh:
+            for rec in json.load(fh):
+                if rec.get("workload") == workload and rec.get("n_gpus") == n_gpus and rec.get("sources_sha16") == _k4_sources_sha():
+                    return rec.get("dram_bytes")
+    except Exception:
+        return None
+    return None
 
 
 class ClockSampler(object):
@@ -110,26 +149,26 @@ class ClockSampler(object):
 def _cpu_block(args):
     """One bounded sample: a chromosome-shaped block (nb bins, all pairs within max_dist) through the whole
     reference path restated in oracle/fithic_oracle.py: histogram, binning, spline, scoring, BH."""
-    nb, seed, repeat = args
+    nb, seed, repeat, R, max_dist, depth = args
     import numpy as np
     from blueberry_b200 import synth
     from oracle import fithic_oracle as fo
     bias = synth.make_bias([nb], seed)
-    fc, fm = synth.make_fragments([nb], RESOLUTION)
-    c = synth.make_contacts([nb], RESOLUTION, MAX_DIST, DEPTH, seed, bias)
+    fc, fm = synth.make_fragments([nb], R)
+    c = synth.make_contacts([nb], R, max_dist, depth, seed, bias)
     bd, _ = fo.read_bias_arrays(np.zeros(nb, dtype=np.int64), fm, bias[0])
     t0 = time.perf_counter()
     for _ in range(repeat):
-        res = fo.fithic_arrays(fc, fm, None, c["mid1"], None, c["mid2"], c["count"], RESOLUTION, N_BINS, 0, MAX_DIST, bias=bd)
+        res = fo.fithic_arrays(fc, fm, None, c["mid1"], None, c["mid2"], c["count"], R, N_BINS, 0, max_dist, bias=bd)
         keep = res.keep
         fo.benjamini_hochberg_correction(res.p[keep], int(keep.sum()))
     return len(c["count"]) * repeat, time.perf_counter() - t0
 
 
-def cpu_baseline(cores, nb=3000, repeat=1):
+def cpu_baseline(cores, wl, nb=3000, repeat=1):
     """pairs/s of the oracle port on `cores` host processes (each gets its own block)."""
     import multiprocessing as mp
-    jobs = [(nb, SEED + 101 * i, repeat) for i in range(cores)]
+    jobs = [(nb, SEED + 101 * i, repeat, wl["R"], wl["max_dist"], wl["depth"]) for i in range(cores)]
     t0 = time.perf_counter()
     if cores == 1:
         res = [_cpu_block(jobs[0])]
@@ -146,25 +185,29 @@ def run_reference_arm(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    cores = min(cores, 64)
-    nb = 2600
+    wl = WORKLOADS[args.workload]
+    cores = min(os.cpu_count() or 1, 64)
+    nb = 2600 if wl["R"] == 5000 else 4200
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline(cores, nb=nb)
+        cpu_baseline(cores, wl, nb=nb)
     vals, per_step = [], []
     for _ in range(args.steps):
-        v, pairs, wall, _ = cpu_baseline(cores, nb=nb)
+        v, pairs, wall, _ = cpu_baseline(cores, wl, nb=nb)
         vals.append(v); per_step.append(wall)
     value = statistics.mean(vals)
-    sample = "%d blocks/step of %d bins (all pairs within 10 Mb at 5 kb, ~%.1fM records each), one per core" % (
-        cores, nb, (2001 * nb - 2000 * 2001 // 2) / 1e6)
+    K = wl["max_dist"] // wl["R"]
+    sample = "%d blocks/step of %d bins (all pairs within %d bp at %d bp, ~%.1fM records each), one per core" % (
+        cores, nb, wl["max_dist"], wl["R"], ((K + 1) * nb - K * (K + 1) // 2) / 1e6)
     line = {
         "impl": "reference", "metric": "fithic_contact_pairs_per_sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(per_step),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2 chr1@5kb pairs within 10Mb (bounded sample per step)", "resolution": RESOLUTION,
-                   "n_bins": N_BINS, "max_dist": MAX_DIST},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"] + " (bounded sample per step)", "resolution": wl["R"],
+                   "n_bins": N_BINS, "max_dist": wl["max_dist"]},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "oracle/fithic_oracle.py (numpy / scipy restatement of fithic.py, ~100x faster than the reference's "
+                                 "per-line Python; the unmodified reference itself needs /root/reference, absent on the GPU box - "
+                                 "its rate, timed in the build container, is in DESIGN.md section 5)"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,113 +217,161 @@ def run_reference_arm(args, out_fd):
 # =================================================================================================
 # GPU arm
 # =================================================================================================
-def run_ours(args, out_fd):
+class Workload(object):
+    """This rank's share of a synthetic genome, resident on the device, plus the genome-wide tables every rank holds."""
+
+    def __init__(self, wl, world, rank, dev, pieces=None, share_of=None):
+        import numpy as np
+        import torch
+        from blueberry_b200 import _lib
+        from blueberry_b200.distributed import layout_rows, plan_shards
+        from blueberry_b200.engine import BiasTables, PassEngine, Shard
+        lib = _lib.load()
+        R, K = wl["R"], wl["max_dist"] // wl["R"]
+        self.R, self.K, self.max_dist = R, K, wl["max_dist"]
+        self.bins = [-(-HG19[c] // R) for c in wl["chroms"]]
+        self.pairs = [int(lib.bbk_synth_n_pairs(nb, K)) for nb in self.bins]
+        # share_of: this run holds `world` of the share_of pieces of the genome (single-GPU stand-in for a larger box)
+        plan = plan_shards(self.pairs, share_of or world)
+        mine = plan[rank]
+        self.P_total = sum(n for r in range(world) for (_, _, n) in plan[r])
+        self.sizes = [n for (_, _, n) in mine]
+        self.chroms = [c for (c, _, _) in mine]
+        starts, rows = layout_rows(self.sizes)
+        self.starts, self.rows = starts, max(rows, 4)
+        self.P_local = sum(self.sizes)
+        self.mid1, self.mid2, self.count = (torch.zeros(self.rows, dtype=torch.int32, device=dev) for _ in range(3))
+        bias_host = []
+        for ci, nb in enumerate(self.bins):
+            rng = np.random.default_rng(SEED + 7919 * (wl["chroms"][ci] + 1))
+            bias_host.append(np.exp(rng.normal(0.0, 0.25, size=nb)))
+        self.bias_host = bias_host
+        for (c, first, n), off in zip(mine, starts):
+            bdev = torch.from_numpy(bias_host[c]).to(dev)
+            _lib.check(lib.bbk_synth_contacts_range(self.bins[c], K, R, wl["depth"], DECAY, SEED + 1000003 * c, _lib.ptr(bdev), first, n,
+                                                    ctypes_ptr(self.mid1, off), ctypes_ptr(self.mid2, off), ctypes_ptr(self.count, off),
+                                                    _lib.stream_ptr()), "bbk_synth_contacts_range")
+            torch.cuda.synchronize()
+        self.shards = [Shard(self.mid1[a:a + n], self.mid2[a:a + n], self.count[a:a + n], chrom=c)
+                       for a, n, c in zip(starts, self.sizes, self.chroms)]
+        self.nkeys = max(self.bins)                      # maxPossibleGenomicDist / R + 1 (fithic.py:300-303)
+        self.eng = PassEngine(R, N_BINS, 0, self.max_dist, self.nkeys, dev)
+        self.eng.set_fragments(self.bins, [(nb - 1) * R for nb in self.bins])
+        tabs = [np.where((b < 0.5) | (b > 2), -1.0, b) for b in bias_host]       # read_bias_file, fithic.py:147-149
+        self.eng.set_bias(BiasTables(tabs, [R // 2] * len(self.bins), dev))
+        self.possible_in_range = sum(nb * K - K * (K + 1) // 2 for nb in self.bins)   # d = R .. K*R
+
+
+def ctypes_ptr(t, offset_elems=0):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def _parity_bits(W, gp, fit, dev, world):
+    """Checks carried in the JSON line: (1) K1's table and S against torch.index_add_ over the same records (all-reduced),
+    bit-exact; (2) a strided 1e6-record sample of p against the oracle's scoring (scipy bdtrc) with the device's spline."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from blueberry_b200 import _lib
-    from blueberry_b200.engine import BiasTables, HostPipeline, PassEngine, Shard
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    out = {}
+    eng = W.eng
+    tab = torch.zeros(W.nkeys, dtype=torch.int64, device=dev)
+    S = torch.zeros(1, dtype=torch.int64, device=dev)
+    for sh in W.shards:
+        if sh.n == 0:
+            continue
+        d = (sh.mid2 - sh.mid1).to(torch.int64)
+        ok = (d > 0) & (d <= W.max_dist)                                   # fithic.py:256-257 (min_dist = 0: d > 0)
+        S += sh.count[ok].sum(dtype=torch.int64)
+        key = ok & (d % W.R == 0) & (d // W.R < W.nkeys)
+        tab.index_add_(0, (d[key] // W.R), sh.count[key].to(torch.int64))
+        del d, ok, key
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
+        dist.all_reduce(tab)
+        dist.all_reduce(S)
+    out["hist_equal_index_add"] = bool(torch.equal(tab, eng.obs_sum)) and int(S.item()) == int(eng.totals[0].item())
+    # p sample vs the oracle
+    try:
+        from oracle import fithic_oracle as fo
+        i_sh = max(range(len(W.shards)), key=lambda i: W.shards[i].n) if W.shards else None
+        if i_sh is not None and W.shards[i_sh].n:
+            sh = W.shards[i_sh]
+            stride = max(1, sh.n // 1_000_000)
+            sel = torch.arange(0, sh.n, stride, device=dev)
+            m1, m2, cn = (t[sel].cpu().numpy() for t in (sh.mid1, sh.mid2, sh.count))
+            pg = gp.shard_p(i_sh)[sel].cpu().numpy()
+            sy = eng.spline_y[:fit.L].cpu().numpy()
+            tabb = np.where((W.bias_host[sh.chrom] < 0.5) | (W.bias_host[sh.chrom] > 2), -1.0, W.bias_host[sh.chrom])
+            b1, b2 = tabb[(m1 - W.R // 2) // W.R], tabb[(m2 - W.R // 2) // W.R]
+            pr, scored, keep = fo.score_pairs(m1, m2, cn, int(fit.S), fit.k0, sy, W.R, 0, W.max_dist, b1, b2)
+            same_keep = bool(np.array_equal(pg <= 1, keep))
+            kk = keep & (pr > 1e-290) & (pg <= 1)
+            err = float(np.abs(np.log10(pg[kk]) - np.log10(pr[kk])).max()) if kk.any() else 0.0
+            out["p_sample_rows"] = int(len(sel))
+            out["p_sample_keep_equal"] = same_keep
+            out["p_sample_max_dlog10p_vs_scipy"] = err
+            out["S"] = int(fit.S)
+    except Exception as e:                                                     # the oracle is a checker, never a dependency
+        out["p_sample_error"] = repr(e)
+    return out
 
-    # --workload cfg4: BASELINE config 4's shape (chr1 @ 1 kb, 249,251 bins, 2 Mb cap, 496,750,251 records, sparse
-    # counts, second pass after outlier removal); the default (and what the driver measures) is config 2
-    global RESOLUTION, MAX_DIST, DEPTH
-    two_pass = False
-    if args.workload == "cfg4":
-        RESOLUTION, MAX_DIST, DEPTH = 1000, 2_000_000, 60.0
-        if args.bins == CHR1_BINS:
-            args.bins = 249251
-        two_pass = True
-    # --workload cfg5: one GPU's share of BASELINE config 5 (genome-wide 1 kb, 2 Mb cap, 3,036,315 bins over 8 GPUs):
-    # 379,540 bins per GPU as one shard, every pair within 2 Mb (759 M records), single pass with q-values
-    if args.workload == "cfg5":
-        RESOLUTION, MAX_DIST, DEPTH = 1000, 2_000_000, 25.0
-        if args.bins == CHR1_BINS:
-            args.bins = 379540
-    R, nb, K = RESOLUTION, args.bins, MAX_DIST // RESOLUTION
-    P = int(lib.bbk_synth_n_pairs(nb, K))
-    # ---- synthetic shard, generated on the device (not timed)
-    rng = np.random.default_rng(SEED + 7919 * rank)
-    bias_host = np.exp(rng.normal(0.0, 0.25, size=nb))
-    bias_dev = torch.from_numpy(bias_host).to(dev)
-    mid1 = torch.empty(P, dtype=torch.int32, device=dev)
-    mid2 = torch.empty(P, dtype=torch.int32, device=dev)
-    count = torch.empty(P, dtype=torch.int32, device=dev)
-    _lib.check(lib.bbk_synth_contacts(nb, K, R, DEPTH, DECAY, SEED + rank, _lib.ptr(bias_dev), _lib.ptr(mid1), _lib.ptr(mid2),
-                                      _lib.ptr(count), _lib.stream_ptr()), "bbk_synth_contacts")
-    shard = Shard(mid1, mid2, count, chrom=rank)
-    # ---- the genome: `world` chromosomes of nb bins each (fragment mid = i*R + R/2)
-    nkeys = (nb - 1) * R // R + 1
-    eng = PassEngine(R, N_BINS, 0, MAX_DIST, nkeys, dev)
-    eng.set_fragments([nb] * world, [(nb - 1) * R] * world)
-    tab = np.where((bias_host < 0.5) | (bias_host > 2), -1.0, bias_host)      # read_bias_file, fithic.py:147-149
-    values = [np.zeros(0)] * world
-    values[rank] = tab
-    eng.set_bias(BiasTables(values, [R // 2] * world, dev))
-    p = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
-    q = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
-    group = None
 
-    genome_q = world > 1 and args.q_scope == "genome"
+def _measure(args, wl_name, world, rank, dev, full, out):
+    """Times one workload; fills `out` (dict).  full: also stages, e2e, parity (the headline workload)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from blueberry_b200.distributed import GenomePass, HostStream
+    from blueberry_b200.engine import PassEngine
 
-    def bh():
-        if genome_q:      # all-reduce of the p histogram + all-gather of the candidate keys (2 host syncs)
-            eng.qvalues_global(p, q, n_tests=-1, group=group, hist=eng.p_hist, prepared=True)
-        else:             # K4 pre-filled q and listed the small p (bbk_pvalues_bh): no second pass over p
-            eng.qvalues(p, q, n_tests=-1, use_hist=True, prepared=True)
-
-    p_first = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P] if two_pass else None
-    p_outlier = 1.0 / float(world * (nb * (K + 1) - K * (K + 1) // 2 - nb))   # 1 / possibleIntraInRangeCount (d = R..K*R)
-
-    def bh_on(pp, qq):
-        if genome_q:
-            eng.qvalues_global(pp, qq, n_tests=-1, group=group, hist=eng.p_hist, prepared=True)
-        else:
-            eng.qvalues(pp, qq, n_tests=-1, use_hist=True, prepared=True)
-
-    def step_on(sh, pp, qq):
-        eng.hist([sh])
-        eng.allreduce_stats(group)
-        eng.fit()
-        eng.p_hist.zero_()
-        if two_pass:
-            eng.pvalues(sh, p_first, with_hist=False)
-            eng.hist_excluding([sh], [p_first], p_outlier)
-            eng.allreduce_stats(group)
-            eng.fit()
-        eng.pvalues(sh, pp, with_hist=True, q_out=qq)
-        bh_on(pp, qq)
-
-    def step():
-        step_on(shard, p, q)
+    wl = WORKLOADS[wl_name]
+    share_of = None
+    if wl_name == "cfg5" and world < 8:
+        share_of = 8                                     # one GPU cannot hold the genome at 1 kb: `world` of 8 pieces
+    W = Workload(wl, world, rank, dev, share_of=share_of)
+    gp = GenomePass(W.eng, q_values=True)
+    gp.attach(W.shards)
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    two_pass = wl["two_pass"]
+    if two_pass:
+        # config 4: pass 1 -> statistics without the outliers -> refit -> every record scored again (engine.run_second_pass)
+        eng, sh = W.eng, W.shards[0]
+        P = sh.n
+        p_first = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
+        p2 = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
+        q2 = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
+        p_outlier = 1.0 / float(W.possible_in_range)
+
+        def step():
+            eng.hist([sh]); eng.allreduce_stats(None); eng.fit()
+            eng.pvalues(sh, p_first, with_hist=False)
+            eng.hist_excluding([sh], [p_first], p_outlier); eng.allreduce_stats(None); eng.fit()
+            eng.p_hist.zero_()
+            eng.pvalues(sh, p2, with_hist=True, q_out=q2)
+            eng.qvalues(p2, q2, n_tests=-1, use_hist=True, prepared=True)
+    else:
+        def step():
+            gp.enqueue()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
-    fit = eng.read_fit()
-    eng.launches = 0
+    fit = gp.finish() if not two_pass else W.eng.read_fit()     # raises for a failed fit; settles the gather capacity
+    W.eng.launches = 0
     step()
-    launches_per_step = eng.launches + 1            # + the p_hist memset
+    launches_per_step = W.eng.launches
     barrier()
 
-    # ---- timed region: exactly K steps, device events, max over ranks
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if (rank == 0 and full) else None
+    if sampler:
+        time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if sampler:
@@ -296,117 +387,230 @@ def run_ours(args, out_fd):
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    clocks = sampler.stop() if sampler else None
-    ms_per_step = ms / args.steps
-    value = world * P / (ms_per_step * 1e-3)
+    ms_per_step = float(tms.item()) / args.steps
+    out["clocks"] = sampler.stop() if sampler else None
+    out["ms_per_step"] = ms_per_step
+    out["P_total"], out["P_local"] = W.P_total, W.P_local
+    out["value"] = W.P_total / (ms_per_step * 1e-3)
+    peak, peak_src = _peaks()
+    bpp = 104 if two_pass else BYTES_PER_PAIR
+    out["whole_pass_frac"] = bpp * W.P_total / (ms_per_step * 1e-3) / 1e9 / (peak * world)
+    out["launches_per_step"] = launches_per_step
+    out["workload_name"] = wl["name"] + (" (%d of 8 pieces: a single-GPU stand-in for the 8-GPU box)" % world if share_of else "")
+    out["W"], out["gp"], out["fit"] = W, gp, fit
+    if not full or two_pass:
+        if two_pass:
+            out["stages_ms"] = None
+        return
 
-    # ---- per-stage device times (separate instrumented steps; same stream, CUDA events)
-    names = ["hist", "allreduce", "fit", "pvalues", "bh"]
+    # ---- per-stage device times (separate instrumented steps; CUDA events on the streams the kernels run on)
+    names = ["hist", "allreduce", "fit", "classify_wait", "guard", "pvalues", "bh"]
     acc = dict((n, 0.0) for n in names)
+    acc["classify_side_stream"] = 0.0
     reps = min(args.steps, 5)
     for _ in range(reps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        ev[0].record(); eng.hist([shard])
-        ev[1].record(); eng.allreduce_stats(group)
-        ev[2].record(); eng.fit()
-        ev[3].record(); eng.p_hist.zero_(); eng.pvalues(shard, p, with_hist=True, q_out=q)
-        ev[4].record(); bh()
-        ev[5].record()
+        marks = {}
+        gp.enqueue(marks=marks)
         torch.cuda.synchronize()
-        for i, n in enumerate(names):
-            acc[n] += ev[i].elapsed_time(ev[i + 1]) / reps
-    fit_diag = eng.read_fit()          # phase cycles of the last instrumented fit (before the e2e section)
-    peak, peak_src = _peaks()
-    k4_gbs = K4_BYTES_PER_PAIR * P / (acc["pvalues"] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one K4 launch on this exact workload, from the ncu --set full
-    # capture summarised in profiles/r01_ncu_full_final.txt (1.1738 GB read + 1.5203 GB written: with the K4 -> K5
-    # hand-over K4 also writes the 8 B/pair of q that the SURVEY's byte table books under K5)
-    k4_traffic = 2.6941e9 if (nb == CHR1_BINS and not two_pass) else None
-    roofline = {"bound": "hbm", "kernel": "pvalues_kernel (K4)", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
-                "frac": k4_gbs / peak, "traffic": k4_traffic, "peak_source": peak_src,
-                "traffic_note": "K4's DRAM bytes include the 8 B/pair of q it writes for K5 (hand-over); its own algorithmic bytes are 20 B/pair, read once and written once",
-                "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * P,
-                "whole_pass_frac": (104 if two_pass else BYTES_PER_PAIR) * P / (ms_per_step * 1e-3) / 1e9 / peak,
-                "stage_gbs": {"hist": 12 * P / (acc["hist"] * 1e-3) / 1e9, "pvalues": k4_gbs,
-                              "bh": 16 * P / (acc["bh"] * 1e-3) / 1e9}}
+        prev = "start"
+        for n in names:
+            if n in marks:
+                acc[n] += marks[prev].elapsed_time(marks[n]) / reps
+                prev = n
+        if "classify_start" in marks:
+            acc["classify_side_stream"] += marks["classify_start"].elapsed_time(marks["classify_end"]) / reps
+    # the K4 kernels alone, back to back on one stream (what the roofline object is computed from)
+    k4a = k4b = 0.0
+    if gp.listed:
+        from blueberry_b200 import _lib
+        import ctypes
+        lib = W.eng.lib
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            st = _lib.stream_ptr()
+            _lib.check(lib.bbk_score_begin(_lib.ptr(gp.score_state), _lib.ptr(W.eng.p_hist), st), "bbk_score_begin")
+            ev[0].record()
+            gp._classify(False, st)
+            ev[1].record()
+            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), _lib.ptr(W.eng.fit_result), _lib.ptr(W.eng.spline_y), W.eng.R,
+                                              _lib.ptr(gp.p), _lib.ptr(gp.q), _lib.ptr(W.eng.p_hist), ctypes.byref(gp.cands),
+                                              _lib.ptr(gp.score_state), st), "bbk_pvalues_listed")
+            ev[2].record()
+            torch.cuda.synchronize()
+            k4a += ev[0].elapsed_time(ev[1]) / reps
+            k4b += ev[1].elapsed_time(ev[2]) / reps
+        gp.enqueue()                                     # leave a complete pass behind (q-values included)
+        torch.cuda.synchronize()
+    score = _score_state(gp)
+    out["stages_ms"] = acc
+    out["k4_alone_ms"] = {"classify_kernel": k4a, "listed_kernel": k4b}
+    out["work_list"] = {"count_eq_1": int(score.n_front), "other": int(score.n_back), "rows_finished_by_classify": int(score.n_ones + score.n_nan),
+                        "candidates_p_lt_2^-5": int(score.n_cand), "exact_mode": int(score.exact)}
+    tmax = torch.tensor([k4a + k4b, acc["hist"], acc["bh"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    k4_ms = float(tmax[0].item())
+    k4_gbs = K4_BYTES_PER_PAIR * W.P_total / world / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+    out["roofline"] = {
+        "bound": "hbm", "kernel": "K4 = classify_kernel + listed_kernel (per GPU, timed back to back on one stream)",
+        "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak,
+        "traffic": _k4_traffic(wl_name, world), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * W.P_total // world,
+        "traffic_note": "classify also writes the 8 B/pair of q that the byte table books under K5, and the 20-byte work-list entries "
+                        "listed_kernel reads back; traffic is null unless profiles/k4_traffic.json holds a capture of these sources",
+        "whole_pass_frac": out["whole_pass_frac"],
+        "stage_gbs_per_gpu": {"hist": 12 * W.P_local / (acc["hist"] * 1e-3) / 1e9 if acc["hist"] > 0 else None,
+                              "classify (12 B in + 16 B of p, q out)": 28 * W.P_local / (k4a * 1e-3) / 1e9 if k4a > 0 else None},
+    }
+    out["parity"] = _parity_bits(W, gp, fit, dev, world)
 
-    # ---- end to end: host (pinned) buffers in, p and q back to the host, every step, through engine.HostPipeline
-    # (the public streamed call: two device slots, so step k+1's records arrive while step k's p/q leave)
-    h_in = [torch.empty(P, dtype=torch.int32).pin_memory() for _ in range(3)]
-    for h, d in zip(h_in, (mid1, mid2, count)):
+    # ---- end to end (1): host (pinned) tables in, p and q back to the host, every step, through distributed.HostStream
+    h_in = [torch.empty(W.rows, dtype=torch.int32).pin_memory() for _ in range(3)]
+    for h, d in zip(h_in, (W.mid1, W.mid2, W.count)):
         h.copy_(d)
-    h_out = [(torch.empty(P, dtype=torch.float64).pin_memory(), torch.empty(P, dtype=torch.float64).pin_memory()) for _ in range(2)]
+    h_out = [(torch.empty(W.rows, dtype=torch.float64).pin_memory(), torch.empty(W.rows, dtype=torch.float64).pin_memory()) for _ in range(2)]
     torch.cuda.synchronize()
-    pipe, e2e_mode = HostPipeline(eng, P, chrom=rank, slots=2), "pipelined across steps (2 device slots)"
-
-    def e2e_step(k):
-        h_p, h_q = h_out[k % 2]
-        pipe.submit(h_in[0], h_in[1], h_in[2], h_p, h_q, run=step_on)
-
-    def e2e_drain():
-        if pipe is not None:
-            pipe.drain()
-        torch.cuda.synchronize()
-
-    e2e_steps = max(2, min(args.steps, 10 if P < 200_000_000 else 3))     # the first inbound copy has nothing to overlap with: more steps amortise it
-    e2e_step(0)
-    e2e_step(1)
-    e2e_drain()
+    W.mid1 = W.mid2 = W.count = None                     # the stream's device slots take their place (memory)
+    W.shards = []
+    gp.shards, gp.p, gp.q = [], None, None
+    torch.cuda.empty_cache()
+    pipe = HostStream(gp, W.sizes, W.chroms, slots=2)
+    e2e_steps = max(2, min(args.steps, 10 if W.P_local < 200_000_000 else 3))
+    for k in range(2):
+        pipe.submit(h_in[0], h_in[1], h_in[2], h_out[k % 2][0], h_out[k % 2][1])
+    pipe.drain(); torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        e2e_step(k)
-    e2e_drain()
-    # what a caller does with a pass whose outputs have arrived (here: the two the pipeline still holds): the fit status
-    # (raises the reference's exception for a failed fit) and whether the reference's own s = min(y)**2 would have differed
-    # from the kernel's (then that pass is submitted again with that s)
-    e2e_resubmit = 0
+        pipe.submit(h_in[0], h_in[1], h_in[2], h_out[k % 2][0], h_out[k % 2][1])
+    pipe.drain(); torch.cuda.synchronize()
+    resub = 0
     for k in range(pipe.submitted - 2, pipe.submitted):
         if PassEngine.reference_smoothing(pipe.fit_of(k)) is not None:
-            e2e_resubmit += 1
-    wall = time.perf_counter() - t0       # host clock around enqueue + drain: the copies run on three streams
+            resub += 1
+    wall = time.perf_counter() - t0
     barrier()
     tms = torch.tensor([wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_value = world * P / (float(tms.item()) / e2e_steps * 1e-3)
+    e2e_ms = float(tms.item()) / e2e_steps
     h_p, h_q = h_out[(e2e_steps - 1) % 2]
-    kept = int((h_p <= 1).sum().item())
-    sig = int((h_q <= 0.01).sum().item())
+    out["emitted_rows_rank0"] = int((h_p <= 1).sum().item())
+    out["q_le_0.01_rank0"] = int((h_q <= 0.01).sum().item())
+    out["e2e"] = {"value": W.P_total / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 12 * W.rows * world,
+                  "d2h_bytes_per_step": (16 * W.rows + int(W.eng.fit_result.numel())) * world,
+                  "steps": e2e_steps, "ms_per_step": e2e_ms,
+                  "mode": "distributed.HostStream: pinned host tables in, dense p and q back, pipelined across steps (2 device slots)",
+                  "fit_checked_passes": 2, "smoothing_resubmits": resub}
+    del pipe, h_in, h_out
+
+    # ---- end to end (2): the drop-in array call users make, FitHiC.fit_transform_arrays (numpy in, numpy out), on chr1 of
+    # the same genome (one process; rank 0 only) - staging, the pass, and the copy back of p / q and all the tables
+    if rank == 0 and not args.no_dropin:
+        from blueberry_b200.fithic import FitHiC
+        c0 = 0
+        nb, K, R = W.bins[c0], W.K, W.R
+        from blueberry_b200 import _lib
+        lib = W.eng.lib
+        n = int(lib.bbk_synth_n_pairs(nb, K))
+        n = min(n, 100_000_000)
+        cols = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3)]
+        bdev = torch.from_numpy(W.bias_host[c0]).to(dev)
+        _lib.check(lib.bbk_synth_contacts_range(nb, K, R, wl["depth"], DECAY, SEED + 1000003 * c0, _lib.ptr(bdev), 0, n,
+                                                _lib.ptr(cols[0]), _lib.ptr(cols[1]), _lib.ptr(cols[2]), _lib.stream_ptr()), "synth")
+        m1, m2, cn = (c.cpu().numpy() for c in cols)
+        del cols
+        fm = (np.arange(nb, dtype=np.int64) * R + R // 2)
+        fc = np.zeros(nb, dtype=np.int32)
+        model = FitHiC("bench", R, n_bins=N_BINS, max_dist=W.max_dist)
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = model.fit_transform_arrays(None, m1, None, m2, cn, fc, fm, bias=(fc, fm, W.bias_host[c0]), q_values=True)
+            times.append(time.perf_counter() - t0)
+        best = min(times[1:])
+        out["e2e_dropin"] = {"call": "FitHiC.fit_transform_arrays(numpy columns) -> numpy p, q", "workload": "chr1 of the same genome",
+                             "pairs": n, "ms_per_call": 1e3 * best, "value": n / best, "unit": "pairs/s", "n_gpus": 1,
+                             "h2d_bytes": 12 * n, "d2h_bytes": 16 * n, "kept_rows": int(res.keep.sum())}
+
+
+def _score_state(gp):
+    from blueberry_b200 import _lib
+    return _lib.ScoreState.from_buffer_copy(gp.score_state.cpu().numpy().tobytes())
+
+
+def run_ours(args, out_fd):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    main = {}
+    _measure(args, args.workload, world, rank, dev, True, main)
+    W, gp, fit = main.pop("W"), main.pop("gp"), main.pop("fit")
+    wl = WORKLOADS[args.workload]
+    totals = W.eng.totals.cpu().numpy()
+    n_knots = int(fit.n_knots)
+    fit_cycles = dict(zip(["stage+boundaries", "bin_stats", "spline_search", "grid_eval", "pava+residual", "total"],
+                          [int(v) for v in fit.phase_cycles]))
+    sizes_gb = 12 * W.P_local / 1e9
+    del W, gp
+    torch.cuda.empty_cache()
+
+    extra = {}
+    if world == 8 and args.workload == "cfg3" and not args.no_cfg5:
+        c5 = {}
+        _measure(args, "cfg5", world, rank, dev, False, c5)
+        extra = {"cfg5_ms_per_step": c5["ms_per_step"], "cfg5_frac": c5["whole_pass_frac"], "cfg5_pairs": c5["P_total"],
+                 "cfg5_pairs_per_sec": c5["value"],
+                 "cfg5_note": "BASELINE config 5 on the same 8 GPUs right after the headline workload: genome-wide 1 kb, 2 Mb cap, band-sharded; "
+                              "frac = 48 B x pairs / (time x 8 x peak); north_star target >= 0.60"}
+        c5.pop("W"); c5.pop("gp"); c5.pop("fit")
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, pairs, wall_c, _ = cpu_baseline(1, nb=4500)
+        v, pairs, wall_c, _ = cpu_baseline(1, wl, nb=4500)
         cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
                "sample": "one %d-bin block of the same workload (%.1fM records): histogram, binning, spline, bdtrc scoring, BH; "
                          "oracle/fithic_oracle.py on 1 of %d host cores, %.1f s" % (4500, pairs / 1e6, os.cpu_count() or 1, wall_c)}
 
     if rank == 0:
-        t = eng.totals.cpu().numpy()
         line = {
-            "metric": "fithic_contact_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("cfg4: chr1@1kb, all pairs within 2 Mb, two passes (refit after outlier removal)" if two_pass else
-                                    "cfg5 share: 1/8 of the genome at 1 kb per GPU, all pairs within 2 Mb, single pass with q-values" if args.workload == "cfg5" else
-                                    "cfg2: chr1@5kb, all pairs within 10 Mb, one chromosome-sized shard per GPU"),
-                       "pairs_per_gpu": P, "bins_per_gpu": nb, "resolution": R, "max_dist": MAX_DIST, "n_bins": N_BINS,
-                       "biases": True, "q_values": "genome-wide (histogram all-reduce + candidate all-gather)" if genome_q else "per shard", "l2": "inputs (%.2f GB/GPU) exceed the 126 MB L2" % (12 * P / 1e9),
-                       "bytes_per_pair": 104 if two_pass else BYTES_PER_PAIR, "S": int(t[0]), "spline_knots": int(fit.n_knots),
-                       "emitted_rows_rank0": kept, "q_le_0.01_rank0": sig},
-            "stages_ms": acc,
-            "fit_phase_cycles": dict(zip(["stage+boundaries", "bin_stats", "spline_search", "grid_eval", "pava+residual", "total"],
-                                         [int(v) for v in fit_diag.phase_cycles])),
-            "spline_diag": [int(v) for v in fit_diag.spline_diag],
-            "roofline": roofline,
+            "metric": "fithic_contact_pairs_per_sec", "value": main["value"], "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if args.workload != "cfg5" or world >= 8 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": main["workload_name"], "pairs_total": main["P_total"], "pairs_rank0": main["P_local"],
+                       "resolution": wl["R"], "max_dist": wl["max_dist"], "n_bins": N_BINS, "biases": True,
+                       "entry_point": "blueberry_b200.distributed.GenomePass" if not wl["two_pass"] else "blueberry_b200.engine.PassEngine (two passes)",
+                       "sharding": "distributed.plan_shards: equal record counts, whole chromosomes, row blocks where a chromosome straddles a cut",
+                       "q_values": "genome-wide (histogram all-reduce + fixed-capacity candidate all-gather, no host round trip)" if world > 1 else "genome-wide (one rank)",
+                       "l2": "inputs (%.2f GB on rank 0) exceed the 126 MB L2" % sizes_gb,
+                       "bytes_per_pair": 104 if wl["two_pass"] else BYTES_PER_PAIR, "S": int(totals[0]), "spline_knots": n_knots,
+                       "emitted_rows_rank0": main.get("emitted_rows_rank0"), "q_le_0.01_rank0": main.get("q_le_0.01_rank0")},
+            "stages_ms": main.get("stages_ms"),
+            "k4_alone_ms": main.get("k4_alone_ms"),
+            "work_list": main.get("work_list"),
+            "fit_phase_cycles": fit_cycles,
+            "roofline": main.get("roofline") or {"bound": "hbm", "whole_pass_frac": main["whole_pass_frac"]},
+            "whole_pass_frac": main["whole_pass_frac"],
+            "parity": main.get("parity"),
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 12 * P, "d2h_bytes_per_step": 16 * P + int(eng.fit_result.numel()),
-                    "steps": e2e_steps, "ms_per_step": float(tms.item()) / e2e_steps, "mode": e2e_mode,
-                    "fit_checked_passes": 2, "smoothing_resubmits": e2e_resubmit},
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks,
+            "e2e": main.get("e2e"),
+            "e2e_dropin": main.get("e2e_dropin"),
+            "gpu_launches": main["launches_per_step"] * args.steps,
+            "clocks": main.get("clocks"),
         }
+        line.update(extra)
         _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
@@ -431,12 +635,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bins", type=int, default=CHR1_BINS, help="bins of the per-GPU chromosome (default chr1 @ 5 kb)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
-                    help="cfg2 (default, the measured config), cfg4 (chr1 at 1 kb, two passes) or cfg5 (one GPU's share of the genome at 1 kb)")
-    ap.add_argument("--q-scope", default="genome", choices=["genome", "shard"],
-                    help="N > 1: rank p-values across all ranks (default) or per shard")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the fit_transform_arrays end-to-end leg")
+    ap.add_argument("--no-cfg5", action="store_true", help="--gpus 8: skip the extra BASELINE config 5 measurement")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
+                    help="cfg3 (default: the configuration the metric is quoted on), cfg2, cfg4 (two passes) or cfg5")
     args = ap.parse_args()
     out_fd = _claim_stdout()
     if args.impl == "reference":

@@ -42,6 +42,21 @@ class BiasTable(ctypes.Structure):
                 ("n_chrom", ctypes.c_int32)]
 
 
+class ScoreState(ctypes.Structure):
+    _fields_ = [("n_front", ctypes.c_uint64), ("n_back", ctypes.c_uint64), ("n_ones", ctypes.c_uint64), ("n_nan", ctypes.c_uint64),
+                ("n_cand", ctypes.c_uint64), ("overflow", ctypes.c_int32), ("cand_overflow", ctypes.c_int32),
+                ("exact", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class WorkList(ctypes.Structure):
+    _fields_ = [("d_row", ctypes.c_void_p), ("d_count", ctypes.c_void_p), ("d_dist", ctypes.c_void_p),
+                ("d_bias_product", ctypes.c_void_p), ("capacity", ctypes.c_int64)]
+
+
+class Candidates(ctypes.Structure):
+    _fields_ = [("d_keys", ctypes.c_void_p), ("d_rows", ctypes.c_void_p), ("capacity", ctypes.c_int64)]
+
+
 _vp, _i32, _i64, _f64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_size_t
 
 # name -> (restype, argtypes); exactly the prototypes of include/bbk.h
@@ -76,6 +91,19 @@ SIGNATURES = {
     "bbk_bh_fix_ones": (ctypes.c_int, [_vp, _i64, _f64, _vp, _vp]),
     "bbk_bh_fix_ones_dev": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "bbk_count_band": (ctypes.c_int, [_vp, _i64, _f64, _f64, _vp, _vp]),
+    "bbk_stats_pack": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "bbk_stats_unpack": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
+    "bbk_score_begin": (ctypes.c_int, [_vp, _vp, _vp]),
+    "bbk_classify_pairs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, ctypes.POINTER(BiasTable), _i64,
+                                          _vp, _vp, ctypes.POINTER(WorkList), _vp, _i32, _vp]),
+    "bbk_score_guard": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "bbk_pvalues_listed": (ctypes.c_int, [ctypes.POINTER(WorkList), _vp, _vp, _i64, _vp, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp]),
+    "bbk_bh_qvalues_listed": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp, _sz, _vp]),
+    "bbk_bh_select_listed": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "bbk_bh_gathered_workspace_bytes": (_sz, [_i32, _i64]),
+    "bbk_bh_pack_count": (ctypes.c_int, [_vp, _vp, _vp]),
+    "bbk_bh_rank_gathered_padded": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bbk_synth_contacts_range": (ctypes.c_int, [_i64, _i64, _i64, _f64, _f64, ctypes.c_uint64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bbk_synth_n_pairs": (_i64, [_i64, _i64]),
     "bbk_synth_contacts": (ctypes.c_int, [_i64, _i64, _i64, _f64, _f64, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),
 }

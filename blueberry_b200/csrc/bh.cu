@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(BH_THREADS) bh_hist_kernel(const double* p, lo
 }
 
 // one CTA of 1024 threads (4 buckets each): totals, N, and the saturation bucket
-__global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const long long* phist, int prune, int prepared) {
+__global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const long long* phist, int prune, int prepared,
+                                                            const BbkScoreState* ss = nullptr) {
     __shared__ long long part[1024];
     __shared__ int first_bucket;
     const int t = threadIdx.x;
@@ -163,14 +164,15 @@ __global__ void __launch_bounds__(1024) bh_threshold_kernel(BhState* st, const l
         const unsigned long long tau = first_bucket < BBK_PHIST_BINS ? (((unsigned long long)first_bucket << 51) | 0x8000000000000000ull) : ~0ull;
         st->tau_key = tau;
         // prepared mode: K4's bit per record (p < BBK_SMALL_P) stands in for the pass over p when it covers every candidate
-        st->use_list = (prepared && tau <= bbk_key_of(BBK_SMALL_P)) ? 1 : 0;
+        // (a candidate list that overflowed is no list: the full pass over p takes over)
+        st->use_list = (prepared && tau <= bbk_key_of(BBK_SMALL_P) && !(ss && ss->cand_overflow)) ? 1 : 0;
     }
 }
 
 // the 16 B/pair pass: q = 1.0 for saturated / p == 1.0 rows, NaN for NaN rows, candidates appended
 __global__ void __launch_bounds__(BH_THREADS) bh_compact_kernel(const double* p, long long m, double* q, BhState* st,
                                                                 unsigned long long* keys, unsigned* idx, int keep_ones,
-                                                                long long* rank) {
+                                                                long long* rank, long long key_cap = -1) {
     if (st->use_list) return;                                // K4 pre-filled q and listed every candidate
     const unsigned long long tau = st->tau_key;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
@@ -192,8 +194,10 @@ __global__ void __launch_bounds__(BH_THREADS) bh_compact_kernel(const double* p,
             base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
             if (cand) {
                 unsigned long long pos = base + __popc(mask & ((1u << lane) - 1));
-                keys[pos] = k;
-                idx[pos] = (unsigned)i;
+                if (key_cap < 0 || (long long)pos < key_cap) {       // a fixed-capacity send block: the count still says how many there were
+                    keys[pos] = k;
+                    idx[pos] = (unsigned)i;
+                }
             }
         }
     }
@@ -248,6 +252,35 @@ __global__ void __launch_bounds__(BH_THREADS) bh_mask_filter_kernel(BhState* st,
             if (threadIdx.x == 0) s_cnt = 0;
         }
         __syncthreads();
+    }
+}
+
+// listed mode (bbk_pvalues_listed): the rows with p < BBK_SMALL_P are already a list of (key, row); keep those below tau
+__global__ void __launch_bounds__(BH_THREADS) bh_cand_filter_kernel(BhState* st, const BbkScoreState* ss, const unsigned long long* ckeys,
+                                                                    const unsigned* crows, unsigned long long* keys, unsigned* idx,
+                                                                    long long key_cap = -1) {
+    if (!st->use_list) return;
+    const unsigned long long tau = st->tau_key;
+    const long long n = (long long)ss->n_cand;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_iter = (n + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    for (long long it = 0; it < n_iter; ++it, i += stride) {
+        unsigned long long k = 0;
+        bool cand = false;
+        if (i < n) { k = ckeys[i]; cand = k < tau; }
+        const unsigned mask = __ballot_sync(0xffffffffu, cand);
+        if (mask) {
+            const int leader = __ffs(mask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&st->n_cand, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cand) {
+                const unsigned long long pos = base + __popc(mask & ((1u << lane) - 1));
+                if (key_cap < 0 || (long long)pos < key_cap) { keys[pos] = k; idx[pos] = crows[i]; }
+            }
+        }
     }
 }
 
@@ -910,6 +943,44 @@ extern "C" int bbk_bh_qvalues_prepared(const double* d_p, int64_t m, int64_t n_t
 }
 
 
+// after bbk_pvalues_listed: q is pre-filled (1.0 / NaN) for every row and the rows with p < BBK_SMALL_P are listed in `cands`
+extern "C" int bbk_bh_qvalues_listed(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist, double* d_q,
+                                     const BbkCandidates* cands, const BbkScoreState* d_state, void* d_workspace,
+                                     size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(m >= 0 && m < (1ll << 32), "bbk_bh_qvalues_listed: m must be in [0, 2^32)");
+    if (m == 0) return BBK_OK;
+    BBK_REQUIRE(d_p && d_q && d_p_hist && d_workspace && cands && d_state, "bbk_bh_qvalues_listed: null pointer");
+    BBK_REQUIRE(cands->capacity >= 0 && (cands->capacity == 0 || (cands->d_keys && cands->d_rows)), "bbk_bh_qvalues_listed: incomplete candidate list");
+    BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_qvalues_listed: workspace must be 256-byte aligned");
+    const int G = sort_blocks();
+    BhLayout L;
+    size_t need = bh_layout(d_workspace, m, G, &L);
+    if (workspace_bytes < need) {
+        bbk_set_error("bbk_bh_qvalues_listed: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return BBK_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = bbk_num_sms();
+    bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist, n_tests);
+    BBK_CHECK_LAUNCH("bh_init_kernel");
+    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, 1, d_state);
+    BBK_CHECK_LAUNCH("bh_threshold_kernel");
+    if (cands->capacity > 0) {
+        bh_cand_filter_kernel<<<sms * 2, BH_THREADS, 0, st>>>(L.st, d_state, (const unsigned long long*)cands->d_keys, cands->d_rows, L.keys[0], L.idx[0]);
+        BBK_CHECK_LAUNCH("bh_cand_filter_kernel");
+    }
+    long long want = (m + BH_THREADS - 1) / BH_THREADS;
+    int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+    // saturation above BBK_SMALL_P, or an overflowed list: the 16 B/pair pass after all; otherwise returns at once
+    bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, L.keys[0], L.idx[0], 0, nullptr);
+    BBK_CHECK_LAUNCH("bh_compact_kernel");
+    int rc = launch_rank(L, d_q, nullptr, st);
+    if (rc != BBK_OK) return rc;
+    ones_fix_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st);
+    BBK_CHECK_LAUNCH("ones_fix_kernel");
+    return BBK_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Genome-wide q-values across ranks (collective 2), in three local steps around two
 // host-side collectives:
@@ -918,7 +989,8 @@ extern "C" int bbk_bh_qvalues_prepared(const double* d_p, int64_t m, int64_t n_t
 // ---------------------------------------------------------------------------------------------------
 static int bh_select_impl(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
                           uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace, size_t workspace_bytes,
-                          bool prepared, void* stream) {
+                          bool prepared, void* stream, const BbkCandidates* cands = nullptr, const BbkScoreState* d_score = nullptr,
+                          long long keys_cap = -1) {
     BBK_REQUIRE(m >= 0 && m < (1ll << 32), "bbk_bh_select: m must be in [0, 2^32)");
     BBK_REQUIRE(d_p_hist_global && d_state && d_workspace, "bbk_bh_select: null pointer");
     BBK_REQUIRE(m == 0 || (d_p && d_q && d_keys && d_idx), "bbk_bh_select: null array");
@@ -926,16 +998,22 @@ static int bh_select_impl(const double* d_p, int64_t m, int64_t n_tests, const i
     const int G = sort_blocks();
     BhLayout L;
     // prepared: the workspace is the one bbk_pvalues_bh left the flag bits in (laid out for m records)
-    size_t need = bh_layout(d_workspace, prepared ? m : 0, G, &L);
+    size_t need = bh_layout(d_workspace, (prepared && !cands) ? m : 0, G, &L);
     if (workspace_bytes < need) { bbk_set_error("bbk_bh_select: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return BBK_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = bbk_num_sms();
     bh_init_kernel<<<(BBK_PHIST_BINS + 2 + 255) / 256, 256, 0, st>>>(L.st, L.phist, (const long long*)d_p_hist_global, n_tests);
     BBK_CHECK_LAUNCH("bh_init_kernel");
-    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, prepared ? 1 : 0);
+    bh_threshold_kernel<<<1, 1024, 0, st>>>(L.st, L.phist, 1, prepared ? 1 : 0, d_score);
     BBK_CHECK_LAUNCH("bh_threshold_kernel");
     if (m > 0) {
-        if (prepared) {
+        if (cands) {
+            if (cands->capacity > 0) {
+                bh_cand_filter_kernel<<<sms * 2, BH_THREADS, 0, st>>>(L.st, d_score, (const unsigned long long*)cands->d_keys, cands->d_rows,
+                                                                      (unsigned long long*)d_keys, d_idx, keys_cap);
+                BBK_CHECK_LAUNCH("bh_cand_filter_kernel");
+            }
+        } else if (prepared) {
             long long words = ((m >> 2) + 31) / 32 * 4 + 1, wantw = (words + BH_THREADS - 1) / BH_THREADS;
             int gridw = (int)(wantw < (long long)sms * 8 ? wantw : (long long)sms * 8);
             bh_mask_filter_kernel<<<gridw, BH_THREADS, 0, st>>>(L.st, L.idx[1], d_p, m, (unsigned long long*)d_keys, d_idx);
@@ -943,7 +1021,7 @@ static int bh_select_impl(const double* d_p, int64_t m, int64_t n_tests, const i
         }
         long long want = (m + BH_THREADS - 1) / BH_THREADS;
         int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-        bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, (unsigned long long*)d_keys, d_idx, 0, nullptr);
+        bh_compact_kernel<<<grid, BH_THREADS, 0, st>>>(d_p, m, d_q, L.st, (unsigned long long*)d_keys, d_idx, 0, nullptr, keys_cap);
         BBK_CHECK_LAUNCH("bh_compact_kernel");
     }
     export_state_kernel<<<1, 1, 0, st>>>(L.st, (unsigned long long*)d_state);
@@ -961,6 +1039,16 @@ extern "C" int bbk_bh_select_prepared(const double* d_p, int64_t m, int64_t n_te
                                       uint64_t* d_keys, uint32_t* d_idx, uint64_t* d_state, void* d_workspace,
                                       size_t workspace_bytes, void* stream) {
     return bh_select_impl(d_p, m, n_tests, d_p_hist_global, d_q, d_keys, d_idx, d_state, d_workspace, workspace_bytes, true, stream);
+}
+
+/* bbk_bh_select after bbk_pvalues_listed (q pre-filled, candidates listed) */
+extern "C" int bbk_bh_select_listed(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                                    const BbkCandidates* cands, const BbkScoreState* d_score, uint64_t* d_keys, uint32_t* d_idx,
+                                    int64_t keys_capacity, uint64_t* d_state, void* d_workspace, size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(cands && d_score && keys_capacity >= 0, "bbk_bh_select_listed: null candidate list / score state");
+    BBK_REQUIRE(cands->capacity >= 0 && (cands->capacity == 0 || (cands->d_keys && cands->d_rows)), "bbk_bh_select_listed: incomplete candidate list");
+    return bh_select_impl(d_p, m, n_tests, d_p_hist_global, d_q, d_keys, d_idx, d_state, d_workspace, workspace_bytes, true, stream, cands, d_score,
+                          keys_capacity);
 }
 
 extern "C" int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, const uint64_t* d_state, double* d_q_all,
@@ -986,6 +1074,107 @@ extern "C" int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, c
     if (rc != BBK_OK) return rc;
     export_ones_kernel<<<1, 1, 0, st>>>(L.st, d_q_ones);
     BBK_CHECK_LAUNCH("export_ones_kernel");
+    return BBK_OK;
+}
+
+// ---- the same with the gather left on the device: no candidate count ever travels to the host -------------------------
+// Every rank sends a fixed-capacity block [count | keys[0 .. cap)] (d_keys of bbk_bh_select with its count in front); the
+// all-gather delivers `world` such blocks.  Here: prefix the counts, compact the blocks into one key array, rank it, and
+// scatter this rank's slice of the q-values back to its rows.  A count above cap sets *d_overflow (the host looks at it when
+// it reads the results and repeats the step with a larger capacity).
+namespace {
+
+__global__ void gathered_prepare_kernel(const unsigned long long* recv, int world, long long cap, const unsigned long long* state_in,
+                                        BhState* st, unsigned long long* offsets, int* overflow) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long run = 0;
+    int ov = 0;
+    for (int r = 0; r < world; ++r) {
+        unsigned long long c = recv[(size_t)r * (size_t)(cap + 1)];
+        if (c > (unsigned long long)cap) { ov = 1; c = (unsigned long long)cap; }
+        offsets[r] = run;
+        run += c;
+    }
+    offsets[world] = run;
+    if (ov) *overflow = 1;
+    st->n_cand = run; st->tau_key = state_in[1]; st->n_tests = (long long)state_in[2]; st->n_ones = state_in[3];
+    st->n_nan = 0; st->n_valid = 0; st->q_ones = 1.0; st->total_max = 0.0; st->need_ones_fix = 0;
+    for (int p = 0; p < NPASS; ++p) st->skip[p] = 0;
+    st->use_list = 0;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) gathered_compact_kernel(const unsigned long long* recv, int world, long long cap,
+                                                                      const unsigned long long* offsets, unsigned long long* keys, unsigned* idx) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int r = 0; r < world; ++r) {
+        const unsigned long long off = offsets[r], n = offsets[r + 1] - off;
+        const unsigned long long* src = recv + (size_t)r * (size_t)(cap + 1) + 1;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n; i += stride) {
+            keys[off + i] = src[i];
+            idx[off + i] = (unsigned)(off + i);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BH_THREADS) scatter_slice_kernel(const double* q_all, const unsigned long long* offsets, int rank,
+                                                                   const unsigned* idx_local, double* dst) {
+    const unsigned long long off = offsets[rank], n = offsets[rank + 1] - off;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n; i += stride) dst[idx_local[i]] = q_all[off + i];
+}
+
+__global__ void pack_count_kernel(const unsigned long long* state, unsigned long long* send) { send[0] = state[0]; }
+
+}  // namespace
+
+extern "C" size_t bbk_bh_gathered_workspace_bytes(int32_t world, int64_t cap) {
+    if (world <= 0 || cap < 0) return 0;
+    const long long n = (long long)world * cap;
+    return bh_layout(nullptr, n, sort_blocks(), nullptr) + align256(sizeof(double) * (size_t)(n + 1)) + align256(8 * (size_t)(world + 1)) + 512;
+}
+
+extern "C" int bbk_bh_pack_count(const uint64_t* d_state, uint64_t* d_send, void* stream) {
+    BBK_REQUIRE(d_state && d_send, "bbk_bh_pack_count: null pointer");
+    pack_count_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_state, (unsigned long long*)d_send);
+    BBK_CHECK_LAUNCH("pack_count_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_bh_rank_gathered_padded(const uint64_t* d_recv, int32_t world, int64_t cap, int32_t rank, const uint64_t* d_state,
+                                           const uint32_t* d_idx_local, double* d_q_dst, double* d_q_ones, int32_t* d_overflow,
+                                           void* d_workspace, size_t workspace_bytes, void* stream) {
+    BBK_REQUIRE(world > 0 && rank >= 0 && rank < world && cap >= 0, "bbk_bh_rank_gathered_padded: bad world / rank / capacity");
+    BBK_REQUIRE((long long)world * cap < (1ll << 32), "bbk_bh_rank_gathered_padded: world * cap must be below 2^32");
+    BBK_REQUIRE(d_recv && d_state && d_q_ones && d_overflow && d_workspace, "bbk_bh_rank_gathered_padded: null pointer");
+    BBK_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "bbk_bh_rank_gathered_padded: workspace must be 256-byte aligned");
+    const long long n_max = (long long)world * cap;
+    const int G = sort_blocks();
+    BhLayout L;
+    size_t used = bh_layout(d_workspace, n_max, G, &L);
+    double* q_all = (double*)((char*)d_workspace + used);
+    used += align256(sizeof(double) * (size_t)(n_max + 1));
+    unsigned long long* offsets = (unsigned long long*)((char*)d_workspace + used);
+    used += align256(8 * (size_t)(world + 1));
+    if (workspace_bytes < used) { bbk_set_error("bbk_bh_rank_gathered_padded: workspace too small (%zu < %zu bytes)", workspace_bytes, used); return BBK_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    gathered_prepare_kernel<<<1, 32, 0, st>>>((const unsigned long long*)d_recv, world, cap, (const unsigned long long*)d_state, L.st, offsets, d_overflow);
+    BBK_CHECK_LAUNCH("gathered_prepare_kernel");
+    if (n_max > 0) {
+        long long want = (cap + BH_THREADS - 1) / BH_THREADS;
+        int grid = (int)(want < (long long)bbk_num_sms() * 4 ? (want > 0 ? want : 1) : (long long)bbk_num_sms() * 4);
+        gathered_compact_kernel<<<grid, BH_THREADS, 0, st>>>((const unsigned long long*)d_recv, world, cap, offsets, L.keys[0], L.idx[0]);
+        BBK_CHECK_LAUNCH("gathered_compact_kernel");
+    }
+    int rc = launch_rank(L, q_all, nullptr, st);
+    if (rc != BBK_OK) return rc;
+    export_ones_kernel<<<1, 1, 0, st>>>(L.st, d_q_ones);
+    BBK_CHECK_LAUNCH("export_ones_kernel");
+    if (cap > 0 && d_idx_local && d_q_dst) {
+        long long want = (cap + BH_THREADS - 1) / BH_THREADS;
+        int grid = (int)(want < (long long)bbk_num_sms() * 4 ? want : (long long)bbk_num_sms() * 4);
+        scatter_slice_kernel<<<grid, BH_THREADS, 0, st>>>(q_all, offsets, rank, d_idx_local, d_q_dst);
+        BBK_CHECK_LAUNCH("scatter_slice_kernel");
+    }
     return BBK_OK;
 }
 

@@ -314,7 +314,34 @@ __global__ void hist_init_kernel(long long* obs, int nkeys, long long* totals) {
     if (i < 8) totals[i] = (i == 6) ? 500000000ll : 0ll;               // fithic.py:25-41
 }
 
+// one SUM all-reduce carries the whole of K1's output: min / max observed distance travel as one slot per rank
+__global__ void stats_pack_kernel(const long long* totals, long long* ext, int world, int rank) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < world) { ext[i] = i == rank ? totals[6] : 0; ext[world + i] = i == rank ? totals[7] : 0; }
+}
+__global__ void stats_unpack_kernel(long long* totals, const long long* ext, int world) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long lo = ext[0], hi = ext[world];
+    for (int r = 1; r < world; ++r) { lo = ext[r] < lo ? ext[r] : lo; hi = ext[world + r] > hi ? ext[world + r] : hi; }
+    totals[6] = lo;                                                    // fithic.py:258-259 over all ranks
+    totals[7] = hi;
+}
+
 }  // namespace
+
+extern "C" int bbk_stats_pack(const int64_t* d_totals, int64_t* d_ext, int32_t world, int32_t rank, void* stream) {
+    BBK_REQUIRE(d_totals && d_ext && world > 0 && rank >= 0 && rank < world, "bbk_stats_pack: bad arguments");
+    stats_pack_kernel<<<(world + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const long long*)d_totals, (long long*)d_ext, world, rank);
+    BBK_CHECK_LAUNCH("stats_pack_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_stats_unpack(int64_t* d_totals, const int64_t* d_ext, int32_t world, void* stream) {
+    BBK_REQUIRE(d_totals && d_ext && world > 0, "bbk_stats_unpack: bad arguments");
+    stats_unpack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long*)d_totals, (const long long*)d_ext, world);
+    BBK_CHECK_LAUNCH("stats_unpack_kernel");
+    return BBK_OK;
+}
 
 extern "C" int bbk_hist_init(int64_t* d_obs_sum, int32_t nkeys, int64_t* d_totals, void* stream) {
     BBK_REQUIRE(d_obs_sum && d_totals && nkeys >= 0, "bbk_hist_init: null table or negative nkeys");

@@ -34,12 +34,13 @@ __device__ int poisson_draw(double lam, unsigned long long& state) {
 
 __global__ void __launch_bounds__(256) synth_kernel(long long n_bins, long long K, long long R, double depth, double decay,
                                                     unsigned long long seed, const double* bias,
-                                                    int* mid1, int* mid2, int* count, long long n_pairs) {
+                                                    int* mid1, int* mid2, int* count, long long first, long long n_pairs) {
     // rows i < n_bins - K are full (K+1 records); the last K rows shrink by one each
     const long long full_rows = n_bins - K > 0 ? n_bins - K : 0;
     const long long full_pairs = full_rows * (K + 1);
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_pairs; r += stride) {
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_pairs; o += stride) {
+        const long long r = first + o;                  // record number inside the chromosome (the RNG counter)
         long long i, d;
         if (r < full_pairs) { i = r / (K + 1); d = r - i * (K + 1); }
         else {
@@ -58,9 +59,9 @@ __global__ void __launch_bounds__(256) synth_kernel(long long n_bins, long long 
         double lam = depth * pow((double)(d + 1), -decay);
         if (bias) lam *= bias[i] * bias[i + d];
         if (d >= 5 && u01(state = mix64(state)) < 1e-3) lam *= 5.0;
-        mid1[r] = (int)(i * R + R / 2);
-        mid2[r] = (int)((i + d) * R + R / 2);
-        count[r] = poisson_draw(lam, state);
+        mid1[o] = (int)(i * R + R / 2);
+        mid2[o] = (int)((i + d) * R + R / 2);
+        count[o] = poisson_draw(lam, state);
     }
 }
 
@@ -72,16 +73,26 @@ extern "C" int64_t bbk_synth_n_pairs(int64_t n_bins, int64_t K) {
     return (K + 1) * n_bins - K * (K + 1) / 2;
 }
 
-extern "C" int bbk_synth_contacts(int64_t n_bins, int64_t K, int64_t resolution, double depth, double decay, uint64_t seed,
-                                  const double* d_bias, int32_t* d_mid1, int32_t* d_mid2, int32_t* d_count, void* stream) {
+extern "C" int bbk_synth_contacts_range(int64_t n_bins, int64_t K, int64_t resolution, double depth, double decay, uint64_t seed,
+                                        const double* d_bias, int64_t first_record, int64_t n_records, int32_t* d_mid1,
+                                        int32_t* d_mid2, int32_t* d_count, void* stream) {
     BBK_REQUIRE(n_bins > 0 && K >= 0 && resolution > 0, "bbk_synth_contacts: bad shape");
-    BBK_REQUIRE(d_mid1 && d_mid2 && d_count, "bbk_synth_contacts: null output");
     BBK_REQUIRE((n_bins + 1) * resolution < (1ll << 31), "bbk_synth_contacts: coordinates overflow int32");
     if (K > n_bins - 1) K = n_bins - 1;
     long long n_pairs = bbk_synth_n_pairs(n_bins, K);
+    BBK_REQUIRE(first_record >= 0 && n_records >= 0 && first_record + n_records <= n_pairs, "bbk_synth_contacts: record range outside the chromosome");
+    if (n_records == 0) return BBK_OK;
+    BBK_REQUIRE(d_mid1 && d_mid2 && d_count, "bbk_synth_contacts: null output");
     int grid = bbk_num_sms() * 8;
     synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_bins, K, resolution, depth, decay, seed, d_bias,
-                                                          d_mid1, d_mid2, d_count, n_pairs);
+                                                          d_mid1, d_mid2, d_count, first_record, n_records);
     BBK_CHECK_LAUNCH("synth_kernel");
     return BBK_OK;
+}
+
+extern "C" int bbk_synth_contacts(int64_t n_bins, int64_t K, int64_t resolution, double depth, double decay, uint64_t seed,
+                                  const double* d_bias, int32_t* d_mid1, int32_t* d_mid2, int32_t* d_count, void* stream) {
+    BBK_REQUIRE(n_bins > 0 && K >= 0, "bbk_synth_contacts: bad shape");
+    return bbk_synth_contacts_range(n_bins, K, resolution, depth, decay, seed, d_bias, 0,
+                                    bbk_synth_n_pairs(n_bins, K > n_bins - 1 ? n_bins - 1 : K), d_mid1, d_mid2, d_count, stream);
 }

@@ -35,6 +35,9 @@ def reduce_distance_stats(obs_sum, totals, group=None):
     totals[7] = ext[1]
 
 
+MAX_WORLD = 64          # ranks the packed statistics buffer has min / max slots for
+
+
 class Shard(object):
     """Contact records of one shard (a chromosome or a diagonal band), as int32 CUDA tensors.
 
@@ -91,8 +94,11 @@ class PassEngine(object):
         self.max_bins = int(max_bins) if max_bins else max(4, min(self.nkeys, max(4 * self.n_bins, 512)))
         dev = self.device
         self.possible = torch.zeros(self.nkeys, dtype=torch.int64, device=dev)
-        self.obs_sum = torch.zeros(self.nkeys, dtype=torch.int64, device=dev)
-        self.totals = torch.zeros(8, dtype=torch.int64, device=dev)
+        # K1's whole output is ONE buffer [obs_sum | totals | 2 x MAX_WORLD slots for the min / max observed distance],
+        # so that one SUM all-reduce makes it genome-wide (bbk_stats_pack / bbk_stats_unpack)
+        self.stats = torch.zeros(self.nkeys + 8 + 2 * MAX_WORLD, dtype=torch.int64, device=dev)
+        self.obs_sum = self.stats[:self.nkeys]
+        self.totals = self.stats[self.nkeys:self.nkeys + 8]
         self.fit_result = torch.zeros(ctypes.sizeof(_lib.FitResult), dtype=torch.uint8, device=dev)
         self.x = torch.zeros(self.max_bins, dtype=torch.float64, device=dev)
         self.y = torch.zeros(self.max_bins, dtype=torch.float64, device=dev)
@@ -148,8 +154,23 @@ class PassEngine(object):
             self.launches += 1
 
     def allreduce_stats(self, group=None):
-        """Sum the distance table and totals over ranks (integers: order-free, bit-exact)."""
-        reduce_distance_stats(self.obs_sum, self.totals, group)
+        """Sum the distance table and totals over ranks (integers: order-free, bit-exact): one collective on the packed
+        buffer, the min / max observed distance travelling in per-rank slots (two one-warp kernels around it)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        if world > MAX_WORLD:
+            reduce_distance_stats(self.obs_sum, self.totals, group)
+            return
+        rank, st = dist.get_rank(group), _lib.stream_ptr()
+        ext = self.stats[self.nkeys + 8:]
+        _lib.check(self.lib.bbk_stats_pack(_lib.ptr(self.totals), _lib.ptr(ext), world, rank, st), "bbk_stats_pack")
+        dist.all_reduce(self.stats[:self.nkeys + 8 + 2 * world], op=dist.ReduceOp.SUM, group=group)
+        _lib.check(self.lib.bbk_stats_unpack(_lib.ptr(self.totals), _lib.ptr(ext), world, st), "bbk_stats_unpack")
+        self.launches += 2
 
     def fit(self, smoothing=None):
         """K2b + K3.  smoothing: the spline's s when the caller wants to give it (see reference_smoothing); by default the

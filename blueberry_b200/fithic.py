@@ -177,55 +177,147 @@ def _bias_tables(bias_dic, resolution, device, n_chrom_hint=0):
 class PassOutput(object):
     """Everything one pass produces, as numpy arrays / Python scalars."""
     __slots__ = ("p", "q", "keep", "x", "y", "spline_x", "spline_y", "spline_y_raw", "residual", "possible",
-                 "observed", "bin_of_key", "totals", "frag", "fit", "gpu_launches", "p_first")
+                 "observed", "bin_of_key", "totals", "frag", "fit", "gpu_launches", "p_first", "rows")
 
 
 def _pad16(n):
     return (n + 1) & ~1          # float64 slices must stay 16-byte aligned
 
 
+_STAGE_BYTES = 64 << 20
+_stage = {}
+
+
+def _staging(dev):
+    """Two pinned staging buffers per device (allocated once): chunk k+1 is converted / copied into one of them by the
+    host while the DMA of chunk k from the other is still running."""
+    key = str(dev)
+    if key not in _stage:
+        _stage[key] = ([torch.empty(_STAGE_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2)],
+                       [torch.cuda.Event() for _ in range(2)])
+    return _stage[key]
+
+
+def _to_device_i32(a, dev, lo=0, hi=None):
+    """Rows [lo, hi) of an integer column -> int32 CUDA tensor.  Pinned int32 torch tensors go by one asynchronous DMA;
+    numpy / pageable input is staged through pinned memory in chunks (conversion to int32 and the DMA overlap).  Values that
+    do not fit int32 raise OverflowError (checked per chunk, only for inputs wider than 32 bits)."""
+    if isinstance(a, torch.Tensor):
+        t = a[lo:hi]
+        if t.is_cuda:
+            return t.to(dev, dtype=torch.int32).contiguous()
+        if t.dtype == torch.int32 and t.is_pinned():
+            return t.to(dev, non_blocking=True)
+        a, lo, hi = t.numpy(), 0, None
+    a = np.asarray(a)
+    a = a[lo:hi]
+    if a.dtype.kind not in "iu":
+        a = a.astype(np.int64)
+    n = int(a.shape[0])
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
+    if n == 0:
+        return out
+    wide = a.dtype.itemsize > 4 or a.dtype == np.uint32
+    bufs, evs = _staging(dev)
+    per = _STAGE_BYTES // 4
+    stream = torch.cuda.current_stream(dev)
+    for k, start in enumerate(range(0, n, per)):
+        stop = min(n, start + per)
+        chunk = a[start:stop]
+        if wide and chunk.size and (chunk.min() < -2**31 or chunk.max() >= 2**31):
+            raise OverflowError("coordinates / counts must fit in int32 on the device")
+        buf, ev = bufs[k & 1], evs[k & 1]
+        if k >= 2:
+            ev.synchronize()                                   # the DMA that last read this buffer has finished
+        h = buf[:4 * (stop - start)].view(torch.int32)
+        np.copyto(h.numpy(), chunk, casting="unsafe")
+        out[start:stop].copy_(h, non_blocking=True)
+        ev.record(stream)
+    for ev in evs:
+        ev.synchronize()
+    return out
+
+
+def _rows_to_shards(chr1, mid1, chr2, mid2, count, lo, hi, dev, max_runs=64):
+    """Rows [lo, hi) of the record table as device shards.  Input sorted by chromosome (the usual case, and what the
+    authors' per-chromosome files are, datatypes.pyx:26) falls into a few runs of intra-chromosomal rows: each run is a
+    shard in the compact 12 B/pair layout, as a view (row order is kept, so p / q line up with the input).  Anything
+    else - inter-chromosomal rows, interleaved chromosomes - is one shard with chromosome columns."""
+    m1, m2, cn = (_to_device_i32(a, dev, lo, hi) for a in (mid1, mid2, count))
+    n = int(m1.numel())
+    if chr1 is None:
+        return [Shard(m1, m2, cn, chrom=0)]
+    c1 = np.asarray(chr1)[lo:hi]
+    c2 = np.asarray(chr2)[lo:hi]
+    if n == 0:
+        return [Shard(m1, m2, cn, chrom=0)]
+    if np.array_equal(c1, c2):
+        cuts = np.flatnonzero(c1[1:] != c1[:-1]) + 1
+        # a run must start on a 16-byte boundary to be a view: 4-record alignment of every cut
+        if len(cuts) < max_runs and not (cuts & 3).any():
+            bounds = [0] + cuts.tolist() + [n]
+            return [Shard(m1[a:b], m2[a:b], cn[a:b], chrom=int(c1[a])) for a, b in zip(bounds[:-1], bounds[1:])]
+        if len(cuts) == 0:
+            return [Shard(m1, m2, cn, chrom=int(c1[0]))]
+        if len(cuts) < max_runs:
+            # unaligned cuts: give every run its own (aligned) copy on the device
+            bounds = [0] + cuts.tolist() + [n]
+            return [Shard(m1[a:b].clone(), m2[a:b].clone(), cn[a:b].clone(), chrom=int(c1[a])) for a, b in zip(bounds[:-1], bounds[1:])]
+    return [Shard(m1, m2, cn, _to_device_i32(c1, dev), _to_device_i32(c2, dev))]
+
+
+def _to_host(t):
+    """Device tensor -> numpy through pinned memory (asynchronous; synchronise before reading)."""
+    h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    h.copy_(t, non_blocking=True)
+    return h
+
+
+def _in_range_possible(possible, resolution, min_dist, max_dist):
+    d = np.arange(len(possible), dtype=np.int64) * int(resolution)
+    ok = np.ones(len(possible), bool)
+    ok &= (d > min_dist) if min_dist > -1 else (np.full(len(possible), min_dist == -1))
+    ok &= (d <= max_dist) if max_dist > -1 else (np.full(len(possible), max_dist == -1))
+    return int(sum(int(v) for v in np.asarray(possible)[ok]))
+
+
 def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1, mid1, chr2, mid2, count,
-              bias_dic=None, want_q=False, n_tests=None, keep_device=False, refit=False):
+              bias_dic=None, want_q=False, n_tests=None, keep_device=False, refit=False, group=None):
+    from .distributed import GenomePass, _world, shard_rows
     dev = _device()
     info = _frag_info(frag_chrom, frag_mid, resolution)
     eng = PassEngine(resolution, n_bins, min_dist, max_dist, info.nkeys, dev)
     eng.set_fragments(info.n_frags, info.max_frag)
     if bias_dic:
         eng.set_bias(_bias_tables(bias_dic, resolution, dev))
-
-    def to_dev(a):
-        a = np.asarray(a)
-        if a.size and (a.min() < -2**31 or a.max() >= 2**31):
-            raise OverflowError("coordinates / counts must fit in int32 on the device")
-        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
-
-    same = chr1 is None or (np.asarray(chr1) == np.asarray(chr2)).all() and np.unique(np.asarray(chr1)).size <= 1
-    if same:
-        chrom = int(np.asarray(chr1).flat[0]) if chr1 is not None and len(chr1) else 0
-        shard = Shard(to_dev(mid1), to_dev(mid2), to_dev(count), chrom=chrom)
-    else:
-        shard = Shard(to_dev(mid1), to_dev(mid2), to_dev(count), to_dev(chr1), to_dev(chr2))
-    n = shard.n
-    p = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n]
-    q = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n] if want_q else None
+    group = False if group is None else (None if group is True else group)      # None: this GPU alone; True: the default group
+    world, rank = _world(group)
+    n_rows = int(len(mid1))
+    lo, hi = shard_rows(n_rows, world, rank)
     nt = -1 if n_tests is None else int(n_tests)
     first = None
-    # The kernel takes s = min(y) * min(y); the reference's `min(y)**2` is libm's pow, one ulp off for ~0.09 % of inputs.
-    # When the two differ (checked on the host once the pass is through) the pass is run again with the reference's s.
-    if not refit:
-        eng.run([shard], [p], [q] if want_q else None, n_tests=nt)
-        s_ref = eng.reference_smoothing(eng.read_fit())
-        if s_ref is not None:
-            eng.run([shard], [p], [q] if want_q else None, n_tests=nt, smoothing=s_ref)
-    else:
-        # pass 1 without q-values, then the refit on the non-outliers scores every record again
+    if refit:
+        if world > 1:
+            raise NotImplementedError("refit=True runs on one GPU")
+        same = chr1 is None or (np.asarray(chr1) == np.asarray(chr2)).all() and np.unique(np.asarray(chr1)).size <= 1
+        if same:
+            chrom = int(np.asarray(chr1).flat[0]) if chr1 is not None and len(chr1) else 0
+            shard = Shard(_to_device_i32(mid1, dev), _to_device_i32(mid2, dev), _to_device_i32(count, dev), chrom=chrom)
+        else:
+            shard = Shard(_to_device_i32(mid1, dev), _to_device_i32(mid2, dev), _to_device_i32(count, dev),
+                          _to_device_i32(chr1, dev), _to_device_i32(chr2, dev))
+        n = shard.n
+        p = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n]
+        q = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n] if want_q else None
+        # pass 1 without q-values, then the refit on the non-outliers scores every record again.  The kernel takes
+        # s = min(y) * min(y); the reference's `min(y)**2` is libm's pow, one ulp off for ~0.09 % of inputs: when the two
+        # differ (checked on the host once the pass is through) the pass is run again with the reference's s.
         eng.run([shard], [p], None)
         s_ref = eng.reference_smoothing(eng.read_fit())
         if s_ref is not None:
             eng.run([shard], [p], None, smoothing=s_ref)
             eng.read_fit()
-        possible_host = eng.possible.cpu().numpy()
-        in_rng = sum(int(v) for k, v in enumerate(possible_host) if in_range_check(k * int(resolution), min_dist, max_dist))
+        in_rng = _in_range_possible(eng.possible.cpu().numpy(), resolution, min_dist, max_dist)
         if in_rng <= 0:
             raise ZeroDivisionError("float division by zero (possibleIntraInRangeCount == 0)")
         first = p.clone()
@@ -233,24 +325,42 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
         s_ref = eng.reference_smoothing(eng.read_fit())
         if s_ref is not None:
             eng.run_second_pass([shard], [first], [p], 1.0 / in_rng, [q] if want_q else None, n_tests=nt, smoothing=s_ref)
-    fit = eng.read_fit()                                        # raises what the reference would raise
+        fit = eng.read_fit()                                    # raises what the reference would raise
+        p_rows, q_rows = p, q
+    else:
+        gp = GenomePass(eng, group=group, q_values=want_q)
+        shards = _rows_to_shards(chr1, mid1, chr2, mid2, count, lo, hi, dev)
+        gp.attach(shards)
+        fit = gp.run(n_tests=nt)                                # raises what the reference would raise
+        if len(shards) == 1:
+            p_rows, q_rows = gp.shard_p(0), (gp.shard_q(0) if want_q else None)
+        else:                                                   # drop the alignment padding between the runs
+            p_rows = torch.cat([gp.shard_p(i) for i in range(len(shards))])
+            q_rows = torch.cat([gp.shard_q(i) for i in range(len(shards))]) if want_q else None
 
     out = PassOutput()
     out.fit = fit
     out.frag = info
-    out.p = p.cpu().numpy()
-    out.q = q.cpu().numpy() if want_q else None
+    out.rows = (lo, hi)
+    host = {"p": _to_host(p_rows), "q": _to_host(q_rows) if want_q else None,
+            "x": _to_host(eng.x[:fit.n_out]), "y": _to_host(eng.y[:fit.n_out]),
+            "spline_y": _to_host(eng.spline_y[:fit.L]), "spline_raw": _to_host(eng.spline_raw[:fit.L]),
+            "possible": _to_host(eng.possible), "observed": _to_host(eng.obs_sum), "bin_of_key": _to_host(eng.bin_of_key),
+            "totals": _to_host(eng.totals), "first": _to_host(first) if first is not None else None}
+    torch.cuda.current_stream(dev).synchronize()
+    out.p = host["p"].numpy()
+    out.q = host["q"].numpy() if want_q else None
     out.keep = out.p <= 1                                       # fithic.py:434 (NaN = not scored or dropped)
-    out.x = eng.x[:fit.n_out].cpu().numpy()
-    out.y = eng.y[:fit.n_out].cpu().numpy()
+    out.x = host["x"].numpy()
+    out.y = host["y"].numpy()
     out.spline_x = (np.arange(fit.L, dtype=np.int64) + fit.k0) * int(resolution)
-    out.spline_y = eng.spline_y[:fit.L].cpu().numpy()
-    out.spline_y_raw = eng.spline_raw[:fit.L].cpu().numpy()
+    out.spline_y = host["spline_y"].numpy()
+    out.spline_y_raw = host["spline_raw"].numpy()
     out.residual = float(fit.residual)
-    out.possible = eng.possible.cpu().numpy()
-    out.observed = eng.obs_sum.cpu().numpy()
-    out.bin_of_key = eng.bin_of_key.cpu().numpy()
-    t = eng.totals.cpu().numpy()
+    out.possible = host["possible"].numpy()
+    out.observed = host["observed"].numpy()
+    out.bin_of_key = host["bin_of_key"].numpy()
+    t = host["totals"].numpy()
     out.totals = {
         "observedIntraInRangeSum": int(t[0]), "observedIntraInRangeCount": int(t[1]),
         "observedIntraAllSum": int(t[2]), "observedIntraAllCount": int(t[3]),
@@ -258,11 +368,10 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
         "minObservedGenomicDist": int(t[6]), "maxObservedGenomicDist": int(t[7]),
         "maxPossibleGenomicDist": info.max_possible,
         "possibleIntraAllCount": info.possible_intra_all, "possibleInterAllCount": info.possible_inter_all,
-        "possibleIntraInRangeCount": int(sum(int(v) for k, v in enumerate(out.possible)
-                                             if in_range_check(k * int(resolution), min_dist, max_dist))),
+        "possibleIntraInRangeCount": _in_range_possible(out.possible, resolution, min_dist, max_dist),
     }
     out.gpu_launches = eng.launches
-    out.p_first = first.cpu().numpy() if first is not None else None
+    out.p_first = host["first"].numpy() if first is not None else None
     return out
 
 
@@ -283,7 +392,7 @@ class FitHiC(object):
                interactions, fragments, biases, verbose)
 
     def fit_transform_arrays(self, chr1, mid1, chr2, mid2, count, frag_chrom, frag_mid, bias=None,
-                             q_values=False, n_tests=None, refit=False):
+                             q_values=False, n_tests=None, refit=False, group=None):
         """The same pass on in-memory records.
 
         chr1/chr2: integer chromosome ids per record (None: all records on one chromosome).
@@ -294,12 +403,16 @@ class FitHiC(object):
         (fithic.py:121-133); with refit=True the rows of pass 1 with p <= 1/possibleIntraInRangeCount are
         left out of the statistics, the bins and spline are refitted with the reference's own stage
         semantics and every record is scored again (p_first keeps the pass-1 values).
+        group: under torch.distributed (one process per GPU, every rank passing the SAME arrays) rank r scores rows
+        shard_rows(n, world, r) of the table - PassOutput.rows says which, p / q / keep cover those rows only; the
+        distance table, S, the bins and the spline are genome-wide (one all-reduce), and so are the q-values
+        (distributed.GenomePass).  group=True: the default process group; or any ProcessGroup; None = this GPU alone.
         """
         bias_dic = None
         if bias is not None:
             bias_dic = _bias_dict_from_arrays(*bias)
         return _run_pass(self.resolution, self.n_bins, self.min_dist, self.max_dist, frag_chrom, frag_mid,
-                         chr1, mid1, chr2, mid2, count, bias_dic, want_q=q_values, n_tests=n_tests, refit=refit)
+                         chr1, mid1, chr2, mid2, count, bias_dic, want_q=q_values, n_tests=n_tests, refit=refit, group=group)
 
 
 def _bias_dict_from_arrays(bias_chrom, bias_mid, bias_val):
@@ -410,7 +523,7 @@ def read_interactions(mainDic, infile, min_dist, max_dist, verbose):
     resolution = sorted(mainDic)[1] if len(mainDic) > 1 else 1
     dev = _device()
     eng = PassEngine(resolution, 100, min_dist, max_dist, len(mainDic), dev)
-    t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    t32 = lambda a: _to_device_i32(a, dev)                       # range-checked: OverflowError instead of a silent wrap
     eng.hist([Shard(t32(m1), t32(m2), t32(cnt), t32(c1), t32(c2))])
     obs = eng.obs_sum.cpu().numpy()
     t = eng.totals.cpu().numpy()
@@ -506,7 +619,7 @@ def fit_spline(mainDic, x, y, yerr, infilename, outfilename, biasDic, resolution
     if len(biasDic) > 0:
         ids = {chroms.ids[name]: sub for name, sub in biasDic.items() if name in chroms.ids}
         eng.set_bias(_bias_tables(ids, resolution, dev, n_chrom_hint=len(chroms.names)))
-    t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    t32 = lambda a: _to_device_i32(a, dev)
     shard = Shard(t32(m1), t32(m2), t32(cnt), t32(c1), t32(c2))
     p = torch.empty(_pad16(shard.n), dtype=torch.float64, device=dev)[:shard.n]
     eng.pvalues(shard, p)

@@ -68,6 +68,14 @@ int bbk_hist_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* 
                    const int32_t* d_count, int64_t n_pairs, int64_t resolution, int64_t min_dist,
                    int64_t max_dist, int32_t nkeys, int64_t* d_obs_sum, int64_t* d_totals, void* stream);
 
+/* Multi-GPU: one SUM all-reduce carries K1's whole output when the distance table, the totals and 2*world extra slots are
+ * one contiguous int64 buffer [obs_sum (nkeys) | totals (8) | ext (2*world)]: bbk_stats_pack puts this rank's min / max
+ * observed distance into its own slots of ext (zero elsewhere) before the all-reduce, bbk_stats_unpack folds the slots back
+ * into totals[6] / totals[7] after it (fithic.py:258-259 over all ranks).  Integer sums: the result is independent of the
+ * reduction order, so every rank holds bit-identical tables. */
+int bbk_stats_pack(const int64_t* d_totals, int64_t* d_ext, int32_t world, int32_t rank, void* stream);
+int bbk_stats_unpack(int64_t* d_totals, const int64_t* d_ext, int32_t world, void* stream);
+
 /* Second pass (BASELINE config 4): the same histogram over the records that are NOT first-pass outliers,
  * i.e. skipping record i when d_p[i] <= p_outlier (NaN never compares true: unscored rows stay in).  The
  * reference has no second pass (n_passes is ignored, fithic.py:121-133); the definition follows SURVEY.md
@@ -173,6 +181,62 @@ int bbk_pvalues_bh(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* 
                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K4 split around the fit                               replaces the same scoring loop, fithic.py:413-435
+ *
+ * Only the prior of a record needs the fit; its distance, the range test (:427), the bias product (:418-425, :431) and
+ * its count do not, and a record with count <= 0 needs no arithmetic at all (p = 1.0, or NaN when bdtrc rejects the
+ * prior).  bbk_classify_pairs therefore runs BEFORE / WHILE the one-CTA fit kernel runs (other stream): it streams the
+ * records once, writes p (and q = p) for every row it can finish - NaN for rows out of range, 1.0 / NaN for count <= 0 -
+ * and appends the others to a work list of (row, count, distance, bias1*bias2) entries, count == 1 from the front,
+ * the rest from the back.  bbk_score_guard (after the fit) checks what the count <= 0 rows assumed about the spline
+ * (0 < splineY, 16 * max(splineY) <= 1); if that fails it raises BbkScoreState.exact and the second
+ * bbk_classify_pairs(exact_only = 1) - always enqueued, returns at once otherwise - sends every in-range row to the list,
+ * so p is exact in every case.  bbk_pvalues_listed then scores the list: same arithmetic and edge semantics as
+ * bbk_pvalues, all lanes on the same branch.  It also fills d_p_hist (incl. the rows classify finished), stores q = 1.0 /
+ * NaN for its rows and appends (key, row) of every p < 2^-5 to `cands` for bbk_bh_qvalues_listed.
+ * Rows are positions in the rank-local p / q buffers: record i of this call is row out_base + i (out_base a multiple of 4,
+ * rows < 2^32), so several shards share one pair of buffers, one list and one q-value step.
+ * Needs 0 <= min_dist <= max_dist and max_dist + resolution < 2^31; otherwise use bbk_pvalues.
+ * A list with capacity >= the number of records cannot overflow; a smaller one sets BbkScoreState.overflow when it does
+ * (p of the lost rows stays NaN; the caller repeats the pass with a larger list).
+ * Sequence:  bbk_score_begin -> bbk_classify_pairs(..., 0) per shard  ||  K1, bbk_fit  ->  bbk_score_guard
+ *            -> bbk_classify_pairs(..., 1) per shard -> bbk_pvalues_listed -> [bbk_bh_qvalues_listed]
+ * ------------------------------------------------------------------------------------------- */
+typedef struct BbkScoreState {
+    uint64_t n_front;        /* work-list entries with count == 1 (positions 0 .. n_front-1) */
+    uint64_t n_back;         /* the other entries (positions capacity-1 down to capacity-n_back) */
+    uint64_t n_ones;         /* rows classify finished with p = 1.0 */
+    uint64_t n_nan;          /* rows classify finished with p = NaN */
+    uint64_t n_cand;         /* candidates appended by bbk_pvalues_listed */
+    int32_t overflow;        /* the work list was too small */
+    int32_t cand_overflow;   /* the candidate list was too small (the q-value step then takes its full pass: still exact) */
+    int32_t exact;           /* the guard failed: classification was repeated without the count <= 0 shortcut */
+    int32_t reserved;
+} BbkScoreState;
+typedef struct BbkWorkList {
+    uint32_t* d_row;
+    int32_t* d_count;
+    int32_t* d_dist;         /* mid2 - mid1 */
+    double* d_bias_product;  /* bias1 * bias2 (1.0 without biases) */
+    int64_t capacity;
+} BbkWorkList;
+typedef struct BbkCandidates {
+    uint64_t* d_keys;        /* order-preserving key of p */
+    uint32_t* d_rows;
+    int64_t capacity;
+} BbkCandidates;
+
+int bbk_score_begin(BbkScoreState* d_state, int64_t* d_p_hist, void* stream);     /* zeroes the state and the histogram */
+int bbk_classify_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
+                       const int32_t* d_count, int64_t n_pairs, int32_t shard_chrom, int64_t resolution, int64_t min_dist,
+                       int64_t max_dist, const BbkBiasTable* bias, int64_t out_base, double* d_p, double* d_q,
+                       const BbkWorkList* list, BbkScoreState* d_state, int32_t exact_only, void* stream);
+int bbk_score_guard(const BbkFitResult* d_fit, const double* d_spline_y, BbkScoreState* d_state, void* stream);
+int bbk_pvalues_listed(const BbkWorkList* list, const BbkFitResult* d_fit, const double* d_spline_y, int64_t resolution,
+                       double* d_p, double* d_q, int64_t* d_p_hist, const BbkCandidates* cands, BbkScoreState* d_state,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K5  Benjamini-Hochberg q-values as the reference computes them: a FORWARD running max of
  *     min(p * N / rank, 1)   (fithic.py:466-487, blueberry.pyx:40-75) - not the textbook reverse
  *     cumulative minimum.  q comes back in input order; NaN p (dropped rows) -> NaN q, not ranked.
@@ -224,6 +288,30 @@ int bbk_bh_fix_ones(const double* d_p, int64_t m, double q_ones, double* d_q, vo
 /* the same, decided on the device from d_q_ones[2] of bbk_bh_rank_gathered (no host round trip) */
 int bbk_bh_fix_ones_dev(const double* d_p, int64_t m, const double* d_q_ones, double* d_q, void* stream);
 
+/* listed mode: after bbk_pvalues_listed on the same d_p / d_p_hist / d_q, ranking from its candidate list */
+int bbk_bh_qvalues_listed(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist, double* d_q,
+                          const BbkCandidates* cands, const BbkScoreState* d_state, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+/* d_keys / d_idx hold keys_capacity entries (a fixed-capacity send block); candidates beyond it are counted in d_state[0] but
+ * not stored - bbk_bh_rank_gathered_padded then reports the overflow */
+int bbk_bh_select_listed(const double* d_p, int64_t m, int64_t n_tests, const int64_t* d_p_hist_global, double* d_q,
+                         const BbkCandidates* cands, const BbkScoreState* d_score, uint64_t* d_keys, uint32_t* d_idx,
+                         int64_t keys_capacity, uint64_t* d_state, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Genome-wide ranking with the gather left on the device (no candidate count ever reaches the host): every rank sends a
+ * fixed-capacity block [count | keys[0 .. cap)] - d_keys of bbk_bh_select* written at send + 1, the count put in front by
+ * bbk_bh_pack_count - and one all-gather delivers `world` such blocks (d_recv: world * (cap + 1) u64).
+ * bbk_bh_rank_gathered_padded prefixes the counts, compacts the blocks, ranks them (forward running max, as
+ * bbk_bh_rank_gathered) and scatters THIS rank's slice back: d_q_dst[d_idx_local[i]] = q of this rank's candidate i.
+ * A count above cap sets *d_overflow (int32, never cleared here); the host checks it when it reads the results and repeats
+ * the q-value step with a larger capacity.  d_q_ones[2] as bbk_bh_rank_gathered.  Workspace:
+ * bbk_bh_gathered_workspace_bytes(world, cap). */
+size_t bbk_bh_gathered_workspace_bytes(int32_t world, int64_t cap);
+int bbk_bh_pack_count(const uint64_t* d_state, uint64_t* d_send, void* stream);
+int bbk_bh_rank_gathered_padded(const uint64_t* d_recv, int32_t world, int64_t cap, int32_t rank, const uint64_t* d_state,
+                                const uint32_t* d_idx_local, double* d_q_dst, double* d_q_ones, int32_t* d_overflow,
+                                void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K6  count_band_regions                               replaces blueberry.pyx:77-91
  *     t = #{(i, j) : j < i, low <= regions[i] - regions[j] <= high}
@@ -271,6 +359,10 @@ int bbk_contact_band_normalize(const int32_t* d_bin1, const int32_t* d_bin2, con
 int64_t bbk_synth_n_pairs(int64_t n_bins, int64_t K);
 int bbk_synth_contacts(int64_t n_bins, int64_t K, int64_t resolution, double depth, double decay, uint64_t seed,
                        const double* d_bias, int32_t* d_mid1, int32_t* d_mid2, int32_t* d_count, void* stream);
+/* records first_record .. first_record + n_records - 1 of the same chromosome (a row block for one rank) */
+int bbk_synth_contacts_range(int64_t n_bins, int64_t K, int64_t resolution, double depth, double decay, uint64_t seed,
+                             const double* d_bias, int64_t first_record, int64_t n_records, int32_t* d_mid1, int32_t* d_mid2,
+                             int32_t* d_count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,329 @@
+"""GPU tests of the multi-shard / multi-GPU pass (blueberry_b200.distributed.GenomePass) and of the K4 split it runs
+(bbk_classify_pairs -> bbk_score_guard -> bbk_pvalues_listed -> bbk_bh_qvalues_listed):
+
+  * the split path against the direct kernel (bbk_pvalues + bbk_bh_qvalues) bit for bit - same arithmetic, so every p and
+    q must be IDENTICAL, whatever the shard sizes, tails, chromosome columns, biases, zero rows;
+  * the exact mode the guard falls back to (every in-range row through the list) and the guard's own decision;
+  * several shards on one GPU against the CPU oracle on the concatenated records (genome-wide S, spline and q);
+  * q end to end against BH over the REFERENCE's p (log10 tolerance; identical ranks outside declared near-ties);
+  * BASELINE config 2's shape on a 1e7-record sample against the oracle;
+  * N > 1 GPUs (skipped on a one-GPU box): tests/multi_gpu_check.py under torchrun for world 2, 4, 8.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import log10_close
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _engine(bins, R, min_dist, max_dist, bias, dev, n_bins=100):
+    from blueberry_b200.engine import BiasTables, PassEngine
+    nkeys = max(bins)
+    eng = PassEngine(R, n_bins, min_dist, max_dist, nkeys, dev)
+    eng.set_fragments(bins, [(b - 1) * R for b in bins])
+    if bias is not None:
+        tabs = [np.where((b < 0.5) | (b > 2), -1.0, b) for b in bias]
+        eng.set_bias(BiasTables(tabs, [R // 2] * len(bins), dev))
+    return eng
+
+
+def _t32(a, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+
+
+def _direct(eng, shards, dev, n_tests=-1):
+    """The direct kernels on the same shards: p per shard, q over the concatenation (one ranking)."""
+    import torch
+    from blueberry_b200 import _lib
+    from blueberry_b200.distributed import layout_rows
+    starts, rows = layout_rows([s.n for s in shards])
+    rows = max(rows, 4)
+    p = torch.full((rows,), float("nan"), dtype=torch.float64, device=dev)
+    q = torch.full((rows,), float("nan"), dtype=torch.float64, device=dev)
+    for s, a in zip(shards, starts):
+        if s.n:
+            eng.pvalues(s, p[a:a + s.n])
+    ws = torch.empty(int(eng.lib.bbk_bh_workspace_bytes(rows)), dtype=torch.uint8, device=dev)
+    _lib.check(eng.lib.bbk_bh_qvalues(_lib.ptr(p), rows, n_tests, _lib.BH_UNSORTED, None, _lib.ptr(q), None, _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()), "bbk_bh_qvalues")
+    torch.cuda.synchronize()
+    return p.cpu().numpy(), q.cpu().numpy(), starts
+
+
+def _same(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+def _random_shards(seed, dev, with_chr=False):
+    """Shards with awkward sizes (tails of 0..3 records, a one-record shard, an empty one), off-grid / negative / out-of-range
+    distances, zero and negative counts."""
+    import torch
+    from blueberry_b200 import synth
+    from blueberry_b200.engine import Shard
+    rng = np.random.default_rng(seed)
+    bins = [int(rng.integers(150, 500)) for _ in range(3)]
+    R = int(rng.choice([1000, 5000, 10000]))
+    max_dist = int(rng.choice([40, 90, 10 ** 5])) * R
+    min_dist = int(rng.choice([0, 0, 3 * R]))
+    with_bias = bool(rng.random() < 0.75)
+    bias = synth.make_bias(bins, seed, sigma=0.3) if with_bias else None
+    c = synth.make_contacts(bins, R, min(max_dist, max(bins) * R), float(rng.choice([2.0, 40.0, 600.0])), seed, bias, keep_zeros=bool(rng.random() < 0.7))
+    chrom, m1, m2, cn = c["chrom"].copy(), c["mid1"].copy(), c["mid2"].copy(), c["count"].copy()
+    n = len(cn)
+    k = rng.choice(n, max(n // 60, 1), replace=False); m2[k] += 333                    # off-grid
+    k = rng.choice(n, max(n // 90, 1), replace=False); m1[k], m2[k] = m2[k].copy(), m1[k].copy()   # negative distances
+    k = rng.choice(n, max(n // 200, 1), replace=False); cn[k] = -2                      # negative counts score like zeros
+    k = rng.choice(n, max(n // 300, 1), replace=False); cn[k] = 700                     # far above any mean
+    shards, parts = [], []
+    for ci in range(len(bins)):
+        sel = np.flatnonzero(chrom == ci)
+        cut = int(rng.integers(1, max(len(sel) - 1, 2)))
+        for piece in (sel[:cut], sel[cut:cut + 1], sel[cut + 1:]):                      # three pieces, one of them a single record
+            parts.append((ci, piece))
+    parts.insert(2, (0, np.zeros(0, dtype=np.int64)))                                   # an empty shard
+    for ci, piece in parts:
+        if with_chr:
+            c2 = np.full(len(piece), ci, dtype=np.int32)
+            if len(piece) > 10:
+                c2[rng.choice(len(piece), 3, replace=False)] = (ci + 1) % len(bins)      # inter-chromosomal rows
+            shards.append(Shard(_t32(m1[piece], dev), _t32(m2[piece], dev), _t32(cn[piece], dev),
+                                _t32(np.full(len(piece), ci), dev), _t32(c2, dev)))
+        else:
+            shards.append(Shard(_t32(m1[piece], dev), _t32(m2[piece], dev), _t32(cn[piece], dev), chrom=ci))
+    eng = _engine(bins, R, min_dist, max_dist, bias, dev, n_bins=int(rng.choice([30, 100])))
+    return eng, shards
+
+
+@pytest.mark.parametrize("seed,with_chr", [(s, False) for s in range(8)] + [(s, True) for s in range(8, 12)])
+def test_split_k4_is_bitwise_the_direct_kernel(seed, with_chr):
+    import torch
+    from blueberry_b200.distributed import GenomePass
+    dev = torch.device("cuda", 0)
+    eng, shards = _random_shards(seed, dev, with_chr)
+    gp = GenomePass(eng, group=False, q_values=True)
+    assert gp.listed
+    gp.attach(shards)
+    try:
+        gp.run()
+    except (ZeroDivisionError, ValueError):
+        pytest.skip("degenerate random case (the fit raises, as the reference would)")
+    p_new, q_new = gp.p.cpu().numpy(), gp.q.cpu().numpy()
+    score = gp.last_score
+    assert score.overflow == 0 and score.cand_overflow == 0
+    p_old, q_old, starts = _direct(eng, shards, dev)
+    assert gp.offsets == starts
+    assert _same(p_new[:gp.rows], p_old[:gp.rows]), "p differs between the split and the direct kernel"
+    assert _same(q_new[:gp.rows], q_old[:gp.rows]), "q differs between the listed and the full Benjamini-Hochberg step"
+    n_rows = sum(s.n for s in shards)
+    assert int(score.n_front + score.n_back + score.n_ones + score.n_nan) == n_rows      # every record went exactly one way
+
+
+@pytest.mark.parametrize("seed", [1, 5])
+def test_exact_mode_equals_speculative_mode(seed):
+    """What the guard falls back to: every in-range row through the list.  Forced here by raising BbkScoreState.exact by
+    hand after the speculative classification (the guard itself is tested below)."""
+    import torch
+    from blueberry_b200 import _lib
+    from blueberry_b200.distributed import GenomePass
+    dev = torch.device("cuda", 0)
+    eng, shards = _random_shards(seed, dev)
+    gp = GenomePass(eng, group=False, q_values=True)
+    gp.attach(shards)
+    gp.run()
+    p_spec, q_spec = gp.p.clone(), gp.q.clone()
+    lib, st = eng.lib, _lib.stream_ptr()
+    _lib.check(lib.bbk_score_begin(_lib.ptr(gp.score_state), _lib.ptr(eng.p_hist), st), "begin")
+    gp._classify(False, st)
+    forced = _lib.ScoreState()
+    forced.exact = 1
+    gp.score_state.copy_(torch.frombuffer(bytearray(bytes(forced)), dtype=torch.uint8))
+    gp.p.fill_(7.0); gp.q.fill_(7.0)
+    gp._classify(True, st)
+    _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), eng.R, _lib.ptr(gp.p),
+                                      _lib.ptr(gp.q), _lib.ptr(eng.p_hist), ctypes.byref(gp.cands), _lib.ptr(gp.score_state), st), "listed")
+    gp._qvalues(st)
+    torch.cuda.synchronize()
+    score = _lib.ScoreState.from_buffer_copy(gp.score_state.cpu().numpy().tobytes())
+    assert score.exact == 1 and score.n_ones == 0                                      # nothing was decided before the fit
+    rows = gp.rows
+    real = np.ones(rows, bool)
+    for s, a in zip(shards, gp.offsets):
+        real[a + s.n:a + ((s.n + 3) & ~3)] = False                                      # padding rows keep their fill value
+    assert _same(gp.p.cpu().numpy()[:rows][real], p_spec.cpu().numpy()[:rows][real])
+    assert _same(gp.q.cpu().numpy()[:rows][real], q_spec.cpu().numpy()[:rows][real])
+
+
+def test_guard_decision():
+    import torch
+    from blueberry_b200 import _lib
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+
+    def run(values, status=0):
+        fit = _lib.FitResult()
+        fit.status, fit.L = status, len(values)
+        d_fit = torch.frombuffer(bytearray(bytes(fit)), dtype=torch.uint8).to(dev)
+        sy = torch.tensor(values, dtype=torch.float64, device=dev)
+        state = torch.zeros(ctypes.sizeof(_lib.ScoreState), dtype=torch.uint8, device=dev)
+        _lib.check(lib.bbk_score_guard(_lib.ptr(d_fit), _lib.ptr(sy), _lib.ptr(state), _lib.stream_ptr()), "guard")
+        return _lib.ScoreState.from_buffer_copy(state.cpu().numpy().tobytes()).exact
+
+    assert run([1e-3, 1e-5, 1e-9]) == 0
+    assert run([0.0625] * 2000) == 0                   # 16 * max == 1: still inside [0, 1]
+    assert run([0.07, 1e-5]) == 1                      # a bias product of 16 could push the prior above 1
+    assert run([1e-3, 0.0]) == 1                       # prior 0 * negative bias = -0.0 is NOT rejected by bdtrc
+    assert run([1e-3, -1e-12]) == 1
+    assert run([1e-3, float("nan")]) == 1
+    assert run([0.5], status=-12) == 0                 # failed fit: nothing is scored, the host raises
+
+
+def test_several_shards_against_oracle_and_reference_q():
+    """Three chromosomes as five shards on one GPU, scored with ONE genome-wide table / S / spline, q ranked over all of them:
+    against the CPU oracle on the concatenated records.  q is also compared with BH over the ORACLE's p (the reference's
+    p): ranks identical outside near-ties, log10 q within the p tolerance."""
+    import torch
+    from blueberry_b200 import synth
+    from blueberry_b200.distributed import GenomePass
+    from blueberry_b200.engine import Shard
+    from oracle import fithic_oracle as fo
+    dev = torch.device("cuda", 0)
+    R, bins, max_dist = 10000, [420, 300, 180], 2_000_000
+    fc, fm = synth.make_fragments(bins, R)
+    bias = synth.make_bias(bins, 11)
+    c = synth.make_contacts(bins, R, max_dist, 150.0, 31, bias)
+    eng = _engine(bins, R, 0, max_dist, bias, dev)
+    cuts = [0, 30000, int((c["chrom"] == 0).sum()), int((c["chrom"] <= 1).sum()) - 17, int((c["chrom"] <= 1).sum()), len(c["count"])]
+    shards = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        shards.append(Shard(_t32(c["mid1"][a:b], dev), _t32(c["mid2"][a:b], dev), _t32(c["count"][a:b], dev), chrom=int(c["chrom"][a])))
+    gp = GenomePass(eng, group=False, q_values=True)
+    gp.attach(shards)
+    fit = gp.run()
+    p = np.concatenate([gp.shard_p(i).cpu().numpy() for i in range(len(shards))])
+    q = np.concatenate([gp.shard_q(i).cpu().numpy() for i in range(len(shards))])
+    bc = np.concatenate([np.full(b, i) for i, b in enumerate(bins)])
+    bd, _ = fo.read_bias_arrays(bc, fm, np.concatenate(bias))
+    ref = fo.fithic_arrays(fc, fm, c["chrom"], c["mid1"], c["chrom"], c["mid2"], c["count"], R, 100, 0, max_dist, bias=bd)
+    assert np.array_equal(eng.obs_sum.cpu().numpy(), ref.contacts.observed) and int(fit.S) == ref.contacts.S
+    assert np.array_equal(eng.spline_y[:fit.L].cpu().numpy(), ref.spline_y)
+    assert np.array_equal(p <= 1, ref.keep)
+    sel = ref.keep & (ref.p > 0)
+    ok, nbad = log10_close(p[sel], ref.p[sel], 1e-6)
+    assert ok, nbad
+    # q on the device's own p: bit-exact BH
+    keep = ref.keep
+    assert np.array_equal(q[keep], fo.benjamini_hochberg_correction(p[keep], int(keep.sum())))
+    # q against BH of the REFERENCE's p
+    q_ref = fo.benjamini_hochberg_correction(ref.p[keep], int(keep.sum()))
+    ok, nbad = log10_close(q[keep], q_ref, 1e-6)
+    assert ok, "%d q-values differ from BH(reference p) by more than 1e-6 in log10" % nbad
+    # ranks: 1 + number of strictly smaller p.  Declared near-ties: pairs of DISTINCT reference p-values closer than 1e-6 in log10
+    pr, pg = ref.p[keep], p[keep]
+    order = np.argsort(pr, kind="stable")
+    srt = pr[order]
+    with np.errstate(divide="ignore"):
+        gap = np.diff(np.log10(np.maximum(srt, 1e-320)))
+    near = np.zeros(len(srt), bool)
+    close = gap < 2e-6                                  # neighbours in the reference's order that the tolerance cannot separate
+    near[1:] |= close; near[:-1] |= close
+    rank_ref = np.searchsorted(srt, pr, side="left")
+    rank_gpu = np.searchsorted(np.sort(pg), pg, side="left")
+    tied_ref = np.zeros(len(pr), bool)
+    tied_ref[order] = near
+    bad = (rank_ref != rank_gpu) & ~tied_ref
+    # (rows inside a cluster may swap or merge; that never changes how many rows lie strictly below a row OUTSIDE it)
+    assert not bad.any(), "%d rows outside declared near-ties changed rank" % int(bad.sum())
+
+
+def test_config2_shape_sample_against_oracle():
+    """BASELINE config 2's shape (5 kb, 10 Mb cap, D = 2001, deep counts near the diagonal) on a 5000-bin chromosome =
+    8.0e6 records, against the oracle."""
+    import torch
+    from blueberry_b200 import synth
+    from blueberry_b200.distributed import GenomePass
+    from blueberry_b200.engine import Shard
+    from oracle import fithic_oracle as fo
+    dev = torch.device("cuda", 0)
+    R, bins, max_dist = 5000, [5000], 10_000_000
+    fc, fm = synth.make_fragments(bins, R)
+    bias = synth.make_bias(bins, 3)
+    c = synth.make_contacts(bins, R, max_dist, 600.0, 77, bias)
+    eng = _engine(bins, R, 0, max_dist, bias, dev)
+    sh = Shard(_t32(c["mid1"], dev), _t32(c["mid2"], dev), _t32(c["count"], dev), chrom=0)
+    gp = GenomePass(eng, group=False, q_values=True)
+    gp.attach([sh])
+    fit = gp.run()
+    p, q = gp.shard_p(0).cpu().numpy(), gp.shard_q(0).cpu().numpy()
+    bd, _ = fo.read_bias_arrays(np.zeros(bins[0], dtype=np.int64), fm, bias[0])
+    ref = fo.fithic_arrays(fc, fm, None, c["mid1"], None, c["mid2"], c["count"], R, 100, 0, max_dist, bias=bd)
+    assert np.array_equal(eng.obs_sum.cpu().numpy(), ref.contacts.observed) and int(fit.S) == ref.contacts.S
+    assert np.array_equal(eng.x[:fit.n_out].cpu().numpy(), np.array(ref.x)) and np.array_equal(eng.y[:fit.n_out].cpu().numpy(), np.array(ref.y))
+    assert np.array_equal(eng.spline_y[:fit.L].cpu().numpy(), ref.spline_y)
+    assert np.array_equal(p <= 1, ref.keep)
+    sel = ref.keep & (ref.p >= 1e-300)
+    ok, nbad = log10_close(p[sel], ref.p[sel], 1e-5)
+    assert ok, nbad
+    keep = ref.keep
+    assert np.array_equal(q[keep], fo.benjamini_hochberg_correction(p[keep], int(keep.sum())))
+    assert gp.last_score.exact == 0
+
+
+def test_list_overflow_is_detected_and_repaired():
+    import torch
+    from blueberry_b200.distributed import GenomePass
+    dev = torch.device("cuda", 0)
+    eng, shards = _random_shards(3, dev)
+    gp = GenomePass(eng, group=False, q_values=True)
+    gp.attach(shards, list_capacity=64, cand_capacity=8)            # far too small
+    gp.run()                                                        # finish() sees the flag and repeats with a full-size list
+    assert gp.last_score.overflow == 0
+    p_old, q_old, _ = _direct(eng, shards, dev)
+    assert _same(gp.p.cpu().numpy()[:gp.rows], p_old[:gp.rows])
+    assert _same(gp.q.cpu().numpy()[:gp.rows], q_old[:gp.rows])     # the candidate overflow falls back to the full pass: still exact
+
+
+def test_fit_transform_arrays_pinned_and_wide_inputs():
+    """The drop-in array call: pinned int32 torch columns, int64 numpy columns and a value beyond int32 (OverflowError)."""
+    import torch
+    from blueberry_b200 import synth
+    from blueberry_b200.fithic import FitHiC
+    R, bins, max_dist = 10000, [300, 200], 1_500_000
+    fc, fm = synth.make_fragments(bins, R)
+    c = synth.make_contacts(bins, R, max_dist, 80.0, 5)
+    model = FitHiC("x", R, max_dist=max_dist)
+    a = model.fit_transform_arrays(c["chrom"], c["mid1"], c["chrom"], c["mid2"], c["count"], fc, fm, q_values=True)
+    pin = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.int32)).pin_memory()
+    b = model.fit_transform_arrays(c["chrom"], pin(c["mid1"]), c["chrom"], pin(c["mid2"]), pin(c["count"]), fc, fm, q_values=True)
+    w = model.fit_transform_arrays(c["chrom"].astype(np.int64), c["mid1"].astype(np.int64), c["chrom"].astype(np.int64),
+                                   c["mid2"].astype(np.int64), c["count"].astype(np.int64), fc, fm, q_values=True)
+    for o in (b, w):
+        assert _same(a.p, o.p) and _same(a.q, o.q)
+    big = c["mid2"].astype(np.int64)
+    big[7] = 2 ** 31 + 5
+    with pytest.raises(OverflowError):
+        model.fit_transform_arrays(c["chrom"], c["mid1"], c["chrom"], big, c["count"], fc, fm)
+
+
+def _torchrun(world, script, timeout=900):
+    env = dict(os.environ)
+    env["MASTER_ADDR"] = "127.0.0.1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), os.path.join(ROOT, "tests", script)]
+    return subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, cwd=ROOT)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_pass_against_single_process_oracle(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    r = _torchrun(world, "multi_gpu_check.py")
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-4000:]

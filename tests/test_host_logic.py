@@ -85,3 +85,36 @@ def test_extract_contacts_from_map_follows_reference_steps():
     assert out.shape == (int(keep.sum()), 5)
     assert (out[:, 0] == 7).all()
     assert np.array_equal(out[:, 1:], tab[keep][:, :4])        # chromosome, mid1, mid2, contactCount, p (utils.py:85-86)
+
+
+def test_plan_shards_covers_every_record_once_and_balances():
+    """distributed.plan_shards on the hg19 genome at 5 kb (BASELINE config 3's shape): every record of every chromosome
+    lands on exactly one rank, pieces are contiguous inside a chromosome, loads are equal to 4 records, and at most
+    world-1 chromosomes are split."""
+    from blueberry_b200 import synth
+    from blueberry_b200.distributed import layout_rows, plan_shards, shard_rows
+    K = 2000
+    pairs = [synth.n_pairs_of(synth.n_bins_of(L, 5000), K) for L in synth.HG19_LENGTHS]
+    assert sum(pairs) == 1169126271                                     # SURVEY.md section 8: cfg3
+    for world in (1, 2, 4, 8):
+        plan = plan_shards(pairs, world)
+        loads = [sum(n for _, _, n in r) for r in plan]
+        assert sum(loads) == sum(pairs) and max(loads) - min(loads) <= 8
+        split = 0
+        for c, n in enumerate(pairs):
+            segs = sorted((f, k) for r in plan for (cc, f, k) in r if cc == c)
+            pos = 0
+            for f, k in segs:
+                assert f == pos
+                pos += k
+            assert pos == n
+            split += len(segs) > 1
+        assert split <= world - 1
+    lpt = plan_shards(pairs, 8, mode="lpt")
+    assert sorted(c for r in lpt for (c, _, _) in r) == list(range(23)) and all(f == 0 for r in lpt for (_, f, _) in r)
+    # arbitrary tables: contiguous row slices, 4-aligned cuts
+    for n in (0, 1, 7, 1000, 1003):
+        got = [shard_rows(n, 3, r) for r in range(3)]
+        assert got[0][0] == 0 and got[-1][1] == n and all(a[1] == b[0] for a, b in zip(got[:-1], got[1:]))
+        assert all(lo % 4 == 0 for lo, _ in got if lo < n)
+    assert layout_rows([5, 0, 8, 3]) == ([0, 8, 8, 16], 20)
