@@ -432,7 +432,7 @@ def _measure(args, wl_name, world, rank, dev, full, out):
             ev[0].record()
             gp._classify(False, st)
             ev[1].record()
-            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), _lib.ptr(W.eng.fit_result), _lib.ptr(W.eng.spline_y), W.eng.R,
+            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), gp.n_tiles, _lib.ptr(W.eng.fit_result), _lib.ptr(W.eng.spline_y), W.eng.R,
                                               _lib.ptr(gp.p), _lib.ptr(gp.q), _lib.ptr(W.eng.p_hist), ctypes.byref(gp.cands),
                                               _lib.ptr(gp.score_state), st), "bbk_pvalues_listed")
             ev[2].record()
@@ -443,8 +443,8 @@ def _measure(args, wl_name, world, rank, dev, full, out):
         torch.cuda.synchronize()
     score = _score_state(gp)
     out["stages_ms"] = acc
-    out["k4_alone_ms"] = {"classify_kernel": k4a, "listed_kernel": k4b}
-    out["work_list"] = {"count_eq_1": int(score.n_front), "other": int(score.n_back), "rows_finished_by_classify": int(score.n_ones + score.n_nan),
+    out["k4_alone_ms"] = {"classify_kernel": k4a, "scored_tiles_kernel": k4b}
+    out["work_list"] = {"count_eq_1": int(score.n_one), "count_2_to_8": int(score.n_small), "other": int(score.n_other), "rows_finished_by_classify": int(score.n_final),
                         "candidates_p_lt_2^-5": int(score.n_cand), "exact_mode": int(score.exact)}
     tmax = torch.tensor([k4a + k4b, acc["hist"], acc["bh"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -452,15 +452,16 @@ def _measure(args, wl_name, world, rank, dev, full, out):
     k4_ms = float(tmax[0].item())
     k4_gbs = K4_BYTES_PER_PAIR * W.P_total / world / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
     out["roofline"] = {
-        "bound": "hbm", "kernel": "K4 = classify_kernel + listed_kernel (per GPU, timed back to back on one stream)",
+        "bound": "hbm", "kernel": "K4 = classify_kernel + scored_tiles_kernel (per GPU, timed back to back on one stream)",
         "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak,
         "traffic": _k4_traffic(wl_name, world), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * W.P_total // world,
-        "traffic_note": "classify also writes the 8 B/pair of q that the byte table books under K5, and the 20-byte work-list entries "
-                        "listed_kernel reads back; traffic is null unless profiles/k4_traffic.json holds a capture of these sources",
+        "traffic_note": "K4 also writes the 8 B/pair of q that the byte table books under K5, and moves the 20-byte work-list entries "
+                        "(written by classify, read back by scored_tiles); traffic is null unless profiles/k4_traffic.json holds a capture of these sources",
         "whole_pass_frac": out["whole_pass_frac"],
         "stage_gbs_per_gpu": {"hist": 12 * W.P_local / (acc["hist"] * 1e-3) / 1e9 if acc["hist"] > 0 else None,
-                              "classify (12 B in + 16 B of p, q out)": 28 * W.P_local / (k4a * 1e-3) / 1e9 if k4a > 0 else None},
+                              "classify (12 B/pair in)": 12 * W.P_local / (k4a * 1e-3) / 1e9 if k4a > 0 else None,
+                              "scored_tiles (16 B/pair of p, q out)": 16 * W.P_local / (k4b * 1e-3) / 1e9 if k4b > 0 else None},
     }
     out["parity"] = _parity_bits(W, gp, fit, dev, world)
 

@@ -777,8 +777,10 @@ extern "C" int bbk_pvalues_bh(const int32_t* d_chr1, const int32_t* d_chr2, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4 split around the fit (pvalue_lists.inl): classification before / during the fit, dense work lists after it
+// K4 split around the fit (pvalue_lists.inl): classification before / during the fit, tiles scored from dense lists after it
 // ---------------------------------------------------------------------------------------------------
+extern "C" int64_t bbk_tiles_of(int64_t n_pairs) { return n_pairs <= 0 ? 0 : (n_pairs + BBK_TILE_ROWS - 1) / BBK_TILE_ROWS; }
+
 extern "C" int bbk_score_begin(BbkScoreState* d_state, int64_t* d_p_hist, void* stream) {
     BBK_REQUIRE(d_state, "bbk_score_begin: null state");
     score_begin_kernel<<<(BBK_PHIST_LEN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_state, (long long*)d_p_hist);
@@ -786,9 +788,18 @@ extern "C" int bbk_score_begin(BbkScoreState* d_state, int64_t* d_p_hist, void* 
     return BBK_OK;
 }
 
+static int check_worklist(const BbkWorkList* list, const char* who) {
+    if (!list || list->capacity < 0 || list->tile_capacity < 0) { bbk_set_error("invalid argument: %s: null work list / negative capacity", who); return BBK_E_INVALID; }
+    if (list->capacity > 0 && !(list->d_row && list->d_count && list->d_dist && list->d_bias_product)) {
+        bbk_set_error("invalid argument: %s: incomplete work list", who); return BBK_E_INVALID; }
+    if (list->tile_capacity > 0 && !(list->d_tiles && list->d_nan_bits)) { bbk_set_error("invalid argument: %s: null tile directory / bit map", who); return BBK_E_INVALID; }
+    if (((uintptr_t)list->d_nan_bits & 15) || ((uintptr_t)list->d_tiles & 15)) { bbk_set_error("invalid argument: %s: tile tables must be 16-byte aligned", who); return BBK_E_INVALID; }
+    return BBK_OK;
+}
+
 extern "C" int bbk_classify_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
                                   const int32_t* d_count, int64_t n_pairs, int32_t shard_chrom, int64_t resolution, int64_t min_dist,
-                                  int64_t max_dist, const BbkBiasTable* bias, int64_t out_base, double* d_p, double* d_q,
+                                  int64_t max_dist, const BbkBiasTable* bias, int64_t out_base, int64_t tile_base,
                                   const BbkWorkList* list, BbkScoreState* d_state, int32_t exact_only, void* stream) {
     BBK_REQUIRE(n_pairs >= 0 && out_base >= 0 && (out_base & 3) == 0, "bbk_classify_pairs: out_base must be a non-negative multiple of 4");
     BBK_REQUIRE(out_base + n_pairs < (1ll << 32), "bbk_classify_pairs: rank-local rows must be below 2^32");
@@ -796,30 +807,30 @@ extern "C" int bbk_classify_pairs(const int32_t* d_chr1, const int32_t* d_chr2, 
     BBK_REQUIRE(min_dist >= 0 && max_dist >= min_dist && max_dist + resolution < (1ll << 31),
                 "bbk_classify_pairs: needs 0 <= min_dist <= max_dist and max_dist + resolution < 2^31 (use bbk_pvalues otherwise)");
     BBK_REQUIRE((d_chr1 == nullptr) == (d_chr2 == nullptr), "bbk_classify_pairs: chr1/chr2 must both be given or both NULL");
-    BBK_REQUIRE(list && d_state && list->capacity >= 0, "bbk_classify_pairs: null work list / state");
+    BBK_REQUIRE(d_state, "bbk_classify_pairs: null state");
+    int rc = check_worklist(list, "bbk_classify_pairs");
+    if (rc != BBK_OK) return rc;
     if (n_pairs == 0) return BBK_OK;
-    BBK_REQUIRE(d_mid1 && d_mid2 && d_count && d_p, "bbk_classify_pairs: null column");
-    BBK_REQUIRE(list->d_row && list->d_count && list->d_dist && list->d_bias_product, "bbk_classify_pairs: incomplete work list");
-    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_chr1 | (uintptr_t)d_chr2 | (uintptr_t)d_p |
-                      (uintptr_t)d_q;
+    BBK_REQUIRE(tile_base >= 0 && tile_base + bbk_tiles_of(n_pairs) <= list->tile_capacity, "bbk_classify_pairs: the shard's tiles do not fit the tile directory");
+    BBK_REQUIRE(d_mid1 && d_mid2 && d_count, "bbk_classify_pairs: null column");
+    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_chr1 | (uintptr_t)d_chr2;
     BBK_REQUIRE((align & 15) == 0, "bbk_classify_pairs: columns must be 16-byte aligned");
     ClsParams C = {};
     PvParams& P = C.pv;
     P.chr1 = d_chr1; P.chr2 = d_chr2; P.mid1 = d_mid1; P.mid2 = d_mid2; P.count = d_count;
     P.n_pairs = n_pairs; P.shard_chrom = shard_chrom; P.R = resolution; P.min_dist = min_dist; P.max_dist = max_dist;
     P.div = make_fastdiv((uint64_t)resolution);
-    P.p = d_p; P.q = d_q;
     const bool has_bias = bias && bias->d_bias;
     if (has_bias) {
         BBK_REQUIRE(bias->d_chrom_base && bias->d_mid0 && bias->n_chrom > 0, "bbk_classify_pairs: incomplete bias table");
         P.bias = bias->d_bias; P.chrom_base = (const long long*)bias->d_chrom_base; P.mid0 = (const long long*)bias->d_mid0;
         P.n_chrom = bias->n_chrom;
     }
-    C.out_base = out_base;
-    C.l_idx = list->d_row; C.l_cnt = list->d_count; C.l_dist = list->d_dist; C.l_bb = list->d_bias_product; C.cap = list->capacity;
+    C.out_base = out_base; C.tile_base = tile_base;
+    C.l_row = list->d_row; C.l_cnt = list->d_count; C.l_dist = list->d_dist; C.l_bb = list->d_bias_product; C.cap = list->capacity;
+    C.dir = list->d_tiles; C.nan_bits = list->d_nan_bits;
     C.st = d_state; C.exact_only = exact_only ? 1 : 0;
-    const long long groups = n_pairs >> 2;
-    long long need = (groups + 2ll * CL_THREADS - 1) / (2ll * CL_THREADS);
+    long long need = bbk_tiles_of(n_pairs);
     long long grid = (long long)bbk_num_sms() * 3;
     if (need < grid) grid = need > 0 ? need : 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -839,20 +850,23 @@ extern "C" int bbk_score_guard(const BbkFitResult* d_fit, const double* d_spline
     return BBK_OK;
 }
 
-extern "C" int bbk_pvalues_listed(const BbkWorkList* list, const BbkFitResult* d_fit, const double* d_spline_y, int64_t resolution,
-                                  double* d_p, double* d_q, int64_t* d_p_hist, const BbkCandidates* cands, BbkScoreState* d_state,
-                                  void* stream) {
-    BBK_REQUIRE(list && d_fit && d_spline_y && d_p && d_state, "bbk_pvalues_listed: null pointer");
+extern "C" int bbk_pvalues_listed(const BbkWorkList* list, int64_t n_tiles, const BbkFitResult* d_fit, const double* d_spline_y,
+                                  int64_t resolution, double* d_p, double* d_q, int64_t* d_p_hist, const BbkCandidates* cands,
+                                  BbkScoreState* d_state, void* stream) {
+    BBK_REQUIRE(d_fit && d_spline_y && d_p && d_state, "bbk_pvalues_listed: null pointer");
     BBK_REQUIRE(resolution > 0 && resolution < (1ll << 32), "bbk_pvalues_listed: resolution must be in [1, 2^32)");
-    BBK_REQUIRE(list->capacity >= 0, "bbk_pvalues_listed: negative capacity");
-    if (list->capacity == 0) return BBK_OK;
-    BBK_REQUIRE(list->d_row && list->d_count && list->d_dist && list->d_bias_product, "bbk_pvalues_listed: incomplete work list");
-    BBK_REQUIRE(!cands || (d_q && d_p_hist), "bbk_pvalues_listed: the candidate list goes with q and the p histogram");
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = ensure_tables(st);
+    int rc = check_worklist(list, "bbk_pvalues_listed");
     if (rc != BBK_OK) return rc;
-    LsParams Q = {};
-    Q.l_idx = list->d_row; Q.l_cnt = list->d_count; Q.l_dist = list->d_dist; Q.l_bb = list->d_bias_product; Q.cap = list->capacity;
+    BBK_REQUIRE(n_tiles >= 0 && n_tiles <= list->tile_capacity, "bbk_pvalues_listed: more tiles than the directory holds");
+    if (n_tiles == 0) return BBK_OK;
+    BBK_REQUIRE(!cands || (d_q && d_p_hist), "bbk_pvalues_listed: the candidate list goes with q and the p histogram");
+    BBK_REQUIRE((((uintptr_t)d_p | (uintptr_t)d_q) & 15) == 0, "bbk_pvalues_listed: p / q must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = ensure_tables(st);
+    if (rc != BBK_OK) return rc;
+    TlParams Q = {};
+    Q.l_row = list->d_row; Q.l_cnt = list->d_count; Q.l_dist = list->d_dist; Q.l_bb = list->d_bias_product; Q.cap = list->capacity;
+    Q.dir = list->d_tiles; Q.nan_bits = list->d_nan_bits; Q.n_tiles = n_tiles;
     Q.fit = d_fit; Q.spline_y = d_spline_y;
     Q.pv.R = resolution; Q.pv.div = make_fastdiv((uint64_t)resolution);
     Q.p = d_p; Q.q = d_q; Q.p_hist = (long long*)d_p_hist;
@@ -861,10 +875,9 @@ extern "C" int bbk_pvalues_listed(const BbkWorkList* list, const BbkFitResult* d
         Q.c_keys = (unsigned long long*)cands->d_keys; Q.c_idx = cands->d_rows; Q.c_cap = cands->capacity;
     }
     Q.st = d_state;
-    long long need = (list->capacity + 32 * PV_WARPS - 1) / (32 * PV_WARPS);
     long long grid = (long long)bbk_num_sms() * 3;
-    if (need < grid) grid = need > 0 ? need : 1;
-    listed_kernel<<<(unsigned)grid, PV_THREADS, 0, st>>>(Q);
-    BBK_CHECK_LAUNCH("listed_kernel");
+    if (n_tiles < grid) grid = n_tiles;
+    scored_tiles_kernel<<<(unsigned)grid, PV_THREADS, sizeof(TlShared), st>>>(Q);
+    BBK_CHECK_LAUNCH("scored_tiles_kernel");
     return BBK_OK;
 }

@@ -10,7 +10,7 @@ p histogram and one fixed-capacity all-gather of the few candidate keys.  Nothin
 of a pass touches the host.
 
     K1 per shard -> [all-reduce] -> fit (one CTA)  ||  K4a classify per shard (side stream)
-    -> guard -> K4b scores the work list -> K5 q-values (local, or genome-wide across ranks)
+    -> guard -> K4b scores the tiles from their work lists -> K5 q-values (local, or genome-wide across ranks)
 
 GenomePass is that sequence; plan_shards / shard_rows decide who holds what.
 """
@@ -133,12 +133,23 @@ class GenomePass(object):
                     self.q[o + sh.n:o + ((sh.n + 3) & ~3)] = float("nan")
         if self.listed:
             cap = int(list_capacity) if list_capacity else m
-            if getattr(self, "worklist", None) is None or self.worklist.capacity < cap or list_capacity:
+            # tiles of TILE_ROWS rows, shard by shard (a shard's last tile may be partial)
+            self.tile_bases, nt = [], 0
+            for sh in self.shards:
+                self.tile_bases.append(nt)
+                nt += (sh.n + _lib.TILE_ROWS - 1) // _lib.TILE_ROWS
+            self.n_tiles = nt
+            have = getattr(self, "worklist", None)
+            if have is None or have.capacity < cap or list_capacity or have.tile_capacity < nt:
+                tcap = max(nt, 1)
                 self.l_row = torch.empty(cap, dtype=torch.int32, device=dev)
                 self.l_cnt = torch.empty(cap, dtype=torch.int32, device=dev)
                 self.l_dist = torch.empty(cap, dtype=torch.int32, device=dev)
                 self.l_bb = torch.empty(cap, dtype=torch.float64, device=dev)
-                self.worklist = _lib.WorkList(self.l_row.data_ptr(), self.l_cnt.data_ptr(), self.l_dist.data_ptr(), self.l_bb.data_ptr(), cap)
+                self.l_tiles = torch.zeros(tcap * 4, dtype=torch.int64, device=dev)               # 32-byte BbkTileDir records
+                self.l_bits = torch.zeros(tcap * (_lib.TILE_ROWS // 32), dtype=torch.int32, device=dev)
+                self.worklist = _lib.WorkList(self.l_row.data_ptr(), self.l_cnt.data_ptr(), self.l_dist.data_ptr(), self.l_bb.data_ptr(), cap,
+                                              self.l_tiles.data_ptr(), self.l_bits.data_ptr(), tcap)
             ccap = int(cand_capacity) if cand_capacity else min(m, max(1 << 20, m // 16))
             if getattr(self, "cands", None) is None or self.cands.capacity < ccap or cand_capacity:
                 self.c_keys = torch.empty(ccap, dtype=torch.int64, device=dev)
@@ -171,13 +182,13 @@ class GenomePass(object):
     def _classify(self, exact_only, st):
         eng, lib = self.eng, self.lib
         bias = ctypes.byref(eng.bias.struct) if eng.bias is not None else None
-        for sh, off in zip(self.shards, self.offsets):
+        for sh, off, tb in zip(self.shards, self.offsets, self.tile_bases):
             if sh.n == 0:
                 continue
             _lib.check(lib.bbk_classify_pairs(_lib.ptr(sh.chr1), _lib.ptr(sh.chr2), _lib.ptr(sh.mid1), _lib.ptr(sh.mid2),
-                                              _lib.ptr(sh.count), sh.n, sh.chrom, eng.R, eng.min_dist, eng.max_dist, bias, off,
-                                              _lib.ptr(self.p), _lib.ptr(self.q), ctypes.byref(self.worklist),
-                                              _lib.ptr(self.score_state), 1 if exact_only else 0, st), "bbk_classify_pairs")
+                                              _lib.ptr(sh.count), sh.n, sh.chrom, eng.R, eng.min_dist, eng.max_dist, bias, off, tb,
+                                              ctypes.byref(self.worklist), _lib.ptr(self.score_state), 1 if exact_only else 0, st),
+                       "bbk_classify_pairs")
             eng.launches += 1
 
     def enqueue(self, n_tests=-1, smoothing=None, marks=None):
@@ -227,7 +238,7 @@ class GenomePass(object):
             _lib.check(lib.bbk_score_guard(_lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), _lib.ptr(self.score_state), st), "bbk_score_guard")
             self._classify(True, st)
             mark("guard")
-            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(self.worklist), _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), eng.R,
+            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(self.worklist), self.n_tiles, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), eng.R,
                                               _lib.ptr(self.p), _lib.ptr(self.q), _lib.ptr(eng.p_hist) if want_q else None,
                                               ctypes.byref(self.cands) if want_q else None, _lib.ptr(self.score_state), st),
                        "bbk_pvalues_listed")

@@ -1,8 +1,9 @@
 """GPU tests of the multi-shard / multi-GPU pass (blueberry_b200.distributed.GenomePass) and of the K4 split it runs
 (bbk_classify_pairs -> bbk_score_guard -> bbk_pvalues_listed -> bbk_bh_qvalues_listed):
 
-  * the split path against the direct kernel (bbk_pvalues + bbk_bh_qvalues) bit for bit - same arithmetic, so every p and
-    q must be IDENTICAL, whatever the shard sizes, tails, chromosome columns, biases, zero rows;
+  * the split path against the direct kernel (bbk_pvalues + bbk_bh_qvalues): same NaN rows, same rows at exactly 1.0,
+    every other p within 1e-10 (relative), q bit for bit the reference's BH of the p beside it - whatever the shard
+    sizes, tails, chromosome columns, biases, zero rows;
   * the exact mode the guard falls back to (every in-range row through the list) and the guard's own decision;
   * several shards on one GPU against the CPU oracle on the concatenated records (genome-wide S, spline and q);
   * q end to end against BH over the REFERENCE's p (log10 tolerance; identical ranks outside declared near-ties);
@@ -62,6 +63,29 @@ def _same(a, b):
     return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
 
 
+def _close(a, b, rel=1e-10):
+    """Same NaN pattern, the same rows at exactly 1.0 / 0.0, everything else within `rel` (relative).  The split path and the
+    direct kernel evaluate the same tail with different but equivalent sums (lower tail for small counts; the direct
+    kernel's serial general form on a shard's last n % 4 records), so they agree to rounding, not to the bit."""
+    if not np.array_equal(np.isnan(a), np.isnan(b)):
+        return False
+    ok = ~np.isnan(a)
+    a, b = a[ok], b[ok]
+    if not (np.array_equal(a == 1.0, b == 1.0) and np.array_equal(a == 0.0, b == 0.0)):
+        return False
+    pos = (a > 0) & (b > 0)
+    return bool((np.abs(a[pos] / b[pos] - 1.0) <= rel).all())
+
+
+def _bh_of(p):
+    """The reference's BH over the non-NaN rows of p, N = their number (the oracle's restatement of fithic.py:466-487)."""
+    from oracle import fithic_oracle as fo
+    q = np.full(len(p), np.nan)
+    ok = ~np.isnan(p)
+    q[ok] = fo.benjamini_hochberg_correction(p[ok], int(ok.sum()))
+    return q
+
+
 def _random_shards(seed, dev, with_chr=False):
     """Shards with awkward sizes (tails of 0..3 records, a one-record shard, an empty one), off-grid / negative / out-of-range
     distances, zero and negative counts."""
@@ -103,7 +127,7 @@ def _random_shards(seed, dev, with_chr=False):
 
 
 @pytest.mark.parametrize("seed,with_chr", [(s, False) for s in range(8)] + [(s, True) for s in range(8, 12)])
-def test_split_k4_is_bitwise_the_direct_kernel(seed, with_chr):
+def test_split_k4_matches_the_direct_kernel(seed, with_chr):
     import torch
     from blueberry_b200.distributed import GenomePass
     dev = torch.device("cuda", 0)
@@ -120,10 +144,11 @@ def test_split_k4_is_bitwise_the_direct_kernel(seed, with_chr):
     assert score.overflow == 0 and score.cand_overflow == 0
     p_old, q_old, starts = _direct(eng, shards, dev)
     assert gp.offsets == starts
-    assert _same(p_new[:gp.rows], p_old[:gp.rows]), "p differs between the split and the direct kernel"
-    assert _same(q_new[:gp.rows], q_old[:gp.rows]), "q differs between the listed and the full Benjamini-Hochberg step"
+    assert _close(p_new[:gp.rows], p_old[:gp.rows]), "p differs between the split and the direct kernel"
+    assert _same(q_new[:gp.rows], _bh_of(p_new[:gp.rows])), "q is not the reference's BH of the p beside it"
+    assert _close(q_new[:gp.rows], q_old[:gp.rows], 1e-9), "q differs between the listed and the full Benjamini-Hochberg step"
     n_rows = sum(s.n for s in shards)
-    assert int(score.n_front + score.n_back + score.n_ones + score.n_nan) == n_rows      # every record went exactly one way
+    assert int(score.n_one + score.n_small + score.n_other + score.n_final) == n_rows and int(score.n_list) == int(score.n_one + score.n_small + score.n_other)   # every record went exactly one way
 
 
 @pytest.mark.parametrize("seed", [1, 5])
@@ -147,12 +172,12 @@ def test_exact_mode_equals_speculative_mode(seed):
     gp.score_state.copy_(torch.frombuffer(bytearray(bytes(forced)), dtype=torch.uint8))
     gp.p.fill_(7.0); gp.q.fill_(7.0)
     gp._classify(True, st)
-    _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), eng.R, _lib.ptr(gp.p),
+    _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), gp.n_tiles, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), eng.R, _lib.ptr(gp.p),
                                       _lib.ptr(gp.q), _lib.ptr(eng.p_hist), ctypes.byref(gp.cands), _lib.ptr(gp.score_state), st), "listed")
     gp._qvalues(st)
     torch.cuda.synchronize()
     score = _lib.ScoreState.from_buffer_copy(gp.score_state.cpu().numpy().tobytes())
-    assert score.exact == 1 and score.n_ones == 0                                      # nothing was decided before the fit
+    assert score.exact == 1                                                            # every in-range row went through the list
     rows = gp.rows
     real = np.ones(rows, bool)
     for s, a in zip(shards, gp.offsets):
@@ -286,8 +311,8 @@ def test_list_overflow_is_detected_and_repaired():
     gp.run()                                                        # finish() sees the flag and repeats with a full-size list
     assert gp.last_score.overflow == 0
     p_old, q_old, _ = _direct(eng, shards, dev)
-    assert _same(gp.p.cpu().numpy()[:gp.rows], p_old[:gp.rows])
-    assert _same(gp.q.cpu().numpy()[:gp.rows], q_old[:gp.rows])     # the candidate overflow falls back to the full pass: still exact
+    assert _close(gp.p.cpu().numpy()[:gp.rows], p_old[:gp.rows])
+    assert _same(gp.q.cpu().numpy()[:gp.rows], _bh_of(gp.p.cpu().numpy()[:gp.rows]))     # the candidate overflow falls back to the full pass: still exact
 
 
 def test_fit_transform_arrays_pinned_and_wide_inputs():
