@@ -404,9 +404,8 @@ def _measure(args, wl_name, world, rank, dev, full, out):
         return
 
     # ---- per-stage device times (separate instrumented steps; CUDA events on the streams the kernels run on)
-    names = ["hist", "allreduce", "fit", "classify_wait", "guard", "pvalues", "bh"]
+    names = ["hist", "allreduce", "fit", "pvalues", "bh"]
     acc = dict((n, 0.0) for n in names)
-    acc["classify_side_stream"] = 0.0
     reps = min(args.steps, 5)
     for _ in range(reps):
         marks = {}
@@ -417,24 +416,29 @@ def _measure(args, wl_name, world, rank, dev, full, out):
             if n in marks:
                 acc[n] += marks[prev].elapsed_time(marks[n]) / reps
                 prev = n
-        if "classify_start" in marks:
-            acc["classify_side_stream"] += marks["classify_start"].elapsed_time(marks["classify_end"]) / reps
     # the K4 kernels alone, back to back on one stream (what the roofline object is computed from)
     k4a = k4b = 0.0
     if gp.listed:
         from blueberry_b200 import _lib
         import ctypes
-        lib = W.eng.lib
+        eng, lib = W.eng, W.eng.lib
+        bias = ctypes.byref(eng.bias.struct) if eng.bias is not None else None
+        flags = _lib.ptr(eng.bias.flags) if eng.bias is not None else None
         for _ in range(reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             st = _lib.stream_ptr()
-            _lib.check(lib.bbk_score_begin(_lib.ptr(gp.score_state), _lib.ptr(W.eng.p_hist), st), "bbk_score_begin")
+            _lib.check(lib.bbk_score_begin(_lib.ptr(gp.score_state), _lib.ptr(eng.p_hist), st), "bbk_score_begin")
+            _lib.check(lib.bbk_score_guard(_lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), _lib.ptr(gp.score_state), st), "bbk_score_guard")
             ev[0].record()
-            gp._classify(False, st)
+            for sh, off in zip(gp.shards, gp.offsets):
+                if sh.n:
+                    _lib.check(lib.bbk_score_pairs(_lib.ptr(sh.mid1), _lib.ptr(sh.mid2), _lib.ptr(sh.count), sh.n, sh.chrom, eng.R,
+                                                   eng.min_dist, eng.max_dist, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), bias, flags,
+                                                   off, _lib.ptr(gp.p), _lib.ptr(gp.q), _lib.ptr(eng.p_hist), ctypes.byref(gp.cands),
+                                                   ctypes.byref(gp.deferred), _lib.ptr(gp.score_state), st), "bbk_score_pairs")
             ev[1].record()
-            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(gp.worklist), gp.n_tiles, _lib.ptr(W.eng.fit_result), _lib.ptr(W.eng.spline_y), W.eng.R,
-                                              _lib.ptr(gp.p), _lib.ptr(gp.q), _lib.ptr(W.eng.p_hist), ctypes.byref(gp.cands),
-                                              _lib.ptr(gp.score_state), st), "bbk_pvalues_listed")
+            _lib.check(lib.bbk_score_deferred(ctypes.byref(gp.deferred), _lib.ptr(eng.fit_result), _lib.ptr(gp.p), _lib.ptr(gp.q),
+                                              _lib.ptr(eng.p_hist), ctypes.byref(gp.cands), _lib.ptr(gp.score_state), st), "bbk_score_deferred")
             ev[2].record()
             torch.cuda.synchronize()
             k4a += ev[0].elapsed_time(ev[1]) / reps
@@ -443,25 +447,23 @@ def _measure(args, wl_name, world, rank, dev, full, out):
         torch.cuda.synchronize()
     score = _score_state(gp)
     out["stages_ms"] = acc
-    out["k4_alone_ms"] = {"classify_kernel": k4a, "scored_tiles_kernel": k4b}
-    out["work_list"] = {"count_eq_1": int(score.n_one), "count_2_to_8": int(score.n_small), "other": int(score.n_other), "rows_finished_by_classify": int(score.n_final),
-                        "candidates_p_lt_2^-5": int(score.n_cand), "exact_mode": int(score.exact)}
+    out["k4_alone_ms"] = {"score_tiles_kernel": k4a, "score_deferred_kernel": k4b}
+    out["work_list"] = {"deferred_rows": int(score.n_list), "candidates_p_lt_2^-5": int(score.n_cand), "exact_mode": int(score.exact)}
     tmax = torch.tensor([k4a + k4b, acc["hist"], acc["bh"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     k4_ms = float(tmax[0].item())
     k4_gbs = K4_BYTES_PER_PAIR * W.P_total / world / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
     out["roofline"] = {
-        "bound": "hbm", "kernel": "K4 = classify_kernel + scored_tiles_kernel (per GPU, timed back to back on one stream)",
+        "bound": "hbm", "kernel": "K4 = score_tiles_kernel (one launch per shard) + score_deferred_kernel (per GPU, timed back to back on one stream)",
         "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak,
         "traffic": _k4_traffic(wl_name, world), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR * W.P_total // world,
-        "traffic_note": "K4 also writes the 8 B/pair of q that the byte table books under K5, and moves the 20-byte work-list entries "
-                        "(written by classify, read back by scored_tiles); traffic is null unless profiles/k4_traffic.json holds a capture of these sources",
+        "traffic_note": "K4 also writes the 8 B/pair of q that the byte table books under K5 (28 B/pair moved for 20 algorithmic); "
+                        "traffic is null unless profiles/k4_traffic.json holds a capture of these sources",
         "whole_pass_frac": out["whole_pass_frac"],
-        "stage_gbs_per_gpu": {"hist": 12 * W.P_local / (acc["hist"] * 1e-3) / 1e9 if acc["hist"] > 0 else None,
-                              "classify (12 B/pair in)": 12 * W.P_local / (k4a * 1e-3) / 1e9 if k4a > 0 else None,
-                              "scored_tiles (16 B/pair of p, q out)": 16 * W.P_local / (k4b * 1e-3) / 1e9 if k4b > 0 else None},
+        "stage_gbs_per_gpu": {"hist (12 B/pair)": 12 * W.P_local / (acc["hist"] * 1e-3) / 1e9 if acc["hist"] > 0 else None,
+                              "score_tiles (12 B/pair in + 16 B/pair of p, q out)": 28 * W.P_local / (k4a * 1e-3) / 1e9 if k4a > 0 else None},
     }
     out["parity"] = _parity_bits(W, gp, fit, dev, world)
 

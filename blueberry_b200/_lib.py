@@ -43,16 +43,13 @@ class BiasTable(ctypes.Structure):
 
 
 class ScoreState(ctypes.Structure):
-    _fields_ = [("n_list", ctypes.c_uint64), ("n_one", ctypes.c_uint64), ("n_small", ctypes.c_uint64), ("n_other", ctypes.c_uint64),
-                ("n_final", ctypes.c_uint64),
-                ("n_cand", ctypes.c_uint64), ("overflow", ctypes.c_int32), ("cand_overflow", ctypes.c_int32),
-                ("exact", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+    _fields_ = [("n_list", ctypes.c_uint64), ("n_cand", ctypes.c_uint64), ("overflow", ctypes.c_int32),
+                ("cand_overflow", ctypes.c_int32), ("exact", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
-class WorkList(ctypes.Structure):
-    _fields_ = [("d_row", ctypes.c_void_p), ("d_count", ctypes.c_void_p), ("d_dist", ctypes.c_void_p),
-                ("d_bias_product", ctypes.c_void_p), ("capacity", ctypes.c_int64),
-                ("d_tiles", ctypes.c_void_p), ("d_nan_bits", ctypes.c_void_p), ("tile_capacity", ctypes.c_int64)]
+class DeferredList(ctypes.Structure):
+    _fields_ = [("d_row", ctypes.c_void_p), ("d_count", ctypes.c_void_p), ("d_prior", ctypes.c_void_p),
+                ("capacity", ctypes.c_int64)]
 
 
 TILE_ROWS = 2048
@@ -99,11 +96,12 @@ SIGNATURES = {
     "bbk_stats_pack": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "bbk_stats_unpack": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "bbk_score_begin": (ctypes.c_int, [_vp, _vp, _vp]),
-    "bbk_tiles_of": (_i64, [_i64]),
-    "bbk_classify_pairs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, ctypes.POINTER(BiasTable), _i64,
-                                          _i64, ctypes.POINTER(WorkList), _vp, _i32, _vp]),
+    "bbk_bias_flags_bytes": (_sz, [_i64]),
+    "bbk_bias_flags": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "bbk_score_guard": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
-    "bbk_pvalues_listed": (ctypes.c_int, [ctypes.POINTER(WorkList), _i64, _vp, _vp, _i64, _vp, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp]),
+    "bbk_score_pairs": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, ctypes.POINTER(BiasTable), _vp, _i64,
+                                       _vp, _vp, _vp, ctypes.POINTER(Candidates), ctypes.POINTER(DeferredList), _vp, _vp]),
+    "bbk_score_deferred": (ctypes.c_int, [ctypes.POINTER(DeferredList), _vp, _vp, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp]),
     "bbk_bh_qvalues_listed": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp, _sz, _vp]),
     "bbk_bh_select_listed": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "bbk_bh_gathered_workspace_bytes": (_sz, [_i32, _i64]),

@@ -94,7 +94,7 @@ long long format_and_deflate(const Job& J, long long lo, long long hi, bool head
     text.clear();
     if (header) text += "chr1\tfragmentMid1\tchr2\tfragmentMid2\tcontactCount\tp-value\tq-value\n";
     long long kept = 0;
-    char line[256];
+    char line[2 * 100 + 160];          // two names of at most 100 bytes (checked by the caller) + 3 integers + 2 doubles + separators
     for (long long i = lo; i < hi; ++i) {
         const double pv = J.p[i];
         if (!(pv <= 1.0)) continue;

@@ -672,7 +672,7 @@ __global__ void pvalues_tail_kernel(PvParams P) {
     }
 }
 
-#include "pvalue_lists.inl"
+#include "pvalue_tiles.inl"
 
 int ensure_tables(cudaStream_t st) {
     // 1/j and ln j! are constants; fill them once per device (same values whoever wins a race)
@@ -777,10 +777,8 @@ extern "C" int bbk_pvalues_bh(const int32_t* d_chr1, const int32_t* d_chr2, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4 split around the fit (pvalue_lists.inl): classification before / during the fit, tiles scored from dense lists after it
+// K4 as one streaming kernel over bulk-staged tiles + a patch kernel for the deferred rows (pvalue_tiles.inl)
 // ---------------------------------------------------------------------------------------------------
-extern "C" int64_t bbk_tiles_of(int64_t n_pairs) { return n_pairs <= 0 ? 0 : (n_pairs + BBK_TILE_ROWS - 1) / BBK_TILE_ROWS; }
-
 extern "C" int bbk_score_begin(BbkScoreState* d_state, int64_t* d_p_hist, void* stream) {
     BBK_REQUIRE(d_state, "bbk_score_begin: null state");
     score_begin_kernel<<<(BBK_PHIST_LEN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_state, (long long*)d_p_hist);
@@ -788,58 +786,14 @@ extern "C" int bbk_score_begin(BbkScoreState* d_state, int64_t* d_p_hist, void* 
     return BBK_OK;
 }
 
-static int check_worklist(const BbkWorkList* list, const char* who) {
-    if (!list || list->capacity < 0 || list->tile_capacity < 0) { bbk_set_error("invalid argument: %s: null work list / negative capacity", who); return BBK_E_INVALID; }
-    if (list->capacity > 0 && !(list->d_row && list->d_count && list->d_dist && list->d_bias_product)) {
-        bbk_set_error("invalid argument: %s: incomplete work list", who); return BBK_E_INVALID; }
-    if (list->tile_capacity > 0 && !(list->d_tiles && list->d_nan_bits)) { bbk_set_error("invalid argument: %s: null tile directory / bit map", who); return BBK_E_INVALID; }
-    if (((uintptr_t)list->d_nan_bits & 15) || ((uintptr_t)list->d_tiles & 15)) { bbk_set_error("invalid argument: %s: tile tables must be 16-byte aligned", who); return BBK_E_INVALID; }
-    return BBK_OK;
-}
+extern "C" size_t bbk_bias_flags_bytes(int64_t n_entries) { return n_entries <= 0 ? 8 : (size_t)((n_entries + 31) / 32 + 1) * 4; }   // one spare (zero) word
 
-extern "C" int bbk_classify_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
-                                  const int32_t* d_count, int64_t n_pairs, int32_t shard_chrom, int64_t resolution, int64_t min_dist,
-                                  int64_t max_dist, const BbkBiasTable* bias, int64_t out_base, int64_t tile_base,
-                                  const BbkWorkList* list, BbkScoreState* d_state, int32_t exact_only, void* stream) {
-    BBK_REQUIRE(n_pairs >= 0 && out_base >= 0 && (out_base & 3) == 0, "bbk_classify_pairs: out_base must be a non-negative multiple of 4");
-    BBK_REQUIRE(out_base + n_pairs < (1ll << 32), "bbk_classify_pairs: rank-local rows must be below 2^32");
-    BBK_REQUIRE(resolution > 0 && resolution < (1ll << 32), "bbk_classify_pairs: resolution must be in [1, 2^32)");
-    BBK_REQUIRE(min_dist >= 0 && max_dist >= min_dist && max_dist + resolution < (1ll << 31),
-                "bbk_classify_pairs: needs 0 <= min_dist <= max_dist and max_dist + resolution < 2^31 (use bbk_pvalues otherwise)");
-    BBK_REQUIRE((d_chr1 == nullptr) == (d_chr2 == nullptr), "bbk_classify_pairs: chr1/chr2 must both be given or both NULL");
-    BBK_REQUIRE(d_state, "bbk_classify_pairs: null state");
-    int rc = check_worklist(list, "bbk_classify_pairs");
-    if (rc != BBK_OK) return rc;
-    if (n_pairs == 0) return BBK_OK;
-    BBK_REQUIRE(tile_base >= 0 && tile_base + bbk_tiles_of(n_pairs) <= list->tile_capacity, "bbk_classify_pairs: the shard's tiles do not fit the tile directory");
-    BBK_REQUIRE(d_mid1 && d_mid2 && d_count, "bbk_classify_pairs: null column");
-    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_chr1 | (uintptr_t)d_chr2;
-    BBK_REQUIRE((align & 15) == 0, "bbk_classify_pairs: columns must be 16-byte aligned");
-    ClsParams C = {};
-    PvParams& P = C.pv;
-    P.chr1 = d_chr1; P.chr2 = d_chr2; P.mid1 = d_mid1; P.mid2 = d_mid2; P.count = d_count;
-    P.n_pairs = n_pairs; P.shard_chrom = shard_chrom; P.R = resolution; P.min_dist = min_dist; P.max_dist = max_dist;
-    P.div = make_fastdiv((uint64_t)resolution);
-    const bool has_bias = bias && bias->d_bias;
-    if (has_bias) {
-        BBK_REQUIRE(bias->d_chrom_base && bias->d_mid0 && bias->n_chrom > 0, "bbk_classify_pairs: incomplete bias table");
-        P.bias = bias->d_bias; P.chrom_base = (const long long*)bias->d_chrom_base; P.mid0 = (const long long*)bias->d_mid0;
-        P.n_chrom = bias->n_chrom;
-    }
-    C.out_base = out_base; C.tile_base = tile_base;
-    C.l_row = list->d_row; C.l_cnt = list->d_count; C.l_dist = list->d_dist; C.l_bb = list->d_bias_product; C.cap = list->capacity;
-    C.dir = list->d_tiles; C.nan_bits = list->d_nan_bits;
-    C.st = d_state; C.exact_only = exact_only ? 1 : 0;
-    long long need = bbk_tiles_of(n_pairs);
-    long long grid = (long long)bbk_num_sms() * 3;
-    if (need < grid) grid = need > 0 ? need : 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool chr = d_chr1 != nullptr;
-    if (chr && has_bias) classify_kernel<true, true><<<(unsigned)grid, CL_THREADS, 0, st>>>(C);
-    else if (chr) classify_kernel<true, false><<<(unsigned)grid, CL_THREADS, 0, st>>>(C);
-    else if (has_bias) classify_kernel<false, true><<<(unsigned)grid, CL_THREADS, 0, st>>>(C);
-    else classify_kernel<false, false><<<(unsigned)grid, CL_THREADS, 0, st>>>(C);
-    BBK_CHECK_LAUNCH("classify_kernel");
+extern "C" int bbk_bias_flags(const double* d_bias, int64_t n_entries, uint32_t* d_flags, void* stream) {
+    BBK_REQUIRE(n_entries >= 0, "bbk_bias_flags: negative size");
+    if (n_entries == 0) return BBK_OK;
+    BBK_REQUIRE(d_bias && d_flags, "bbk_bias_flags: null pointer");
+    bias_flags_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_bias, n_entries, d_flags);
+    BBK_CHECK_LAUNCH("bias_flags_kernel");
     return BBK_OK;
 }
 
@@ -850,34 +804,105 @@ extern "C" int bbk_score_guard(const BbkFitResult* d_fit, const double* d_spline
     return BBK_OK;
 }
 
-extern "C" int bbk_pvalues_listed(const BbkWorkList* list, int64_t n_tiles, const BbkFitResult* d_fit, const double* d_spline_y,
-                                  int64_t resolution, double* d_p, double* d_q, int64_t* d_p_hist, const BbkCandidates* cands,
-                                  BbkScoreState* d_state, void* stream) {
-    BBK_REQUIRE(d_fit && d_spline_y && d_p && d_state, "bbk_pvalues_listed: null pointer");
-    BBK_REQUIRE(resolution > 0 && resolution < (1ll << 32), "bbk_pvalues_listed: resolution must be in [1, 2^32)");
-    int rc = check_worklist(list, "bbk_pvalues_listed");
+static int check_deferred(const BbkDeferredList* list, const char* who) {
+    if (!list || list->capacity < 0) { bbk_set_error("invalid argument: %s: null deferred list / negative capacity", who); return BBK_E_INVALID; }
+    if (list->capacity > 0 && !(list->d_row && list->d_count && list->d_prior)) {
+        bbk_set_error("invalid argument: %s: incomplete deferred list", who); return BBK_E_INVALID; }
+    return BBK_OK;
+}
+
+extern "C" int bbk_score_pairs(const int32_t* d_mid1, const int32_t* d_mid2, const int32_t* d_count, int64_t n_pairs,
+                               int32_t shard_chrom, int64_t resolution, int64_t min_dist, int64_t max_dist,
+                               const BbkFitResult* d_fit, const double* d_spline_y, const BbkBiasTable* bias,
+                               const uint32_t* d_bias_flags, int64_t out_base, double* d_p, double* d_q, int64_t* d_p_hist,
+                               const BbkCandidates* cands, const BbkDeferredList* deferred, BbkScoreState* d_state, void* stream) {
+    BBK_REQUIRE(n_pairs >= 0 && out_base >= 0 && (out_base & 3) == 0, "bbk_score_pairs: out_base must be a non-negative multiple of 4");
+    BBK_REQUIRE(out_base + n_pairs < (1ll << 32), "bbk_score_pairs: rank-local rows must be below 2^32");
+    BBK_REQUIRE(resolution > 0 && resolution < (1ll << 31), "bbk_score_pairs: resolution must be in [1, 2^31)");
+    BBK_REQUIRE(min_dist >= 0 && max_dist >= min_dist && max_dist + resolution < (1ll << 31),
+                "bbk_score_pairs: needs 0 <= min_dist <= max_dist and max_dist + resolution < 2^31 (use bbk_pvalues otherwise)");
+    BBK_REQUIRE(d_fit && d_spline_y && d_state, "bbk_score_pairs: null pointer");
+    int rc = check_deferred(deferred, "bbk_score_pairs");
     if (rc != BBK_OK) return rc;
-    BBK_REQUIRE(n_tiles >= 0 && n_tiles <= list->tile_capacity, "bbk_pvalues_listed: more tiles than the directory holds");
-    if (n_tiles == 0) return BBK_OK;
-    BBK_REQUIRE(!cands || (d_q && d_p_hist), "bbk_pvalues_listed: the candidate list goes with q and the p histogram");
-    BBK_REQUIRE((((uintptr_t)d_p | (uintptr_t)d_q) & 15) == 0, "bbk_pvalues_listed: p / q must be 16-byte aligned");
+    if (n_pairs == 0) return BBK_OK;
+    BBK_REQUIRE(d_mid1 && d_mid2 && d_count && d_p, "bbk_score_pairs: null column");
+    uintptr_t align = (uintptr_t)d_mid1 | (uintptr_t)d_mid2 | (uintptr_t)d_count | (uintptr_t)d_p | (uintptr_t)d_q;
+    BBK_REQUIRE((align & 15) == 0, "bbk_score_pairs: columns must be 16-byte aligned");
+    BBK_REQUIRE(!cands || (d_q && d_p_hist), "bbk_score_pairs: the candidate list goes with q and the p histogram");
+    StParams Q = {};
+    Q.mid1 = d_mid1; Q.mid2 = d_mid2; Q.count = d_count; Q.n_pairs = n_pairs;
+    Q.shard_chrom = shard_chrom; Q.min_dist = min_dist; Q.max_dist = max_dist;
+    Q.div = make_fastdiv((uint64_t)resolution);
+    Q.fit = d_fit; Q.spline_y = d_spline_y;
+    const bool has_bias = bias && bias->d_bias;
+    if (has_bias) {
+        BBK_REQUIRE(bias->d_chrom_base && bias->d_mid0 && bias->n_chrom > 0, "bbk_score_pairs: incomplete bias table");
+        BBK_REQUIRE(d_bias_flags, "bbk_score_pairs: a bias table needs its flag bits (bbk_bias_flags)");
+        Q.bias = bias->d_bias; Q.chrom_base = (const long long*)bias->d_chrom_base; Q.mid0 = (const long long*)bias->d_mid0;
+        Q.n_chrom = bias->n_chrom; Q.flags = d_bias_flags;
+    }
+    Q.out_base = out_base; Q.p = d_p; Q.q = d_q; Q.p_hist = (long long*)d_p_hist;
+    if (cands && cands->capacity > 0) {
+        BBK_REQUIRE(cands->d_keys && cands->d_rows, "bbk_score_pairs: incomplete candidate list");
+        Q.c_keys = (unsigned long long*)cands->d_keys; Q.c_idx = cands->d_rows; Q.c_cap = cands->capacity;
+    }
+    Q.d_row = deferred->d_row; Q.d_cnt = deferred->d_count; Q.d_prior = deferred->d_prior; Q.d_cap = deferred->capacity;
+    Q.st = d_state;
+    const long long need = (n_pairs + BBK_TILE_ROWS - 1) / BBK_TILE_ROWS;
+    long long grid = (long long)bbk_num_sms() * ST_CTAS_PER_SM;
+    if (need < grid) grid = need;
+    cudaStream_t st = (cudaStream_t)stream;
+    static std::mutex mu;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    BBK_CHECK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!(dev >= 0 && dev < 64 && attr_done[dev])) {
+            BBK_CHECK_CUDA(cudaFuncSetAttribute(score_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StShared)));
+            BBK_CHECK_CUDA(cudaFuncSetAttribute(score_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StShared)));
+            BBK_CHECK_CUDA(cudaFuncSetAttribute(score_tiles_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            BBK_CHECK_CUDA(cudaFuncSetAttribute(score_tiles_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+    }
+    if (has_bias) score_tiles_kernel<true><<<(unsigned)grid, ST_THREADS, sizeof(StShared), st>>>(Q);
+    else score_tiles_kernel<false><<<(unsigned)grid, ST_THREADS, sizeof(StShared), st>>>(Q);
+    BBK_CHECK_LAUNCH("score_tiles_kernel");
+    return BBK_OK;
+}
+
+extern "C" int bbk_score_deferred(const BbkDeferredList* deferred, const BbkFitResult* d_fit, double* d_p, double* d_q,
+                                  int64_t* d_p_hist, const BbkCandidates* cands, BbkScoreState* d_state, void* stream) {
+    BBK_REQUIRE(d_fit && d_p && d_state, "bbk_score_deferred: null pointer");
+    int rc = check_deferred(deferred, "bbk_score_deferred");
+    if (rc != BBK_OK) return rc;
+    if (deferred->capacity == 0) return BBK_OK;
+    BBK_REQUIRE(!cands || (d_q && d_p_hist), "bbk_score_deferred: the candidate list goes with q and the p histogram");
     cudaStream_t st = (cudaStream_t)stream;
     rc = ensure_tables(st);
     if (rc != BBK_OK) return rc;
-    TlParams Q = {};
-    Q.l_row = list->d_row; Q.l_cnt = list->d_count; Q.l_dist = list->d_dist; Q.l_bb = list->d_bias_product; Q.cap = list->capacity;
-    Q.dir = list->d_tiles; Q.nan_bits = list->d_nan_bits; Q.n_tiles = n_tiles;
-    Q.fit = d_fit; Q.spline_y = d_spline_y;
-    Q.pv.R = resolution; Q.pv.div = make_fastdiv((uint64_t)resolution);
-    Q.p = d_p; Q.q = d_q; Q.p_hist = (long long*)d_p_hist;
+    DfParams D = {};
+    D.d_row = deferred->d_row; D.d_cnt = deferred->d_count; D.d_prior = deferred->d_prior; D.d_cap = deferred->capacity;
+    D.fit = d_fit; D.p = d_p; D.q = d_q; D.p_hist = (long long*)d_p_hist;
     if (cands && cands->capacity > 0) {
-        BBK_REQUIRE(cands->d_keys && cands->d_rows, "bbk_pvalues_listed: incomplete candidate list");
-        Q.c_keys = (unsigned long long*)cands->d_keys; Q.c_idx = cands->d_rows; Q.c_cap = cands->capacity;
+        BBK_REQUIRE(cands->d_keys && cands->d_rows, "bbk_score_deferred: incomplete candidate list");
+        D.c_keys = (unsigned long long*)cands->d_keys; D.c_idx = cands->d_rows; D.c_cap = cands->capacity;
     }
-    Q.st = d_state;
-    long long grid = (long long)bbk_num_sms() * 3;
-    if (n_tiles < grid) grid = n_tiles;
-    scored_tiles_kernel<<<(unsigned)grid, PV_THREADS, sizeof(TlShared), st>>>(Q);
-    BBK_CHECK_LAUNCH("scored_tiles_kernel");
+    D.st = d_state;
+    static std::mutex mu;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    BBK_CHECK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!(dev >= 0 && dev < 64 && attr_done[dev])) {
+            BBK_CHECK_CUDA(cudaFuncSetAttribute(score_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+    }
+    // the list length is only known on the device: a grid that covers the device, rounds handed out by stride
+    score_deferred_kernel<<<(unsigned)(bbk_num_sms() * 2), PV_THREADS, sizeof(DfShared), st>>>(D);
+    BBK_CHECK_LAUNCH("score_deferred_kernel");
     return BBK_OK;
 }

@@ -1,0 +1,606 @@
+// pvalue_tiles.inl - K4 as one streaming kernel over bulk-staged record tiles (included by pvalue.cu inside its
+// anonymous namespace).  Reference: the scoring loop of fit_spline, fithic.py:413-435.
+//
+// What the records look like decides the design: most have count 0 (60 % at 5 kb, 93 % at 1 kb) and need no arithmetic,
+// most of the rest have a count of 1..8, whose p-value is a handful of FP64 operations in the LOWER-tail form, and a few
+// per cent (large counts next to the diagonal, the significant rows) need a tail sum of tens to hundreds of terms.  So:
+//
+//   score_tiles_kernel  streams every record once.  Every WARP runs on its own over tiles of 256 rows - no CTA barrier, no
+//       shared state between warps.  The three record columns of a tile arrive in the warp's shared memory by bulk
+//       asynchronous copies (cp.async.bulk + mbarrier, two stages: the warp's next two tiles are in flight while it works
+//       on one, without holding a register).
+//         decode   class of every row from its count and distance alone.  count <= 0: p = 1.0 unless one of the two loci
+//                  carries a flag bit in the bias bit map (value < 0 or > 4: the prior has to be looked at) - one bit per
+//                  locus instead of an 8-byte gather, which is what made the 1 kb workloads latency-bound.  The result of
+//                  every such row (1.0 / NaN) replaces the row in the tile; rows that need arithmetic go on the warp's
+//                  list, sorted count <= 1 | 2..8 | rest.
+//         rounds   32 list entries at a time, every lane busy on the same path; the gathers of the NEXT round (spline value,
+//                  two bias values) are in flight while a round computes.  prior = splineY[i] * (b1 * b2), fithic.py:429-431;
+//                      count == 1     1 - (1-q)^S                                (bdtrc's closed form)
+//                      2..SMALL_C     1 - (1-q)^S (1 + r1 + r1 r2 + ...), count-1 terms (the lower tail)
+//                  rows this cannot finish - larger counts, a prior outside (0, 2^-10), a lower-tail result below 1e-4
+//                  (digits lost in the subtraction), tiny S - are DEFERRED: (row, count, prior) goes to a global list.
+//         output   the warp writes its 256 rows of p (and q = 1.0 / NaN) with full coalesced 128-bit stores; no partial
+//                  sector is ever written by this kernel.
+//       It also fills the coarse p histogram and appends (key, row) of every p < BBK_SMALL_P to the q-value step's
+//       candidate list; deferred rows and candidates collect in warp-private buffers and leave 32 or more at a time
+//       (one global atomic per batch).
+//   score_deferred_kernel  scores the deferred list with the tail-sum machinery of bbk_pvalues (bdtrc's case analysis,
+//       upper-tail sum as a resumable state, saddle-point form outside the series' range) and patches p in place - a few
+//       per cent of the rows, so the 8-byte scattered stores cost nothing next to the stream.
+//   score_guard_kernel  (after the fit, before the two) checks what the count <= 0 shortcut assumes about the spline
+//       (0 <= splineY, 16 max(splineY) <= 1); if that fails BbkScoreState.exact is raised and every in-range row goes
+//       through its prior, so the result is exact in every case.
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr int ST_WROWS = 256;                      // rows of a warp tile: a lane owns two groups of four
+constexpr int ST_CTAS_PER_SM = 3;
+constexpr int ST_BUF = 64;                         // warp-private output buffers: flushed as soon as they hold 32
+constexpr int SMALL_C = 8;                         // counts up to here are scored through the lower tail (count - 1 terms)
+constexpr double LOWER_MIN_P = 1e-4;               // below this the lower-tail form has lost digits: deferred
+constexpr double LEAN_MAX_PRIOR = 9.765625e-4;     // 2^-10: ln(1-q) and q/(1-q) as short series
+constexpr double BIAS_FLAG_MAX = 4.0;              // bias values in [0, 4] (and absent loci) carry no flag bit
+constexpr int ST_HBASE = 959 * 2;                  // CTA-local histogram: buckets of p >= 2^-64, the rest goes straight to global
+constexpr int ST_HBINS = 128;
+constexpr int HI_ONE = 0x3ff00000, HI_NAN = 0x7ff80000;   // high words of 1.0 and of the one NaN this kernel writes
+static_assert(BBK_TILE_ROWS == ST_WARPS * ST_WROWS, "BBK_TILE_ROWS is what one CTA has in flight per stage");
+static_assert(ST_HBASE + ST_HBINS == 2046, "the local histogram ends with the bucket below 1.0");
+
+struct StWarp {                                    // one warp's shared memory
+    int m1[2][ST_WROWS];                           // mid1; after decode: low word of p (non-listed rows) / still mid1 (listed rows) / after its round: low word of p
+    int m2[2][ST_WROWS];                           // mid2; high word likewise
+    int cnt[2][ST_WROWS];
+    unsigned long long c_key[ST_BUF]; unsigned c_row[ST_BUF];                     // candidates on their way out
+    unsigned long long d_prior[ST_BUF]; unsigned d_row[ST_BUF]; int d_cnt[ST_BUF];  // deferred rows on their way out
+    unsigned char list[ST_WROWS];                  // slots of the rows that need arithmetic
+    unsigned long long full[2];                    // mbarriers: the stage's records have landed
+};
+
+struct StShared {
+    StWarp w[ST_WARPS];
+    unsigned hist[ST_HBINS];
+};
+
+struct StParams {
+    const int* mid1; const int* mid2; const int* count; long long n_pairs;
+    int shard_chrom; long long min_dist, max_dist; FastDiv div;
+    const BbkFitResult* fit; const double* spline_y;
+    const double* bias; const long long* chrom_base; const long long* mid0; int n_chrom; const unsigned* flags;
+    long long out_base; double* p; double* q; long long* p_hist;
+    unsigned long long* c_keys; unsigned* c_idx; long long c_cap;
+    unsigned* d_row; int* d_cnt; double* d_prior; long long d_cap;
+    BbkScoreState* st;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (TMA unit, no registers), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// the records of warp tile `wt` into stage `stage` (one lane): whole groups of four by bulk copy, a shard's last 1..3 by hand
+__device__ __forceinline__ void st_issue_tile(StWarp& ws, const StParams& Q, long long wt, int stage) {
+    const long long r0 = wt * ST_WROWS;
+    const long long left = Q.n_pairs - r0;
+    const int rows = left < ST_WROWS ? (int)left : ST_WROWS;
+    const int r4 = rows & ~3;
+    for (int e = r4; e < rows; ++e) {
+        ws.m1[stage][e] = Q.mid1[r0 + e]; ws.m2[stage][e] = Q.mid2[r0 + e]; ws.cnt[stage][e] = Q.count[r0 + e];
+    }
+    if (r4) {
+        const unsigned bytes = (unsigned)r4 * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the stage's last readers (generic proxy) are done
+        mbar_arrive_expect_tx(&ws.full[stage], 3u * bytes);
+        bulk_g2s(ws.m1[stage], Q.mid1 + r0, bytes, &ws.full[stage]);
+        bulk_g2s(ws.m2[stage], Q.mid2 + r0, bytes, &ws.full[stage]);
+        bulk_g2s(ws.cnt[stage], Q.count + r0, bytes, &ws.full[stage]);
+    } else {
+        mbar_arrive(&ws.full[stage]);
+    }
+}
+
+// biasDic[chr][mid] (default 1.0) for a shard whose table does not fit the 32-bit path: 64-bit arithmetic, rare
+__device__ __noinline__ double st_bias_wide(const double* tab, long long nloc, long long mid0, long long R, int mid) {
+    const long long off = (long long)mid - mid0;
+    if (off < 0 || off % R) return 1.0;
+    const long long idx = off / R;
+    if (idx >= nloc) return 1.0;
+    const double v = __ldg(tab + idx);
+    return isnan(v) ? 1.0 : v;
+}
+
+// the shard's bias row as the 32-bit path sees it
+struct StBias {
+    const double* tab; const unsigned* flg;        // flg == nullptr: no flag lookups (no table for this chromosome, or the wide path)
+    unsigned mid0u, spanu, fbit0;
+    long long nloc, mid0;
+    bool wide;                                     // the table does not fit the 32-bit path
+};
+
+// the flag bit of a locus (bias < 0 or > 4); loci outside the table have none.  An off-grid locus reads its floor entry's bit:
+// at worst the row takes the exact path for nothing.
+__device__ __forceinline__ bool st_flagged(const StBias& B, const FastDiv& div, int mid) {
+    const unsigned o = (unsigned)mid - B.mid0u;
+    if (o >= B.spanu) return false;
+    const unsigned b = fastdiv31(o, div) + B.fbit0;
+    return (__ldg(B.flg + (b >> 5)) >> (b & 31)) & 1u;
+}
+
+// everything a list entry needs before its arithmetic: loaded one round ahead
+struct StEntry { int slot, c; double y, v1, v2; bool ok1, ok2, active; };
+
+template <bool HAS_BIAS>
+__device__ __forceinline__ StEntry st_fetch(const StParams& Q, const StBias& B, const int* s_m1, const int* s_m2, const int* s_c,
+                                            const unsigned char* s_list, int kk, int n_list, int k0R, int L) {
+    StEntry E;
+    E.active = kk < n_list;
+    E.slot = E.active ? (int)s_list[kk] : 0;
+    const int m1 = s_m1[E.slot], m2 = s_m2[E.slot];
+    E.c = s_c[E.slot];
+    const unsigned R = Q.div.R;
+    const int t = (int)((unsigned)m2 - (unsigned)m1) - k0R;                                  // fithic.py:429-430 in closed form
+    int i = 0;
+    if (t > 0) { const unsigned qd = fastdiv31((unsigned)t + R - 1u, Q.div); i = qd > (unsigned)(L - 1) ? L - 1 : (int)qd; }
+    E.y = 0.0; E.v1 = 1.0; E.v2 = 1.0; E.ok1 = false; E.ok2 = false;
+    if (E.active) {
+        E.y = __ldg(Q.spline_y + i);
+        if (HAS_BIAS) {
+            if (B.wide) {
+                E.v1 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)R, m1); E.v2 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)R, m2);
+                E.ok1 = true; E.ok2 = true;
+            } else if (B.spanu) {
+                const unsigned o1 = (unsigned)m1 - B.mid0u, o2 = (unsigned)m2 - B.mid0u;
+                const unsigned x1 = fastdiv31(o1 & 0x7fffffffu, Q.div), x2 = fastdiv31(o2 & 0x7fffffffu, Q.div);
+                E.ok1 = o1 < B.spanu && x1 * R == o1; E.ok2 = o2 < B.spanu && x2 * R == o2;   // fithic.py:418-425: on the grid, inside the table
+                E.v1 = __ldg(B.tab + (E.ok1 ? x1 : 0u)); E.v2 = __ldg(B.tab + (E.ok2 ? x2 : 0u));
+            }
+        }
+    }
+    return E;
+}
+
+// a warp-private buffer's content to its global list: one reservation
+__device__ __forceinline__ void st_flush_cands(StWarp& ws, const StParams& Q, int lane, int& n) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd((unsigned long long*)&Q.st->n_cand, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < n; i += 32) {
+        const unsigned long long at = base + i;
+        if ((long long)at < Q.c_cap) { Q.c_keys[at] = ws.c_key[i]; Q.c_idx[at] = ws.c_row[i]; } else Q.st->cand_overflow = 1;
+    }
+    n = 0;
+    __syncwarp();
+}
+__device__ __forceinline__ void st_flush_deferred(StWarp& ws, const StParams& Q, int lane, int& n) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd((unsigned long long*)&Q.st->n_list, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < n; i += 32) {
+        const unsigned long long at = base + i;
+        if ((long long)at < Q.d_cap) { Q.d_row[at] = ws.d_row[i]; Q.d_cnt[at] = ws.d_cnt[i]; Q.d_prior[at] = __longlong_as_double((long long)ws.d_prior[i]); }
+        else Q.st->overflow = 1;
+    }
+    n = 0;
+    __syncwarp();
+}
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel(const __grid_constant__ StParams Q) {
+    extern __shared__ __align__(128) unsigned char st_raw[];
+    StShared& sh = *reinterpret_cast<StShared*>(st_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    StWarp& ws = sh.w[warp];
+    const long long S = Q.fit->S;
+    const int k0 = Q.fit->k0, L = Q.fit->L;
+    if (!(Q.fit->status == BBK_FIT_OK && L > 0)) return;                       // failed fit: the host raises, p is never read
+    const bool exact = Q.st->exact != 0;
+    const bool all_defer = S < 64;                                             // tiny S: bdtrc's k >= n cases stay with the general code
+    const double dn = (double)S;
+    const unsigned R = Q.div.R;
+    const int k0R = k0 * (int)R;                                               // k0 * R <= max_dist < 2^31
+    const unsigned lo_u = (unsigned)Q.min_dist, span_u = (unsigned)(Q.max_dist - Q.min_dist);
+    const long long n = Q.n_pairs;
+    const long long n_wt = (n + ST_WROWS - 1) / ST_WROWS;
+    const long long gw = (long long)blockIdx.x * ST_WARPS + warp, nw = (long long)gridDim.x * ST_WARPS;
+    StBias B;
+    B.tab = nullptr; B.flg = nullptr; B.mid0u = 0; B.spanu = 0; B.fbit0 = 0; B.nloc = 0; B.mid0 = 0; B.wide = false;
+    if (HAS_BIAS && Q.shard_chrom >= 0 && Q.shard_chrom < Q.n_chrom) {
+        const long long base = __ldg(&Q.chrom_base[Q.shard_chrom]);
+        B.nloc = __ldg(&Q.chrom_base[Q.shard_chrom + 1]) - base;
+        B.mid0 = __ldg(&Q.mid0[Q.shard_chrom]);
+        B.tab = Q.bias + base;
+        if (B.nloc > 0) {
+            const unsigned long long span = (unsigned long long)B.nloc * R;
+            if (B.mid0 >= 0 && B.mid0 < (1ll << 31) && span < (1ull << 31) && base + B.nloc < (1ll << 32)) {
+                B.mid0u = (unsigned)B.mid0; B.spanu = (unsigned)span;
+                B.flg = Q.flags + (base >> 5); B.fbit0 = (unsigned)(base & 31);
+            } else B.wide = true;
+        }
+    }
+    const bool zero_slow = exact || B.wide;                                    // count <= 0 rows go through their prior
+    for (int i = tid; i < ST_HBINS; i += ST_THREADS) sh.hist[i] = 0;
+    if (lane == 0) {
+        mbar_init(&ws.full[0], 1); mbar_init(&ws.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (lane == 0) {
+        if (gw < n_wt) st_issue_tile(ws, Q, gw, 0);
+        if (gw + nw < n_wt) st_issue_tile(ws, Q, gw + nw, 1);
+    }
+    unsigned ones = 0, nans = 0;
+    int n_cb = 0, n_db = 0;                                                    // entries in the warp's two output buffers (warp-uniform)
+    const unsigned lt = (1u << lane) - 1;
+
+    for (int k = 0; ; ++k) {
+        const long long wt = gw + (long long)k * nw;
+        if (wt >= n_wt) break;
+        const int stage = k & 1;
+        const unsigned parity = (unsigned)(k >> 1) & 1u;
+        const long long left = n - wt * ST_WROWS;
+        const int wrows = left < ST_WROWS ? (int)left : ST_WROWS;
+        int* const s_m1 = ws.m1[stage];
+        int* const s_m2 = ws.m2[stage];
+        const int* const s_c = ws.cnt[stage];
+        const unsigned row0 = (unsigned)(Q.out_base + wt * ST_WROWS);
+        if (!mbar_try_wait(&ws.full[stage], parity)) {
+            while (!mbar_try_wait(&ws.full[stage], parity)) __nanosleep(64);
+        }
+        // ---- decode: class of every row (0 p = 1.0, 1 NaN, 2 count <= 1 list, 3 small counts, 4 the rest, 7 no row); the result of
+        // the rows that need no arithmetic replaces them in the tile
+        unsigned codes = 0, nA = 0, nB = 0, nC = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rb = u * 128 + lane * 4;
+            const int4 a1 = *reinterpret_cast<const int4*>(s_m1 + rb);
+            const int4 a2 = *reinterpret_cast<const int4*>(s_m2 + rb);
+            const int4 ac = *reinterpret_cast<const int4*>(s_c + rb);
+            const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
+            int code[4];
+            bool any_zero = false;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned ud = (unsigned)m2s[e] - (unsigned)m1s[e];                            // fithic.py:416
+                const bool inr = m2s[e] >= m1s[e] && (ud - lo_u) <= span_u;                          // fithic.py:427 (inclusive on both sides)
+                const int c = cs[e];
+                int cd = c == 1 ? 2 : (c <= SMALL_C ? 3 : 4);
+                if (c <= 0) cd = zero_slow ? 2 : 0;
+                if (!inr) cd = 1;
+                if (rb + e >= wrows) cd = 7;
+                code[e] = cd;
+                any_zero |= cd == 0;
+            }
+            if (HAS_BIAS && B.flg != nullptr && any_zero) {
+                // count <= 0: p = 1.0 unless a locus is flagged (bias < 0 or > 4); then the row goes through its prior.
+                // Row-major input: the four rows share their first locus and their second loci are neighbours on the grid -
+                // one division, and the four bits come out of two words.
+                const bool regular = (a1.x == a1.y) & (a1.y == a1.z) & (a1.z == a1.w) & ((unsigned)(a2.y - a2.x) == R) &
+                                     ((unsigned)(a2.z - a2.y) == R) & ((unsigned)(a2.w - a2.z) == R);
+                const unsigned o2 = (unsigned)a2.x - B.mid0u;
+                if (regular && o2 < B.spanu && o2 + 3u * R < B.spanu) {
+                    const unsigned b = fastdiv31(o2, Q.div) + B.fbit0;
+                    const unsigned w0 = __ldg(B.flg + (b >> 5)), w1 = __ldg(B.flg + (b >> 5) + 1);   // (the bit map has a spare word at its end)
+                    unsigned bits = __funnelshift_r(w0, w1, b & 31) & 0xfu;
+                    if (st_flagged(B, Q.div, a1.x)) bits = 0xfu;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (code[e] == 0 && ((bits >> e) & 1u)) code[e] = 2;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (code[e] == 0 && (st_flagged(B, Q.div, m1s[e]) || st_flagged(B, Q.div, m2s[e]))) code[e] = 2;
+                }
+            }
+            int4 lo4 = a1, hi4 = a2;
+            int* los = reinterpret_cast<int*>(&lo4);
+            int* his = reinterpret_cast<int*>(&hi4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int cd = code[e];
+                const bool fin = cd < 2 || cd == 7;
+                los[e] = fin ? 0 : los[e];
+                his[e] = fin ? (cd == 0 ? HI_ONE : HI_NAN) : his[e];
+                ones += cd == 0; nans += cd == 1;
+                codes |= (unsigned)cd << (3 * (u * 4 + e));
+                nA += cd == 2; nB += cd == 3; nC += cd == 4;
+            }
+            *reinterpret_cast<int4*>(s_m1 + rb) = lo4;
+            *reinterpret_cast<int4*>(s_m2 + rb) = hi4;
+        }
+        // ---- the warp's list: count <= 1 rows, then the small counts, then the rest
+        const unsigned packed = nA | (nB << 10) | (nC << 20);
+        unsigned inc = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+        const unsigned tA = tot & 1023u, tB = (tot >> 10) & 1023u, tC = tot >> 20;
+        const unsigned exc = inc - packed;
+        unsigned at_a = exc & 1023u, at_b = tA + ((exc >> 10) & 1023u), at_c = tA + tB + (exc >> 20);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const unsigned cd = (codes >> (3 * s)) & 7u;
+            const unsigned is_a = cd == 2, is_b = cd == 3, is_c = cd == 4;
+            const unsigned pos = is_a ? at_a : (is_b ? at_b : at_c);
+            at_a += is_a; at_b += is_b; at_c += is_c;
+            if (is_a | is_b | is_c) ws.list[pos] = (unsigned char)((s >> 2) * 128 + lane * 4 + (s & 3));
+        }
+        __syncwarp();
+        // ---- rounds of 32 entries; the next round's gathers are in flight while one computes
+        const int n_list = (int)(tA + tB + tC);
+        StEntry E = st_fetch<HAS_BIAS>(Q, B, s_m1, s_m2, s_c, ws.list, lane, n_list, k0R, L);
+        for (int kb = 0; kb < n_list; kb += 32) {
+            const StEntry C = E;
+            if (kb + 32 < n_list) E = st_fetch<HAS_BIAS>(Q, B, s_m1, s_m2, s_c, ws.list, kb + 32 + lane, n_list, k0R, L);
+            const bool active = C.active;
+            const int c = C.c;
+            double prior = C.y;
+            if (HAS_BIAS) prior = prior * (bias_value(C.v1, C.ok1) * bias_value(C.v2, C.ok2));      // fithic.py:431
+            const bool valid = active && prior >= 0.0 && prior <= 1.0;                          // bdtrc: NaN otherwise, before anything else
+            double out = __hiloint2double(HI_NAN, 0);
+            if (valid && c <= 0) out = 1.0;                                                     // k < 0 -> 1
+            const bool lean = valid && c >= 1 && c <= SMALL_C && !all_defer && prior > 0.0 && prior < LEAN_MAX_PRIOR;
+            bool defer = valid && c >= 1 && !lean;
+            const int cmax = __reduce_max_sync(0xffffffffu, lean ? c : 0);
+            if (cmax > 0) {
+                // P(X >= c) = 1 - pmf(0) (1 + r1 + r1 r2 + ...), c - 1 terms, r_i = (S - i + 1) q / (i (1 - q));
+                // count == 1 is the same form without terms (bdtrc's 1 - (1-q)^S)
+                const double q = lean ? prior : 0.0;
+                const double l1m = -q * (1.0 + q * (0.5 + q * (1.0 / 3.0 + q * (0.25 + q * (0.2 + q * (1.0 / 6.0))))));
+                const double u = dn * l1m;
+                const double e0 = exp(u);
+                double sum = 1.0;
+                if (cmax > 1) {
+                    const double qr = q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q))))));   // q / (1 - q)
+                    double a = dn * qr, t = 1.0;
+#pragma unroll
+                    for (int i = 1; i < SMALL_C; ++i) {
+                        if (i < cmax) {                                      // warp-uniform
+                            if (i < c) { t *= a * (1.0 / (double)i); sum += t; a -= qr; }
+                        }
+                    }
+                }
+                double pc = fma(-e0, sum, 1.0);
+                const bool tiny = lean && c == 1 && u > -0.0078125;          // 1 - e^u loses digits: -expm1(u) by its series
+                if (__any_sync(0xffffffffu, tiny)) {
+                    if (tiny) pc = -u * (1.0 + u * 0.5 * (1.0 + u * (1.0 / 3.0) * (1.0 + u * 0.25 * (1.0 + u * 0.2 * (1.0 + u * (1.0 / 6.0) * (1.0 + u * (1.0 / 7.0)))))));
+                }
+                if (lean) {
+                    if (c >= 2 && !(pc >= LOWER_MIN_P)) defer = true;        // digits lost (or the row is significant): the upper sum
+                    else out = pc;
+                }
+            }
+            if (defer) out = 0.5;                                            // placeholder: a number, so that q is pre-filled with 1.0
+            const int hi = __double2hiint(out), lo = __double2loint(out);
+            if (active) { s_m1[C.slot] = lo; s_m2[C.slot] = hi; }
+            const bool fin = active && !defer;
+            ones += fin && hi == HI_ONE && lo == 0;
+            nans += fin && hi == HI_NAN;
+            const bool scored = fin && out < 1.0;                            // (false for NaN)
+            if (Q.p_hist && scored) {
+                const unsigned b = ((unsigned)hi >> 19) & (BBK_PHIST_BINS - 1);
+                if (b >= (unsigned)ST_HBASE) atomicAdd(&sh.hist[b - ST_HBASE], 1u);
+                else atomicAdd((unsigned long long*)&Q.p_hist[b], 1ull);
+            }
+            const unsigned row = row0 + (unsigned)C.slot;
+            if (Q.c_keys) {
+                const bool cand = scored && out < BBK_SMALL_P;
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    if (cand) { const int at = n_cb + __popc(m & lt); ws.c_key[at] = bbk_key_of(out); ws.c_row[at] = row; }
+                    n_cb += __popc(m);
+                    __syncwarp();
+                    if (n_cb >= 32) st_flush_cands(ws, Q, lane, n_cb);
+                }
+            }
+            {
+                const unsigned m = __ballot_sync(0xffffffffu, defer);
+                if (m) {
+                    if (defer) { const int at = n_db + __popc(m & lt); ws.d_prior[at] = (unsigned long long)__double_as_longlong(prior); ws.d_row[at] = row; ws.d_cnt[at] = c; }
+                    n_db += __popc(m);
+                    __syncwarp();
+                    if (n_db >= 32) st_flush_deferred(ws, Q, lane, n_db);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- the warp's rows out: coalesced 128-bit stores of p and of q = 1.0 / NaN
+        const int wrows4 = (wrows + 3) & ~3;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rb = u * 128 + lane * 4;
+            if (rb < wrows4) {
+                const int4 lo = *reinterpret_cast<const int4*>(s_m1 + rb);
+                const int4 hi = *reinterpret_cast<const int4*>(s_m2 + rb);
+                double2* pv2 = reinterpret_cast<double2*>(Q.p + row0 + rb);
+                st_stream_double2(pv2, make_double2(__hiloint2double(hi.x, lo.x), __hiloint2double(hi.y, lo.y)));
+                st_stream_double2(pv2 + 1, make_double2(__hiloint2double(hi.z, lo.z), __hiloint2double(hi.w, lo.w)));
+                if (Q.q) {
+                    double2* qv2 = reinterpret_cast<double2*>(Q.q + row0 + rb);
+                    st_stream_double2(qv2, make_double2(__hiloint2double(hi.x == HI_NAN ? HI_NAN : HI_ONE, 0), __hiloint2double(hi.y == HI_NAN ? HI_NAN : HI_ONE, 0)));
+                    st_stream_double2(qv2 + 1, make_double2(__hiloint2double(hi.z == HI_NAN ? HI_NAN : HI_ONE, 0), __hiloint2double(hi.w == HI_NAN ? HI_NAN : HI_ONE, 0)));
+                }
+            }
+        }
+        // ---- the stage is free: the tile after next
+        __syncwarp();
+        if (lane == 0 && wt + 2 * nw < n_wt) st_issue_tile(ws, Q, wt + 2 * nw, stage);
+    }
+    if (n_cb) st_flush_cands(ws, Q, lane, n_cb);
+    if (n_db) st_flush_deferred(ws, Q, lane, n_db);
+    if (Q.p_hist) {
+        __syncthreads();
+        for (int i = tid; i < ST_HBINS; i += ST_THREADS) {
+            const unsigned v = sh.hist[i];
+            if (v) atomicAdd((unsigned long long*)&Q.p_hist[ST_HBASE + i], (unsigned long long)v);
+        }
+        const unsigned o = __reduce_add_sync(0xffffffffu, ones), zn = __reduce_add_sync(0xffffffffu, nans);
+        if (lane == 0) {
+            if (o) atomicAdd((unsigned long long*)&Q.p_hist[BBK_PHIST_BINS], (unsigned long long)o);
+            if (zn) atomicAdd((unsigned long long*)&Q.p_hist[BBK_PHIST_BINS + 1], (unsigned long long)zn);
+        }
+    }
+}
+
+// one flag bit per bias table entry: the value is < 0 or > 4 (NaN = absent locus = 1.0 carries none)
+__global__ void bias_flags_kernel(const double* bias, long long n, unsigned* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool f = false;
+    if (i < n) { const double v = bias[i]; f = v < 0.0 || v > BIAS_FLAG_MAX; }
+    const unsigned w = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && i < n) flags[i >> 5] = w;
+}
+
+// after the fit: may the count <= 0 shortcut stand?
+__global__ void __launch_bounds__(1024) score_guard_kernel(const BbkFitResult* fit, const double* spline_y, BbkScoreState* st) {
+    __shared__ double s_lo[32], s_hi[32];
+    __shared__ int s_nan[32];
+    const int L = fit->status == BBK_FIT_OK ? fit->L : 0;
+    double lo = INFINITY, hi = -INFINITY;
+    int bad = 0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const double v = spline_y[i];
+        if (isnan(v)) bad = 1;
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; s_nan[threadIdx.x >> 5] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); bad |= s_nan[w]; }
+        // count <= 0 rows whose loci carry no flag have 0 <= b1*b2 <= 16 and are taken as p = 1.0: right iff every
+        // prior splineY * b1*b2 lies in [0, 1]
+        const bool ok = L > 0 && !bad && lo >= 0.0 && hi * (BIAS_FLAG_MAX * BIAS_FLAG_MAX) <= 1.0;
+        if (L > 0 && !ok) st->exact = 1;
+    }
+}
+
+struct DfParams {
+    const unsigned* d_row; const int* d_cnt; const double* d_prior; long long d_cap;
+    const BbkFitResult* fit;
+    double* p; double* q; long long* p_hist;
+    unsigned long long* c_keys; unsigned* c_idx; long long c_cap;
+    BbkScoreState* st;
+};
+
+struct DfShared {
+    double rcp[RCP_TAB];
+    double lfact[LF_TAB];
+    unsigned hist[BBK_PHIST_BINS];
+};
+
+__global__ void __launch_bounds__(PV_THREADS, 2) score_deferred_kernel(DfParams D) {
+    extern __shared__ __align__(16) unsigned char df_raw[];
+    DfShared& sh = *reinterpret_cast<DfShared*>(df_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!(D.fit->status == BBK_FIT_OK && D.fit->L > 0)) return;
+    if (D.st->overflow) return;                                                 // the host repeats the pass with a larger list
+    const long long n = (long long)D.st->n_list;
+    if (n == 0) return;
+    const long long S = D.fit->S;
+    for (int j = tid; j < RCP_TAB; j += PV_THREADS) sh.rcp[j] = g_rcp[j];
+    for (int j = tid; j < LF_TAB; j += PV_THREADS) sh.lfact[j] = g_lfact[j];
+    for (int i = tid; i < BBK_PHIST_BINS; i += PV_THREADS) sh.hist[i] = 0;
+    __syncthreads();
+    TailConst K;
+    K.dn = (double)S;
+    K.inv_n = S > 0 ? 1.0 / K.dn : 0.0;
+    K.c_max = 1e-4 * K.dn;
+    K.c5_max = 2e-11 * (K.dn * K.dn) * (K.dn * K.dn);
+    const bool s_fits = S <= 0x7fffffffll;
+    const int s_cap = s_fits ? (int)S : 0x7fffffff;
+    unsigned ones = 0, nans = 0;
+    const long long rounds = (n + 31) >> 5;
+    for (long long r = (long long)blockIdx.x * PV_WARPS + warp; r < rounds; r += (long long)gridDim.x * PV_WARPS) {
+        const long long k = (r << 5) + lane;
+        const bool active = k < n;
+        unsigned row = 0; int c = 0; double prior = 0.0;
+        if (active) { row = D.d_row[k]; c = D.d_cnt[k]; prior = D.d_prior[k]; }
+        int cls = 0;
+        double out = __longlong_as_double(0x7ff8000000000000ll);
+        if (active) cls = bdtrc_class(c, s_cap, s_fits, prior, &out);
+        const bool closed = cls == 1, upper = cls == 2;
+        if (__any_sync(0xffffffffu, closed)) { if (closed) out = -expm1(K.dn * log1m(prior)); }    // bdtrc's closed form for k == 0
+        if (__any_sync(0xffffffffu, upper)) {
+            TailState T;
+            T.lp = 0.0; T.term = 0.0; T.sum = 1.0; T.a = 0.0; T.step = 0.0; T.j = 0;
+            bool running = false, fast = false;
+            if (upper) {
+                fast = fast_ok(c, K);
+                if (fast) { tail_setup(c, prior, K, sh.lfact, T); running = true; }
+                else out = tail_general(c, S, prior);
+            }
+            unsigned rmask = __ballot_sync(0xffffffffu, running);
+            while (rmask) {
+                if (running) {
+                    const bool exhausted = tail_terms16(T, K, sh.rcp);
+                    running = !(exhausted || T.term < TAIL_EPS * T.sum);
+                }
+                rmask = __ballot_sync(0xffffffffu, running);
+            }
+            if (fast) out = tail_finish(T.lp, T.sum);
+        }
+        const double pv = finish_p(out);                                        // fithic.py:434
+        if (active) {
+            D.p[row] = pv;
+            if (D.q && isnan(pv)) D.q[row] = pv;                                // (the stream pre-filled 1.0)
+            if (D.p_hist) hist_p(sh.hist, pv, ones, nans);
+        }
+        if (D.c_keys) {
+            const bool cand = active && pv < BBK_SMALL_P;
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd((unsigned long long*)&D.st->n_cand, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cand) {
+                    const unsigned long long at = base + __popc(m & ((1u << lane) - 1));
+                    if ((long long)at < D.c_cap) { D.c_keys[at] = bbk_key_of(pv); D.c_idx[at] = row; }
+                    else D.st->cand_overflow = 1;
+                }
+            }
+        }
+    }
+    if (D.p_hist) {
+        __syncthreads();
+        for (int i = tid; i < BBK_PHIST_BINS; i += PV_THREADS) {
+            const unsigned v = sh.hist[i];
+            if (v) atomicAdd((unsigned long long*)&D.p_hist[i], (unsigned long long)v);
+        }
+        const unsigned o = __reduce_add_sync(0xffffffffu, ones), zn = __reduce_add_sync(0xffffffffu, nans);
+        if (lane == 0) {
+            if (o) atomicAdd((unsigned long long*)&D.p_hist[BBK_PHIST_BINS], (unsigned long long)o);
+            if (zn) atomicAdd((unsigned long long*)&D.p_hist[BBK_PHIST_BINS + 1], (unsigned long long)zn);
+        }
+    }
+}
+
+__global__ void score_begin_kernel(BbkScoreState* st, long long* p_hist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p_hist && i < BBK_PHIST_LEN) p_hist[i] = 0;
+    if (i == 0) { st->n_list = 0; st->n_cand = 0; st->overflow = 0; st->cand_overflow = 0; st->exact = 0; st->reserved = 0; }
+}

@@ -69,8 +69,9 @@ class FithicContactMap(object):
         if col is None:
             raise ValueError
         r = self.resolution
-        i = ((self.map[:, 0] - r / 2) / r).astype(np.int64)
-        j = ((self.map[:, 1] - r / 2) / r).astype(np.int64)
+        h = int(r) // 2                               # the reference's Python-2 `resolution / 2` floors
+        i = ((self.map[:, 0] - h) / r).astype(np.int64)
+        j = ((self.map[:, 1] - h) / r).astype(np.int64)
         d = int(n_bins) if n_bins is not None else (int(max(i.max(), j.max())) + 1 if len(i) else 0)
         matrix = np.zeros((d, d))
         matrix[i, j] = self.map[:, col]          # later rows win, like the reference's loop

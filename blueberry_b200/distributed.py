@@ -9,8 +9,8 @@ gathers the p-values of all chromosomes, utils.py:31-90 -> blueberry.pyx:40-75) 
 p histogram and one fixed-capacity all-gather of the few candidate keys.  Nothing between the first and the last kernel
 of a pass touches the host.
 
-    K1 per shard -> [all-reduce] -> fit (one CTA)  ||  K4a classify per shard (side stream)
-    -> guard -> K4b scores the tiles from their work lists -> K5 q-values (local, or genome-wide across ranks)
+    K1 per shard -> [all-reduce] -> fit (one CTA) -> guard -> K4 per shard (one streaming pass over bulk-staged tiles)
+    -> K4 patch pass over the deferred rows -> K5 q-values (local, or genome-wide across ranks)
 
 GenomePass is that sequence; plan_shards / shard_rows decide who holds what.
 """
@@ -96,20 +96,19 @@ class GenomePass(object):
         self.q_values = bool(q_values)
         self.gather_cap = int(gather_capacity)
         R = engine.R
-        # the split K4 needs every in-range distance (and distance + R) to fit 31 bits; otherwise the direct kernel runs
+        # the streaming K4 needs every in-range distance (and distance + R) to fit 31 bits; otherwise the direct kernel runs
         self.listed = 0 <= engine.min_dist <= engine.max_dist and engine.max_dist + R < (1 << 31)
+        self._range_ok = self.listed
         self.shards = []
         self.offsets = []
         self.rows = 0
         self.p = self.q = None
-        self.side = torch.cuda.Stream(self.device)
-        self.ev_hist = torch.cuda.Event()
-        self.ev_cls = torch.cuda.Event()
         dev = self.device
         self.score_state = torch.zeros(ctypes.sizeof(_lib.ScoreState), dtype=torch.uint8, device=dev)
         self.bh_state = torch.zeros(4, dtype=torch.int64, device=dev)
         self.q_ones = torch.zeros(2, dtype=torch.float64, device=dev)
         self.gather_overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.force_exact = False        # tests: raise BbkScoreState.exact whatever the guard says
         self._host = torch.zeros(engine.fit_result.numel() + self.score_state.numel() + 8, dtype=torch.uint8).pin_memory()
         self.n_tests = -1
 
@@ -131,25 +130,20 @@ class GenomePass(object):
                 self.p[o + sh.n:o + ((sh.n + 3) & ~3)] = float("nan")
                 if self.q is not None:
                     self.q[o + sh.n:o + ((sh.n + 3) & ~3)] = float("nan")
+        # shards with chromosome columns (mixed rows) go through the direct kernel
+        mixed = any(sh.chr1 is not None for sh in self.shards)
+        if mixed and self.world > 1:
+            raise ValueError("multi-GPU passes take one-chromosome shards (no chromosome columns)")
+        self.listed = self._range_ok and not mixed
         if self.listed:
-            cap = int(list_capacity) if list_capacity else m
-            # tiles of TILE_ROWS rows, shard by shard (a shard's last tile may be partial)
-            self.tile_bases, nt = [], 0
-            for sh in self.shards:
-                self.tile_bases.append(nt)
-                nt += (sh.n + _lib.TILE_ROWS - 1) // _lib.TILE_ROWS
-            self.n_tiles = nt
-            have = getattr(self, "worklist", None)
-            if have is None or have.capacity < cap or list_capacity or have.tile_capacity < nt:
-                tcap = max(nt, 1)
+            # rows the streaming pass defers (large counts, significant rows): a few per cent; an overflow repeats the pass
+            cap = int(list_capacity) if list_capacity else min(m, max(1 << 20, m // 4))
+            have = getattr(self, "deferred", None)
+            if have is None or have.capacity < cap or list_capacity:
                 self.l_row = torch.empty(cap, dtype=torch.int32, device=dev)
                 self.l_cnt = torch.empty(cap, dtype=torch.int32, device=dev)
-                self.l_dist = torch.empty(cap, dtype=torch.int32, device=dev)
-                self.l_bb = torch.empty(cap, dtype=torch.float64, device=dev)
-                self.l_tiles = torch.zeros(tcap * 4, dtype=torch.int64, device=dev)               # 32-byte BbkTileDir records
-                self.l_bits = torch.zeros(tcap * (_lib.TILE_ROWS // 32), dtype=torch.int32, device=dev)
-                self.worklist = _lib.WorkList(self.l_row.data_ptr(), self.l_cnt.data_ptr(), self.l_dist.data_ptr(), self.l_bb.data_ptr(), cap,
-                                              self.l_tiles.data_ptr(), self.l_bits.data_ptr(), tcap)
+                self.l_prior = torch.empty(cap, dtype=torch.float64, device=dev)
+                self.deferred = _lib.DeferredList(self.l_row.data_ptr(), self.l_cnt.data_ptr(), self.l_prior.data_ptr(), cap)
             ccap = int(cand_capacity) if cand_capacity else min(m, max(1 << 20, m // 16))
             if getattr(self, "cands", None) is None or self.cands.capacity < ccap or cand_capacity:
                 self.c_keys = torch.empty(ccap, dtype=torch.int64, device=dev)
@@ -179,31 +173,43 @@ class GenomePass(object):
         return self.q[self.offsets[i]:self.offsets[i] + self.shards[i].n]
 
     # ------------------------------------------------------------------ the pass
-    def _classify(self, exact_only, st):
+    def _score(self, st, want_q=True):
+        """K4: the guard, one streaming pass per shard, the patch pass over the deferred rows."""
         eng, lib = self.eng, self.lib
         bias = ctypes.byref(eng.bias.struct) if eng.bias is not None else None
-        for sh, off, tb in zip(self.shards, self.offsets, self.tile_bases):
+        flags = _lib.ptr(eng.bias.flags) if eng.bias is not None else None
+        hist = _lib.ptr(eng.p_hist) if want_q else None
+        cands = ctypes.byref(self.cands) if want_q else None
+        q = _lib.ptr(self.q) if want_q else None
+        _lib.check(lib.bbk_score_guard(_lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), _lib.ptr(self.score_state), st), "bbk_score_guard")
+        eng.launches += 1
+        if self.force_exact:
+            self.score_state[24:28] = torch.tensor([1, 0, 0, 0], dtype=torch.uint8, device=self.device)     # BbkScoreState.exact
+        for sh, off in zip(self.shards, self.offsets):
             if sh.n == 0:
                 continue
-            _lib.check(lib.bbk_classify_pairs(_lib.ptr(sh.chr1), _lib.ptr(sh.chr2), _lib.ptr(sh.mid1), _lib.ptr(sh.mid2),
-                                              _lib.ptr(sh.count), sh.n, sh.chrom, eng.R, eng.min_dist, eng.max_dist, bias, off, tb,
-                                              ctypes.byref(self.worklist), _lib.ptr(self.score_state), 1 if exact_only else 0, st),
-                       "bbk_classify_pairs")
+            _lib.check(lib.bbk_score_pairs(_lib.ptr(sh.mid1), _lib.ptr(sh.mid2), _lib.ptr(sh.count), sh.n, sh.chrom, eng.R,
+                                           eng.min_dist, eng.max_dist, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), bias, flags,
+                                           off, _lib.ptr(self.p), q, hist, cands, ctypes.byref(self.deferred),
+                                           _lib.ptr(self.score_state), st), "bbk_score_pairs")
             eng.launches += 1
+        _lib.check(lib.bbk_score_deferred(ctypes.byref(self.deferred), _lib.ptr(eng.fit_result), _lib.ptr(self.p), q, hist, cands,
+                                          _lib.ptr(self.score_state), st), "bbk_score_deferred")
+        eng.launches += 1
 
     def enqueue(self, n_tests=-1, smoothing=None, marks=None):
-        """Enqueue the whole pass on the current stream (K4a on the side stream); no host synchronisation.
-        marks (optional dict): filled with CUDA events at the stage boundaries of the main stream (name -> event recorded
-        AFTER that stage) and the start / end of K4a on the side stream, for per-stage timing."""
+        """Enqueue the whole pass on the current stream; no host synchronisation.
+        marks (optional dict): filled with CUDA events at the stage boundaries (name -> event recorded AFTER that stage),
+        for per-stage timing."""
         import torch.distributed as dist
         eng, lib = self.eng, self.lib
         main = torch.cuda.current_stream(self.device)
         st = _lib.stream_ptr(main)
 
-        def mark(name, stream=None):
+        def mark(name):
             if marks is not None:
                 ev = torch.cuda.Event(enable_timing=True)
-                ev.record(stream if stream is not None else main)
+                ev.record(main)
                 marks[name] = ev
 
         self.n_tests = int(n_tests)
@@ -218,31 +224,13 @@ class GenomePass(object):
             eng.launches += 1
         eng.hist(self.shards)
         mark("hist")
-        if self.listed:
-            # K4a streams the records again while the all-reduce and the one-CTA fit kernel run
-            self.ev_hist.record(main)
-            self.side.wait_event(self.ev_hist)
-            with torch.cuda.stream(self.side):
-                mark("classify_start", self.side)
-                self._classify(False, _lib.stream_ptr(self.side))
-                mark("classify_end", self.side)
-                self.ev_cls.record(self.side)
         if self.world > 1:
             eng.allreduce_stats(self.group)
         mark("allreduce")
         eng.fit(smoothing)
         mark("fit")
         if self.listed:
-            main.wait_event(self.ev_cls)
-            mark("classify_wait")
-            _lib.check(lib.bbk_score_guard(_lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), _lib.ptr(self.score_state), st), "bbk_score_guard")
-            self._classify(True, st)
-            mark("guard")
-            _lib.check(lib.bbk_pvalues_listed(ctypes.byref(self.worklist), self.n_tiles, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), eng.R,
-                                              _lib.ptr(self.p), _lib.ptr(self.q), _lib.ptr(eng.p_hist) if want_q else None,
-                                              ctypes.byref(self.cands) if want_q else None, _lib.ptr(self.score_state), st),
-                       "bbk_pvalues_listed")
-            eng.launches += 2
+            self._score(st, want_q)
         else:
             for i, sh in enumerate(self.shards):
                 if sh.n:

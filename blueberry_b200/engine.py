@@ -75,6 +75,13 @@ class BiasTables(object):
         self.chrom_base = torch.from_numpy(base).to(device)
         self.mid0 = torch.from_numpy(np.asarray(mid0, dtype=np.int64)).to(device)
         self.struct = _lib.BiasTable(self.bias.data_ptr(), self.chrom_base.data_ptr(), self.mid0.data_ptr(), self.n_chrom)
+        # one flag bit per entry (value < 0 or > 4) for bbk_score_pairs: count <= 0 rows look at two bits, not two values
+        lib = _lib.load()
+        n = int(self.bias.numel())
+        self.flags = torch.zeros(int(lib.bbk_bias_flags_bytes(n)) // 4, dtype=torch.int32, device=device)
+        if n:
+            with torch.cuda.device(self.bias.device):
+                _lib.check(lib.bbk_bias_flags(_lib.ptr(self.bias), n, _lib.ptr(self.flags), _lib.stream_ptr()), "bbk_bias_flags")
 
 
 class PassEngine(object):

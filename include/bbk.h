@@ -181,77 +181,62 @@ int bbk_pvalues_bh(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* 
                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * K4 split around the fit                               replaces the same scoring loop, fithic.py:413-435
+ * K4 as one streaming pass + a patch pass       replaces the scoring loop of fit_spline, fithic.py:413-435
  *
- * Only the prior of a record needs the fit; its distance, the range test (:427), the bias product (:418-425, :431) and
- * its count do not, and a record with count <= 0 needs no arithmetic at all (p = 1.0, or NaN when bdtrc rejects the
- * prior).  bbk_classify_pairs therefore runs BEFORE / WHILE the one-CTA fit kernel runs (other stream): it streams the
- * records once and, per tile of BBK_TILE_ROWS consecutive rows, leaves one bit per row ("p is NaN": out of range, or
- * count <= 0 with a rejected prior) and one contiguous block of work-list entries (row, count, distance, bias1*bias2) for
- * the rows that need arithmetic - count == 1 first, then counts 2..8, then the rest - found through the tile directory.
- * bbk_score_guard (after the fit) checks what the count <= 0 rows assumed about the spline (0 < splineY,
- * 16 * max(splineY) <= 1); if that fails it raises BbkScoreState.exact and the second bbk_classify_pairs(exact_only = 1) -
- * always enqueued, returns at once otherwise - sends every in-range row to the list, so p is exact in every case.
- * bbk_pvalues_listed then scores tile by tile: same arithmetic and edge semantics as bbk_pvalues, all lanes on the same
- * branch, the tile's p column assembled in shared memory and written with full coalesced stores, q = 1.0 / NaN beside it.
- * It also fills d_p_hist and appends (key, row) of every p < 2^-5 to `cands` for bbk_bh_qvalues_listed.
- * Rows are positions in the rank-local p / q buffers: record i of a classify call is row out_base + i (out_base a multiple
- * of 4, rows < 2^32) and its tiles are tile_base .. tile_base + bbk_tiles_of(n_pairs) - 1, so several shards share one pair
- * of buffers, one list, one directory and one q-value step.  p / q need (n_pairs + 3) & ~3 rows per shard.
+ * Most records need no arithmetic (count <= 0: p = 1.0, or NaN when bdtrc rejects the prior), most of the rest have a count
+ * of 1..8 (a handful of FP64 operations in the lower-tail form), a few per cent need a long tail sum.  bbk_score_pairs
+ * streams the records of one shard once - tiles of BBK_TILE_ROWS rows staged in shared memory by bulk asynchronous copies -
+ * finishes everything but that last kind and writes EVERY row's p (and q = 1.0 / NaN, the value of a row that is not a
+ * q-value candidate) with full coalesced stores; the rows it cannot finish (count > 8, prior outside (0, 2^-10), a
+ * lower-tail result below 1e-4, S < 64) are appended as (row, count, prior) to `deferred` and get a placeholder.
+ * bbk_score_deferred then scores that list with the arithmetic and edge semantics of bbk_pvalues and patches p in place.
+ * Both fill d_p_hist and append (key, row) of every p < 2^-5 to `cands` for bbk_bh_qvalues_listed.
+ * count <= 0 rows are taken as p = 1.0 without looking at their prior when neither locus carries a flag bit
+ * (bbk_bias_flags: bias < 0 or > 4) - which is right iff 0 <= splineY and 16 max(splineY) <= 1; bbk_score_guard (after the
+ * fit) checks that and raises BbkScoreState.exact otherwise: every in-range row then goes through its prior.
+ * Rows are positions in the rank-local p / q buffers: record i of a call is row out_base + i (out_base a multiple of 4,
+ * rows < 2^32), so several shards share one pair of buffers, one deferred list, one candidate list and one q-value step.
+ * p / q need (n_pairs + 3) & ~3 rows per shard.  No chromosome columns: a shard is one chromosome (shard_chrom).
  * Needs 0 <= min_dist <= max_dist and max_dist + resolution < 2^31; otherwise use bbk_pvalues.
- * A list with capacity >= the number of records cannot overflow; a smaller one sets BbkScoreState.overflow when it does
- * (bbk_pvalues_listed then writes nothing; the caller repeats the pass with a larger list).
- * Sequence:  bbk_score_begin -> bbk_classify_pairs(..., 0) per shard  ||  K1, bbk_fit  ->  bbk_score_guard
- *            -> bbk_classify_pairs(..., 1) per shard -> bbk_pvalues_listed -> [bbk_bh_qvalues_listed]
+ * A deferred list with capacity >= the number of records cannot overflow; a smaller one sets BbkScoreState.overflow when
+ * it does (bbk_score_deferred then does nothing; the caller repeats the pass with a larger list).
+ * Sequence:  bbk_score_begin -> K1, bbk_fit -> bbk_score_guard -> bbk_score_pairs per shard -> bbk_score_deferred
+ *            -> [bbk_bh_qvalues_listed]
  * ------------------------------------------------------------------------------------------- */
 #define BBK_TILE_ROWS 2048
 typedef struct BbkScoreState {
-    uint64_t n_list;         /* work-list entries reserved so far */
-    uint64_t n_one;          /* entries with count == 1 */
-    uint64_t n_small;        /* entries with 2 <= count <= 8 (scored through the lower tail) */
-    uint64_t n_other;        /* the other entries */
-    uint64_t n_final;        /* rows classify finished (p = 1.0 or NaN without arithmetic) */
-    uint64_t n_cand;         /* candidates appended by bbk_pvalues_listed */
-    int32_t overflow;        /* the work list was too small */
+    uint64_t n_list;         /* deferred rows appended so far */
+    uint64_t n_cand;         /* candidates appended so far */
+    int32_t overflow;        /* the deferred list was too small */
     int32_t cand_overflow;   /* the candidate list was too small (the q-value step then takes its full pass: still exact) */
-    int32_t exact;           /* the guard failed: classification was repeated without the count <= 0 shortcut */
+    int32_t exact;           /* the guard failed: no count <= 0 shortcut in this pass */
     int32_t reserved;
 } BbkScoreState;
-typedef struct BbkTileDir {
-    uint64_t base;           /* first entry of the tile's block in the work list */
-    uint32_t n_one;          /* entries with count == 1 (first part of the block) */
-    uint32_t n_small;        /* entries with 2 <= count <= 8 (second part) */
-    uint32_t n_other;        /* the other entries (third part) */
-    uint32_t row_base;       /* rank-local row of the tile's first record */
-    uint32_t n_rows;         /* records in the tile (BBK_TILE_ROWS except in a shard's last tile) */
-    uint32_t pad;
-} BbkTileDir;
-typedef struct BbkWorkList {
-    uint32_t* d_row;
+typedef struct BbkDeferredList {
+    uint32_t* d_row;         /* rank-local row */
     int32_t* d_count;
-    int32_t* d_dist;         /* mid2 - mid1 */
-    double* d_bias_product;  /* bias1 * bias2 (1.0 without biases) */
+    double* d_prior;         /* newSplineY[i] * (bias1 * bias2), fithic.py:431 */
     int64_t capacity;        /* entries */
-    BbkTileDir* d_tiles;     /* [tile_capacity] */
-    uint32_t* d_nan_bits;    /* [tile_capacity * BBK_TILE_ROWS / 32], 16-byte aligned */
-    int64_t tile_capacity;
-} BbkWorkList;
+} BbkDeferredList;
 typedef struct BbkCandidates {
     uint64_t* d_keys;        /* order-preserving key of p */
-    uint32_t* d_rows;
+    uint32_t* d_rows;        /* rank-local row */
     int64_t capacity;
 } BbkCandidates;
 
-int64_t bbk_tiles_of(int64_t n_pairs);                                           /* ceil(n_pairs / BBK_TILE_ROWS) */
 int bbk_score_begin(BbkScoreState* d_state, int64_t* d_p_hist, void* stream);     /* zeroes the state and the histogram */
-int bbk_classify_pairs(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,
-                       const int32_t* d_count, int64_t n_pairs, int32_t shard_chrom, int64_t resolution, int64_t min_dist,
-                       int64_t max_dist, const BbkBiasTable* bias, int64_t out_base, int64_t tile_base,
-                       const BbkWorkList* list, BbkScoreState* d_state, int32_t exact_only, void* stream);
+/* one flag bit per entry of the concatenated bias table (bit j of word j / 32): value < 0 or > 4.  d_flags holds
+ * bbk_bias_flags_bytes(n_entries) bytes, ZEROED by the caller before bbk_bias_flags (the size includes a spare word). */
+size_t bbk_bias_flags_bytes(int64_t n_entries);
+int bbk_bias_flags(const double* d_bias, int64_t n_entries, uint32_t* d_flags, void* stream);
 int bbk_score_guard(const BbkFitResult* d_fit, const double* d_spline_y, BbkScoreState* d_state, void* stream);
-int bbk_pvalues_listed(const BbkWorkList* list, int64_t n_tiles, const BbkFitResult* d_fit, const double* d_spline_y,
-                       int64_t resolution, double* d_p, double* d_q, int64_t* d_p_hist, const BbkCandidates* cands,
-                       BbkScoreState* d_state, void* stream);
+int bbk_score_pairs(const int32_t* d_mid1, const int32_t* d_mid2, const int32_t* d_count, int64_t n_pairs,
+                    int32_t shard_chrom, int64_t resolution, int64_t min_dist, int64_t max_dist,
+                    const BbkFitResult* d_fit, const double* d_spline_y, const BbkBiasTable* bias,
+                    const uint32_t* d_bias_flags, int64_t out_base, double* d_p, double* d_q, int64_t* d_p_hist,
+                    const BbkCandidates* cands, const BbkDeferredList* deferred, BbkScoreState* d_state, void* stream);
+int bbk_score_deferred(const BbkDeferredList* deferred, const BbkFitResult* d_fit, double* d_p, double* d_q,
+                       int64_t* d_p_hist, const BbkCandidates* cands, BbkScoreState* d_state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  Benjamini-Hochberg q-values as the reference computes them: a FORWARD running max of
