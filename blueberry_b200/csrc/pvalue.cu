@@ -818,7 +818,7 @@ extern "C" int bbk_score_pairs(const int32_t* d_mid1, const int32_t* d_mid2, con
                                const BbkCandidates* cands, const BbkDeferredList* deferred, BbkScoreState* d_state, void* stream) {
     BBK_REQUIRE(n_pairs >= 0 && out_base >= 0 && (out_base & 3) == 0, "bbk_score_pairs: out_base must be a non-negative multiple of 4");
     BBK_REQUIRE(out_base + n_pairs < (1ll << 32), "bbk_score_pairs: rank-local rows must be below 2^32");
-    BBK_REQUIRE(resolution > 0 && resolution < (1ll << 31), "bbk_score_pairs: resolution must be in [1, 2^31)");
+    BBK_REQUIRE(resolution > 1 && resolution < (1ll << 31), "bbk_score_pairs: resolution must be in [2, 2^31) (use bbk_pvalues otherwise)");
     BBK_REQUIRE(min_dist >= 0 && max_dist >= min_dist && max_dist + resolution < (1ll << 31),
                 "bbk_score_pairs: needs 0 <= min_dist <= max_dist and max_dist + resolution < 2^31 (use bbk_pvalues otherwise)");
     BBK_REQUIRE(d_fit && d_spline_y && d_state, "bbk_score_pairs: null pointer");

@@ -46,6 +46,7 @@ constexpr int ST_HBINS = 128;
 constexpr int HI_ONE = 0x3ff00000, HI_NAN = 0x7ff80000;   // high words of 1.0 and of the one NaN this kernel writes
 static_assert(BBK_TILE_ROWS == ST_WARPS * ST_WROWS, "BBK_TILE_ROWS is what one CTA has in flight per stage");
 static_assert(ST_HBASE + ST_HBINS == 2046, "the local histogram ends with the bucket below 1.0");
+static_assert(SMALL_C == 8, "the lower-tail factors are written out for counts up to 8");
 
 struct StWarp {                                    // one warp's shared memory
     int m1[2][ST_WROWS];                           // mid1; after decode: low word of p (non-listed rows) / still mid1 (listed rows) / after its round: low word of p
@@ -59,6 +60,7 @@ struct StWarp {                                    // one warp's shared memory
 
 struct StShared {
     StWarp w[ST_WARPS];
+    double exp2[64];                               // 2^(j/64)
     unsigned hist[ST_HBINS];
 };
 
@@ -143,37 +145,53 @@ __device__ __forceinline__ bool st_flagged(const StBias& B, const FastDiv& div, 
     return (__ldg(B.flg + (b >> 5)) >> (b & 31)) & 1u;
 }
 
+// exact floor(a / R) for a < 2^31, R >= 2 (FastDiv's 31-bit form without its R == 1 case: the host sends R == 1 elsewhere)
+__device__ __forceinline__ unsigned st_div(unsigned a, const FastDiv& f) { return __umulhi(a, f.mul31) >> f.sh31; }
+
+// e^u for -708 <= u <= 0: u = (64 k + j) ln2/64 + r, |r| <= ln2/128; 2^(j/64) from a table, e^r by its series (r^6/720 < 4e-17)
+__device__ __forceinline__ double st_exp_neg(double u, const double* __restrict__ tab) {
+    const double t = fma(u, 92.33248261689366, 6755399441055744.0);            // 64/ln2; 1.5 * 2^52: the integer lands in the low word
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -0.01083042469326756, u);                               // ln2/64, high 32 bits (kf * hi is exact)
+    r = fma(kf, -2.9815858269852933e-12, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = tab[k & 63] * p;                                          // in [1, 2)
+    return __hiloint2double(__double2hiint(v) + (k >> 6) * 1048576, __double2loint(v));
+}
+
 // everything a list entry needs before its arithmetic: loaded one round ahead
-struct StEntry { int slot, c; double y, v1, v2; bool ok1, ok2, active; };
+struct StEntry { int slot, c; double y, v1, v2; bool active; };
 
 template <bool HAS_BIAS>
-__device__ __forceinline__ StEntry st_fetch(const StParams& Q, const StBias& B, const int* s_m1, const int* s_m2, const int* s_c,
-                                            const unsigned char* s_list, int kk, int n_list, int k0R, int L) {
-    StEntry E;
+__device__ __forceinline__ void st_fetch(StEntry& E, const StParams& Q, const StBias& B, const int* s_m1, const int* s_m2, const int* s_c,
+                                         const unsigned char* s_list, int kk, int n_list, int k0R, int L) {
     E.active = kk < n_list;
     E.slot = E.active ? (int)s_list[kk] : 0;
     const int m1 = s_m1[E.slot], m2 = s_m2[E.slot];
     E.c = s_c[E.slot];
     const unsigned R = Q.div.R;
     const int t = (int)((unsigned)m2 - (unsigned)m1) - k0R;                                  // fithic.py:429-430 in closed form
-    int i = 0;
-    if (t > 0) { const unsigned qd = fastdiv31((unsigned)t + R - 1u, Q.div); i = qd > (unsigned)(L - 1) ? L - 1 : (int)qd; }
-    E.y = 0.0; E.v1 = 1.0; E.v2 = 1.0; E.ok1 = false; E.ok2 = false;
+    const unsigned qd = t > 0 ? st_div((unsigned)t + R - 1u, Q.div) : 0u;
+    const unsigned i = qd > (unsigned)(L - 1) ? (unsigned)(L - 1) : qd;
+    E.y = 0.0; E.v1 = 1.0; E.v2 = 1.0;
     if (E.active) {
         E.y = __ldg(Q.spline_y + i);
         if (HAS_BIAS) {
             if (B.wide) {
                 E.v1 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)R, m1); E.v2 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)R, m2);
-                E.ok1 = true; E.ok2 = true;
             } else if (B.spanu) {
                 const unsigned o1 = (unsigned)m1 - B.mid0u, o2 = (unsigned)m2 - B.mid0u;
-                const unsigned x1 = fastdiv31(o1 & 0x7fffffffu, Q.div), x2 = fastdiv31(o2 & 0x7fffffffu, Q.div);
-                E.ok1 = o1 < B.spanu && x1 * R == o1; E.ok2 = o2 < B.spanu && x2 * R == o2;   // fithic.py:418-425: on the grid, inside the table
-                E.v1 = __ldg(B.tab + (E.ok1 ? x1 : 0u)); E.v2 = __ldg(B.tab + (E.ok2 ? x2 : 0u));
+                const unsigned x1 = st_div(o1 & 0x7fffffffu, Q.div), x2 = st_div(o2 & 0x7fffffffu, Q.div);
+                if (o1 < B.spanu && x1 * R == o1) E.v1 = __ldg(B.tab + x1);                  // fithic.py:418-425: on the grid, inside the table
+                if (o2 < B.spanu && x2 * R == o2) E.v2 = __ldg(B.tab + x2);
             }
         }
     }
-    return E;
 }
 
 // a warp-private buffer's content to its global list: one reservation
@@ -199,6 +217,23 @@ __device__ __forceinline__ void st_flush_deferred(StWarp& ws, const StParams& Q,
     }
     n = 0;
     __syncwarp();
+}
+
+// class of a group of four rows, 2 bits per row: 0 p = 1.0, 1 NaN (out of range), 2 on the list with count <= 1, 3 on the list with
+// count >= 2.  slow: 4 bits, row e's count <= 0 does not get the shortcut.
+__device__ __forceinline__ unsigned st_classes(const int4& a1, const int4& a2, const int4& ac, unsigned lo_u, unsigned span_u, unsigned slow) {
+    const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
+    unsigned cls = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool inr = ((unsigned)m2s[e] - (unsigned)m1s[e] - lo_u) <= span_u;                // fithic.py:416, :427 (coordinates >= 0 here)
+        const int c = cs[e];
+        unsigned cd = (unsigned)min(c, 2) + 1u;                                                 // 1 -> 2, >= 2 -> 3
+        if (c <= 0) cd = ((slow >> e) & 1u) ? 2u : 0u;
+        if (!inr) cd = 1u;
+        cls |= cd << (2 * e);
+    }
+    return cls;
 }
 
 template <bool HAS_BIAS>
@@ -235,7 +270,9 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
         }
     }
     const bool zero_slow = exact || B.wide;                                    // count <= 0 rows go through their prior
+    const bool use_flags = HAS_BIAS && B.flg != nullptr && !zero_slow;
     for (int i = tid; i < ST_HBINS; i += ST_THREADS) sh.hist[i] = 0;
+    if (tid < 64) sh.exp2[tid] = exp2((double)tid * (1.0 / 64.0));
     if (lane == 0) {
         mbar_init(&ws.full[0], 1); mbar_init(&ws.full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -263,68 +300,64 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
         if (!mbar_try_wait(&ws.full[stage], parity)) {
             while (!mbar_try_wait(&ws.full[stage], parity)) __nanosleep(64);
         }
-        // ---- decode: class of every row (0 p = 1.0, 1 NaN, 2 count <= 1 list, 3 small counts, 4 the rest, 7 no row); the result of
-        // the rows that need no arithmetic replaces them in the tile
-        unsigned codes = 0, nA = 0, nB = 0, nC = 0;
+        // ---- decode: class of every row; the result of the rows that need no arithmetic replaces them in the tile
+        unsigned codes = 0;                                                    // 2 bits per row, the lane's eight rows
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int rb = u * 128 + lane * 4;
-            const int4 a1 = *reinterpret_cast<const int4*>(s_m1 + rb);
-            const int4 a2 = *reinterpret_cast<const int4*>(s_m2 + rb);
+            int4 a1 = *reinterpret_cast<const int4*>(s_m1 + rb);
+            int4 a2 = *reinterpret_cast<const int4*>(s_m2 + rb);
             const int4 ac = *reinterpret_cast<const int4*>(s_c + rb);
-            const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
-            int code[4];
-            bool any_zero = false;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const unsigned ud = (unsigned)m2s[e] - (unsigned)m1s[e];                            // fithic.py:416
-                const bool inr = m2s[e] >= m1s[e] && (ud - lo_u) <= span_u;                          // fithic.py:427 (inclusive on both sides)
-                const int c = cs[e];
-                int cd = c == 1 ? 2 : (c <= SMALL_C ? 3 : 4);
-                if (c <= 0) cd = zero_slow ? 2 : 0;
-                if (!inr) cd = 1;
-                if (rb + e >= wrows) cd = 7;
-                code[e] = cd;
-                any_zero |= cd == 0;
-            }
-            if (HAS_BIAS && B.flg != nullptr && any_zero) {
+            unsigned slow = zero_slow ? 0xfu : 0u;
+            if (use_flags && min(min(ac.x, ac.y), min(ac.z, ac.w)) <= 0) {
                 // count <= 0: p = 1.0 unless a locus is flagged (bias < 0 or > 4); then the row goes through its prior.
                 // Row-major input: the four rows share their first locus and their second loci are neighbours on the grid -
                 // one division, and the four bits come out of two words.
-                const bool regular = (a1.x == a1.y) & (a1.y == a1.z) & (a1.z == a1.w) & ((unsigned)(a2.y - a2.x) == R) &
-                                     ((unsigned)(a2.z - a2.y) == R) & ((unsigned)(a2.w - a2.z) == R);
+                const unsigned t1 = (unsigned)((a1.x ^ a1.y) | (a1.x ^ a1.z) | (a1.x ^ a1.w));
+                const unsigned t2 = ((unsigned)(a2.y - a2.x) - R) | ((unsigned)(a2.z - a2.y) - R) | ((unsigned)(a2.w - a2.z) - R);
                 const unsigned o2 = (unsigned)a2.x - B.mid0u;
-                if (regular && o2 < B.spanu && o2 + 3u * R < B.spanu) {
-                    const unsigned b = fastdiv31(o2, Q.div) + B.fbit0;
+                if ((t1 | t2) == 0u && o2 < B.spanu && o2 + 3u * R < B.spanu) {
+                    const unsigned b = st_div(o2, Q.div) + B.fbit0;
                     const unsigned w0 = __ldg(B.flg + (b >> 5)), w1 = __ldg(B.flg + (b >> 5) + 1);   // (the bit map has a spare word at its end)
-                    unsigned bits = __funnelshift_r(w0, w1, b & 31) & 0xfu;
-                    if (st_flagged(B, Q.div, a1.x)) bits = 0xfu;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) if (code[e] == 0 && ((bits >> e) & 1u)) code[e] = 2;
+                    const bool f1 = st_flagged(B, Q.div, a1.x);
+                    slow = f1 ? 0xfu : (__funnelshift_r(w0, w1, b & 31) & 0xfu);
                 } else {
+                    const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (code[e] == 0 && (st_flagged(B, Q.div, m1s[e]) || st_flagged(B, Q.div, m2s[e]))) code[e] = 2;
+                    for (int e = 0; e < 4; ++e) slow |= (st_flagged(B, Q.div, m1s[e]) || st_flagged(B, Q.div, m2s[e])) ? (1u << e) : 0u;
                 }
             }
-            int4 lo4 = a1, hi4 = a2;
-            int* los = reinterpret_cast<int*>(&lo4);
-            int* his = reinterpret_cast<int*>(&hi4);
+            unsigned cls = st_classes(a1, a2, ac, lo_u, span_u, slow);
+            if ((a1.x | a1.y | a1.z | a1.w | a2.x | a2.y | a2.z | a2.w) < 0) {
+                // a negative coordinate (never in real data): the wrapped subtraction is not the distance; rows with mid2 < mid1 are out of range
+                const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (m2s[e] < m1s[e]) cls = (cls & ~(3u << (2 * e))) | (1u << (2 * e));
+            }
+            if (wrows < ST_WROWS) {
+                // a shard's last tile: rows it does not have are NaN (and not counted)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (rb + e >= wrows) { cls = (cls & ~(3u << (2 * e))) | (1u << (2 * e)); nans -= 1; }
+            }
+            int* los = reinterpret_cast<int*>(&a1);
+            int* his = reinterpret_cast<int*>(&a2);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int cd = code[e];
-                const bool fin = cd < 2 || cd == 7;
-                los[e] = fin ? 0 : los[e];
-                his[e] = fin ? (cd == 0 ? HI_ONE : HI_NAN) : his[e];
-                ones += cd == 0; nans += cd == 1;
-                codes |= (unsigned)cd << (3 * (u * 4 + e));
-                nA += cd == 2; nB += cd == 3; nC += cd == 4;
+                const unsigned cd = (cls >> (2 * e)) & 3u;
+                los[e] = cd < 2u ? 0 : los[e];
+                his[e] = cd < 2u ? (cd == 0u ? HI_ONE : HI_NAN) : his[e];
             }
-            *reinterpret_cast<int4*>(s_m1 + rb) = lo4;
-            *reinterpret_cast<int4*>(s_m2 + rb) = hi4;
+            *reinterpret_cast<int4*>(s_m1 + rb) = a1;
+            *reinterpret_cast<int4*>(s_m2 + rb) = a2;
+            codes |= cls << (8 * u);
         }
-        // ---- the warp's list: count <= 1 rows, then the small counts, then the rest
-        const unsigned packed = nA | (nB << 10) | (nC << 20);
+        // ---- the warp's list: count <= 1 rows first, then the rest
+        {
+            const unsigned b0 = codes & 0x5555u, b1 = (codes >> 1) & 0x5555u;
+            ones += __popc(~b0 & ~b1 & 0x5555u); nans += __popc(b0 & ~b1);
+        }
+        const unsigned nA = __popc(~codes & (codes >> 1) & 0x5555u), nB = __popc(codes & (codes >> 1) & 0x5555u);
+        const unsigned packed = nA | (nB << 16);
         unsigned inc = packed;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -332,51 +365,54 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
             if (lane >= o) inc += y;
         }
         const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-        const unsigned tA = tot & 1023u, tB = (tot >> 10) & 1023u, tC = tot >> 20;
+        const unsigned tA = tot & 0xffffu, tB = tot >> 16;
         const unsigned exc = inc - packed;
-        unsigned at_a = exc & 1023u, at_b = tA + ((exc >> 10) & 1023u), at_c = tA + tB + (exc >> 20);
+        unsigned at_a = exc & 0xffffu, at_b = tA + (exc >> 16);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const unsigned cd = (codes >> (3 * s)) & 7u;
-            const unsigned is_a = cd == 2, is_b = cd == 3, is_c = cd == 4;
-            const unsigned pos = is_a ? at_a : (is_b ? at_b : at_c);
-            at_a += is_a; at_b += is_b; at_c += is_c;
-            if (is_a | is_b | is_c) ws.list[pos] = (unsigned char)((s >> 2) * 128 + lane * 4 + (s & 3));
+            const unsigned cd = (codes >> (2 * s)) & 3u;
+            const unsigned pos = cd == 2u ? at_a : at_b;
+            at_a += cd == 2u; at_b += cd == 3u;
+            if (cd >= 2u) ws.list[pos] = (unsigned char)((s >> 2) * 128 + lane * 4 + (s & 3));
         }
         __syncwarp();
         // ---- rounds of 32 entries; the next round's gathers are in flight while one computes
-        const int n_list = (int)(tA + tB + tC);
-        StEntry E = st_fetch<HAS_BIAS>(Q, B, s_m1, s_m2, s_c, ws.list, lane, n_list, k0R, L);
+        const int n_list = (int)(tA + tB);
+        StEntry E;
+        st_fetch<HAS_BIAS>(E, Q, B, s_m1, s_m2, s_c, ws.list, lane, n_list, k0R, L);
         for (int kb = 0; kb < n_list; kb += 32) {
-            const StEntry C = E;
-            if (kb + 32 < n_list) E = st_fetch<HAS_BIAS>(Q, B, s_m1, s_m2, s_c, ws.list, kb + 32 + lane, n_list, k0R, L);
-            const bool active = C.active;
-            const int c = C.c;
-            double prior = C.y;
-            if (HAS_BIAS) prior = prior * (bias_value(C.v1, C.ok1) * bias_value(C.v2, C.ok2));      // fithic.py:431
+            const bool active = E.active;
+            const int c = E.c, slot = E.slot;
+            double prior = E.y;
+            if (HAS_BIAS) prior = prior * ((isnan(E.v1) ? 1.0 : E.v1) * (isnan(E.v2) ? 1.0 : E.v2));   // fithic.py:431 (NaN = locus absent)
+            if (kb + 32 < n_list) st_fetch<HAS_BIAS>(E, Q, B, s_m1, s_m2, s_c, ws.list, kb + 32 + lane, n_list, k0R, L);
             const bool valid = active && prior >= 0.0 && prior <= 1.0;                          // bdtrc: NaN otherwise, before anything else
-            double out = __hiloint2double(HI_NAN, 0);
-            if (valid && c <= 0) out = 1.0;                                                     // k < 0 -> 1
             const bool lean = valid && c >= 1 && c <= SMALL_C && !all_defer && prior > 0.0 && prior < LEAN_MAX_PRIOR;
             bool defer = valid && c >= 1 && !lean;
+            int hi = (valid && c <= 0) ? HI_ONE : HI_NAN, lo = 0;                               // k < 0 -> 1
             const int cmax = __reduce_max_sync(0xffffffffu, lean ? c : 0);
             if (cmax > 0) {
-                // P(X >= c) = 1 - pmf(0) (1 + r1 + r1 r2 + ...), c - 1 terms, r_i = (S - i + 1) q / (i (1 - q));
-                // count == 1 is the same form without terms (bdtrc's 1 - (1-q)^S)
+                // P(X >= c) = 1 - pmf(0) (1 + r1 (1 + r2 (1 + ...))), c - 1 factors, r_i = (S - i + 1) q / (i (1 - q));
+                // count == 1 is the same form without factors (bdtrc's 1 - (1-q)^S)
                 const double q = lean ? prior : 0.0;
                 const double l1m = -q * (1.0 + q * (0.5 + q * (1.0 / 3.0 + q * (0.25 + q * (0.2 + q * (1.0 / 6.0))))));
                 const double u = dn * l1m;
-                const double e0 = exp(u);
+                const double e0 = st_exp_neg(fmax(u, -708.0), sh.exp2);
                 double sum = 1.0;
                 if (cmax > 1) {
                     const double qr = q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q))))));   // q / (1 - q)
-                    double a = dn * qr, t = 1.0;
-#pragma unroll
-                    for (int i = 1; i < SMALL_C; ++i) {
-                        if (i < cmax) {                                      // warp-uniform
-                            if (i < c) { t *= a * (1.0 / (double)i); sum += t; a -= qr; }
-                        }
+                    const double a = dn * qr;
+#define BBK_ST_TERM(i) { double ri = fma(-(double)((i) - 1), qr, a) * (1.0 / (double)(i)); ri = (i) < c ? ri : 0.0; sum = fma(ri, sum, 1.0); }
+                    switch (cmax) {                                          // warp-uniform
+                        default: BBK_ST_TERM(7)
+                        case 7: BBK_ST_TERM(6)
+                        case 6: BBK_ST_TERM(5)
+                        case 5: BBK_ST_TERM(4)
+                        case 4: BBK_ST_TERM(3)
+                        case 3: BBK_ST_TERM(2)
+                        case 2: BBK_ST_TERM(1)
                     }
+#undef BBK_ST_TERM
                 }
                 double pc = fma(-e0, sum, 1.0);
                 const bool tiny = lean && c == 1 && u > -0.0078125;          // 1 - e^u loses digits: -expm1(u) by its series
@@ -385,27 +421,26 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
                 }
                 if (lean) {
                     if (c >= 2 && !(pc >= LOWER_MIN_P)) defer = true;        // digits lost (or the row is significant): the upper sum
-                    else out = pc;
+                    else { hi = __double2hiint(pc); lo = __double2loint(pc); }
                 }
             }
-            if (defer) out = 0.5;                                            // placeholder: a number, so that q is pre-filled with 1.0
-            const int hi = __double2hiint(out), lo = __double2loint(out);
-            if (active) { s_m1[C.slot] = lo; s_m2[C.slot] = hi; }
+            if (defer) { hi = 0x3fe00000; lo = 0; }                          // placeholder 0.5: a number, so that q is pre-filled with 1.0
+            if (active) { s_m1[slot] = lo; s_m2[slot] = hi; }
             const bool fin = active && !defer;
             ones += fin && hi == HI_ONE && lo == 0;
             nans += fin && hi == HI_NAN;
-            const bool scored = fin && out < 1.0;                            // (false for NaN)
+            const bool scored = fin && (unsigned)hi < (unsigned)HI_ONE;      // a p below 1.0 (p >= 0 here; false for NaN)
             if (Q.p_hist && scored) {
-                const unsigned b = ((unsigned)hi >> 19) & (BBK_PHIST_BINS - 1);
+                const unsigned b = (unsigned)hi >> 19;                       // = (IEEE bits >> 51), below 2046
                 if (b >= (unsigned)ST_HBASE) atomicAdd(&sh.hist[b - ST_HBASE], 1u);
                 else atomicAdd((unsigned long long*)&Q.p_hist[b], 1ull);
             }
-            const unsigned row = row0 + (unsigned)C.slot;
+            const unsigned row = row0 + (unsigned)slot;
             if (Q.c_keys) {
-                const bool cand = scored && out < BBK_SMALL_P;
+                const bool cand = scored && (unsigned)hi < 0x3fa00000u;      // p < BBK_SMALL_P = 2^-5
                 const unsigned m = __ballot_sync(0xffffffffu, cand);
                 if (m) {
-                    if (cand) { const int at = n_cb + __popc(m & lt); ws.c_key[at] = bbk_key_of(out); ws.c_row[at] = row; }
+                    if (cand) { const int at = n_cb + __popc(m & lt); ws.c_key[at] = ((unsigned long long)(unsigned)hi << 32 | (unsigned)lo) | 0x8000000000000000ull; ws.c_row[at] = row; }
                     n_cb += __popc(m);
                     __syncwarp();
                     if (n_cb >= 32) st_flush_cands(ws, Q, lane, n_cb);

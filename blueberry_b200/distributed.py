@@ -97,7 +97,7 @@ class GenomePass(object):
         self.gather_cap = int(gather_capacity)
         R = engine.R
         # the streaming K4 needs every in-range distance (and distance + R) to fit 31 bits; otherwise the direct kernel runs
-        self.listed = 0 <= engine.min_dist <= engine.max_dist and engine.max_dist + R < (1 << 31)
+        self.listed = 0 <= engine.min_dist <= engine.max_dist and engine.max_dist + R < (1 << 31) and R >= 2
         self._range_ok = self.listed
         self.shards = []
         self.offsets = []
