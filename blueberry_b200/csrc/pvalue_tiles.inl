@@ -37,7 +37,8 @@ constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_WROWS = 256;                      // rows of a warp tile: a lane owns two groups of four
 constexpr int ST_CTAS_PER_SM = 3;
 constexpr int ST_BUF = 64;                         // warp-private output buffers: flushed as soon as they hold 32
-constexpr int SMALL_C = 8;                         // counts up to here are scored through the lower tail (count - 1 terms)
+constexpr int SMALL_C = 8;                         // counts up to here: the lower tail with its factors written out
+constexpr int LOW_C_MAX = 32;                      // counts up to here: the lower tail as a loop (count - 1 terms); above: deferred
 constexpr double LOWER_MIN_P = 1e-4;               // below this the lower-tail form has lost digits: deferred
 constexpr double LEAN_MAX_PRIOR = 9.765625e-4;     // 2^-10: ln(1-q) and q/(1-q) as short series
 constexpr double BIAS_FLAG_MAX = 4.0;              // bias values in [0, 4] (and absent loci) carry no flag bit
@@ -61,6 +62,7 @@ struct StWarp {                                    // one warp's shared memory
 struct StShared {
     StWarp w[ST_WARPS];
     double exp2[64];                               // 2^(j/64)
+    double rcp[LOW_C_MAX];                         // 1/i
     unsigned hist[ST_HBINS];
 };
 
@@ -219,8 +221,8 @@ __device__ __forceinline__ void st_flush_deferred(StWarp& ws, const StParams& Q,
     __syncwarp();
 }
 
-// class of a group of four rows, 2 bits per row: 0 p = 1.0, 1 NaN (out of range), 2 on the list with count <= 1, 3 on the list with
-// count >= 2.  slow: 4 bits, row e's count <= 0 does not get the shortcut.
+// class of a group of four rows, 3 bits per row: 0 p = 1.0, 1 NaN (out of range), on the list: 2 count <= 1, 3 count 2..SMALL_C,
+// 4 larger counts.  slow: 4 bits, row e's count <= 0 does not get the shortcut.
 __device__ __forceinline__ unsigned st_classes(const int4& a1, const int4& a2, const int4& ac, unsigned lo_u, unsigned span_u, unsigned slow) {
     const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
     unsigned cls = 0;
@@ -228,10 +230,10 @@ __device__ __forceinline__ unsigned st_classes(const int4& a1, const int4& a2, c
     for (int e = 0; e < 4; ++e) {
         const bool inr = ((unsigned)m2s[e] - (unsigned)m1s[e] - lo_u) <= span_u;                // fithic.py:416, :427 (coordinates >= 0 here)
         const int c = cs[e];
-        unsigned cd = (unsigned)min(c, 2) + 1u;                                                 // 1 -> 2, >= 2 -> 3
+        unsigned cd = 2u + (unsigned)(c > 1) + (unsigned)(c > SMALL_C);
         if (c <= 0) cd = ((slow >> e) & 1u) ? 2u : 0u;
         if (!inr) cd = 1u;
-        cls |= cd << (2 * e);
+        cls |= cd << (3 * e);
     }
     return cls;
 }
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
     const bool use_flags = HAS_BIAS && B.flg != nullptr && !zero_slow;
     for (int i = tid; i < ST_HBINS; i += ST_THREADS) sh.hist[i] = 0;
     if (tid < 64) sh.exp2[tid] = exp2((double)tid * (1.0 / 64.0));
+    if (tid >= 64 && tid < 64 + LOW_C_MAX) sh.rcp[tid - 64] = tid > 64 ? 1.0 / (double)(tid - 64) : 0.0;
     if (lane == 0) {
         mbar_init(&ws.full[0], 1); mbar_init(&ws.full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
             while (!mbar_try_wait(&ws.full[stage], parity)) __nanosleep(64);
         }
         // ---- decode: class of every row; the result of the rows that need no arithmetic replaces them in the tile
-        unsigned codes = 0;                                                    // 2 bits per row, the lane's eight rows
+        unsigned codes = 0;                                                    // 3 bits per row, the lane's eight rows
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int rb = u * 128 + lane * 4;
@@ -332,32 +335,30 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
                 // a negative coordinate (never in real data): the wrapped subtraction is not the distance; rows with mid2 < mid1 are out of range
                 const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (m2s[e] < m1s[e]) cls = (cls & ~(3u << (2 * e))) | (1u << (2 * e));
+                for (int e = 0; e < 4; ++e) if (m2s[e] < m1s[e]) cls = (cls & ~(7u << (3 * e))) | (1u << (3 * e));
             }
             if (wrows < ST_WROWS) {
                 // a shard's last tile: rows it does not have are NaN (and not counted)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (rb + e >= wrows) { cls = (cls & ~(3u << (2 * e))) | (1u << (2 * e)); nans -= 1; }
+                for (int e = 0; e < 4; ++e) if (rb + e >= wrows) { cls = (cls & ~(7u << (3 * e))) | (1u << (3 * e)); nans -= 1; }
             }
             int* los = reinterpret_cast<int*>(&a1);
             int* his = reinterpret_cast<int*>(&a2);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const unsigned cd = (cls >> (2 * e)) & 3u;
+                const unsigned cd = (cls >> (3 * e)) & 7u;
                 los[e] = cd < 2u ? 0 : los[e];
                 his[e] = cd < 2u ? (cd == 0u ? HI_ONE : HI_NAN) : his[e];
             }
             *reinterpret_cast<int4*>(s_m1 + rb) = a1;
             *reinterpret_cast<int4*>(s_m2 + rb) = a2;
-            codes |= cls << (8 * u);
+            codes |= cls << (12 * u);
         }
-        // ---- the warp's list: count <= 1 rows first, then the rest
-        {
-            const unsigned b0 = codes & 0x5555u, b1 = (codes >> 1) & 0x5555u;
-            ones += __popc(~b0 & ~b1 & 0x5555u); nans += __popc(b0 & ~b1);
-        }
-        const unsigned nA = __popc(~codes & (codes >> 1) & 0x5555u), nB = __popc(codes & (codes >> 1) & 0x5555u);
-        const unsigned packed = nA | (nB << 16);
+        // ---- the warp's list: count <= 1 rows first, then the small counts, then the rest
+        const unsigned x0 = codes & 0x249249u, x1 = (codes >> 1) & 0x249249u, x2 = (codes >> 2) & 0x249249u;
+        ones += __popc(~(x0 | x1 | x2) & 0x249249u); nans += __popc(x0 & ~x1 & ~x2);
+        const unsigned nA = __popc(~x0 & x1 & ~x2), nB = __popc(x0 & x1 & ~x2), nC = __popc(x2);
+        const unsigned packed = nA | (nB << 10) | (nC << 20);
         unsigned inc = packed;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -365,19 +366,19 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
             if (lane >= o) inc += y;
         }
         const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-        const unsigned tA = tot & 0xffffu, tB = tot >> 16;
+        const unsigned tA = tot & 1023u, tB = (tot >> 10) & 1023u, tC = tot >> 20;
         const unsigned exc = inc - packed;
-        unsigned at_a = exc & 0xffffu, at_b = tA + (exc >> 16);
+        unsigned at_a = exc & 1023u, at_b = tA + ((exc >> 10) & 1023u), at_c = tA + tB + (exc >> 20);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const unsigned cd = (codes >> (2 * s)) & 3u;
-            const unsigned pos = cd == 2u ? at_a : at_b;
-            at_a += cd == 2u; at_b += cd == 3u;
+            const unsigned cd = (codes >> (3 * s)) & 7u;
+            const unsigned pos = cd == 2u ? at_a : (cd == 3u ? at_b : at_c);
+            at_a += cd == 2u; at_b += cd == 3u; at_c += cd == 4u;
             if (cd >= 2u) ws.list[pos] = (unsigned char)((s >> 2) * 128 + lane * 4 + (s & 3));
         }
         __syncwarp();
         // ---- rounds of 32 entries; the next round's gathers are in flight while one computes
-        const int n_list = (int)(tA + tB);
+        const int n_list = (int)(tA + tB + tC);
         StEntry E;
         st_fetch<HAS_BIAS>(E, Q, B, s_m1, s_m2, s_c, ws.list, lane, n_list, k0R, L);
         for (int kb = 0; kb < n_list; kb += 32) {
@@ -387,11 +388,14 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
             if (HAS_BIAS) prior = prior * ((isnan(E.v1) ? 1.0 : E.v1) * (isnan(E.v2) ? 1.0 : E.v2));   // fithic.py:431 (NaN = locus absent)
             if (kb + 32 < n_list) st_fetch<HAS_BIAS>(E, Q, B, s_m1, s_m2, s_c, ws.list, kb + 32 + lane, n_list, k0R, L);
             const bool valid = active && prior >= 0.0 && prior <= 1.0;                          // bdtrc: NaN otherwise, before anything else
-            const bool lean = valid && c >= 1 && c <= SMALL_C && !all_defer && prior > 0.0 && prior < LEAN_MAX_PRIOR;
+            const bool lean = valid && c >= 1 && c <= LOW_C_MAX && !all_defer && prior > 0.0 && prior < LEAN_MAX_PRIOR;
             bool defer = valid && c >= 1 && !lean;
             int hi = (valid && c <= 0) ? HI_ONE : HI_NAN, lo = 0;                               // k < 0 -> 1
-            const int cmax = __reduce_max_sync(0xffffffffu, lean ? c : 0);
-            if (cmax > 0) {
+            // which form a row takes depends on its own count only (never on its neighbours in the round): p is a function of
+            // (count, prior, S), whatever the tiling
+            const int cmax_s = __reduce_max_sync(0xffffffffu, lean && c <= SMALL_C ? c : 0);
+            const int cmax_l = __reduce_max_sync(0xffffffffu, lean && c > SMALL_C ? c : 0);
+            if ((cmax_s | cmax_l) > 0) {
                 // P(X >= c) = 1 - pmf(0) (1 + r1 (1 + r2 (1 + ...))), c - 1 factors, r_i = (S - i + 1) q / (i (1 - q));
                 // count == 1 is the same form without factors (bdtrc's 1 - (1-q)^S)
                 const double q = lean ? prior : 0.0;
@@ -399,20 +403,30 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
                 const double u = dn * l1m;
                 const double e0 = st_exp_neg(fmax(u, -708.0), sh.exp2);
                 double sum = 1.0;
-                if (cmax > 1) {
+                if (cmax_s > 1 || cmax_l > 0) {
                     const double qr = q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q * (1.0 + q))))));   // q / (1 - q)
                     const double a = dn * qr;
 #define BBK_ST_TERM(i) { double ri = fma(-(double)((i) - 1), qr, a) * (1.0 / (double)(i)); ri = (i) < c ? ri : 0.0; sum = fma(ri, sum, 1.0); }
-                    switch (cmax) {                                          // warp-uniform
-                        default: BBK_ST_TERM(7)
+                    switch (cmax_s) {                                        // warp-uniform
+                        case 8: BBK_ST_TERM(7)
                         case 7: BBK_ST_TERM(6)
                         case 6: BBK_ST_TERM(5)
                         case 5: BBK_ST_TERM(4)
                         case 4: BBK_ST_TERM(3)
                         case 3: BBK_ST_TERM(2)
                         case 2: BBK_ST_TERM(1)
+                        default: break;
                     }
 #undef BBK_ST_TERM
+                    if (cmax_l > 0) {                                        // warp-uniform: counts above SMALL_C, the terms as a loop
+                        double ai = a, t = 1.0, sl = 1.0;
+                        for (int i = 1; i < cmax_l; ++i) {
+                            double ri = __dmul_rn(ai, sh.rcp[i]);             // (explicit roundings: however the loop is unrolled,
+                            ri = i < c ? ri : 0.0;                            //  a row's p does not depend on the round's longest count)
+                            t = __dmul_rn(t, ri); sl = __dadd_rn(sl, t); ai = __dsub_rn(ai, qr);
+                        }
+                        if (c > SMALL_C) sum = sl;
+                    }
                 }
                 double pc = fma(-e0, sum, 1.0);
                 const bool tiny = lean && c == 1 && u > -0.0078125;          // 1 - e^u loses digits: -expm1(u) by its series
