@@ -221,8 +221,8 @@ __device__ __forceinline__ void st_flush_deferred(StWarp& ws, const StParams& Q,
     __syncwarp();
 }
 
-// class of a group of four rows, 3 bits per row: 0 p = 1.0, 1 NaN (out of range), on the list: 2 count <= 1, 3 count 2..SMALL_C,
-// 4 larger counts.  slow: 4 bits, row e's count <= 0 does not get the shortcut.
+// class of a group of four rows, 2 bits per row: 0 p = 1.0, 1 NaN (out of range), on the list: 2 count <= 1, 3 count >= 2.
+// slow: 4 bits, row e's count <= 0 does not get the shortcut.
 __device__ __forceinline__ unsigned st_classes(const int4& a1, const int4& a2, const int4& ac, unsigned lo_u, unsigned span_u, unsigned slow) {
     const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w}, cs[4] = {ac.x, ac.y, ac.z, ac.w};
     unsigned cls = 0;
@@ -230,10 +230,10 @@ __device__ __forceinline__ unsigned st_classes(const int4& a1, const int4& a2, c
     for (int e = 0; e < 4; ++e) {
         const bool inr = ((unsigned)m2s[e] - (unsigned)m1s[e] - lo_u) <= span_u;                // fithic.py:416, :427 (coordinates >= 0 here)
         const int c = cs[e];
-        unsigned cd = 2u + (unsigned)(c > 1) + (unsigned)(c > SMALL_C);
+        unsigned cd = (unsigned)min(c, 2) + 1u;                                                 // 1 -> 2, >= 2 -> 3
         if (c <= 0) cd = ((slow >> e) & 1u) ? 2u : 0u;
         if (!inr) cd = 1u;
-        cls |= cd << (3 * e);
+        cls |= cd << (2 * e);
     }
     return cls;
 }
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
             while (!mbar_try_wait(&ws.full[stage], parity)) __nanosleep(64);
         }
         // ---- decode: class of every row; the result of the rows that need no arithmetic replaces them in the tile
-        unsigned codes = 0;                                                    // 3 bits per row, the lane's eight rows
+        unsigned codes = 0;                                                    // 2 bits per row, the lane's eight rows
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int rb = u * 128 + lane * 4;
@@ -335,30 +335,33 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
                 // a negative coordinate (never in real data): the wrapped subtraction is not the distance; rows with mid2 < mid1 are out of range
                 const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (m2s[e] < m1s[e]) cls = (cls & ~(7u << (3 * e))) | (1u << (3 * e));
+                for (int e = 0; e < 4; ++e) if (m2s[e] < m1s[e]) cls = (cls & ~(3u << (2 * e))) | (1u << (2 * e));
             }
             if (wrows < ST_WROWS) {
                 // a shard's last tile: rows it does not have are NaN (and not counted)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (rb + e >= wrows) { cls = (cls & ~(7u << (3 * e))) | (1u << (3 * e)); nans -= 1; }
+                for (int e = 0; e < 4; ++e) if (rb + e >= wrows) { cls = (cls & ~(3u << (2 * e))) | (1u << (2 * e)); nans -= 1; }
             }
             int* los = reinterpret_cast<int*>(&a1);
             int* his = reinterpret_cast<int*>(&a2);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const unsigned cd = (cls >> (3 * e)) & 7u;
+                const unsigned cd = (cls >> (2 * e)) & 3u;
                 los[e] = cd < 2u ? 0 : los[e];
                 his[e] = cd < 2u ? (cd == 0u ? HI_ONE : HI_NAN) : his[e];
             }
             *reinterpret_cast<int4*>(s_m1 + rb) = a1;
             *reinterpret_cast<int4*>(s_m2 + rb) = a2;
-            codes |= cls << (12 * u);
+            codes |= cls << (8 * u);
         }
-        // ---- the warp's list: count <= 1 rows first, then the small counts, then the rest
-        const unsigned x0 = codes & 0x249249u, x1 = (codes >> 1) & 0x249249u, x2 = (codes >> 2) & 0x249249u;
-        ones += __popc(~(x0 | x1 | x2) & 0x249249u); nans += __popc(x0 & ~x1 & ~x2);
-        const unsigned nA = __popc(~x0 & x1 & ~x2), nB = __popc(x0 & x1 & ~x2), nC = __popc(x2);
-        const unsigned packed = nA | (nB << 10) | (nC << 20);
+        // ---- the warp's list: count <= 1 rows first, then the rest.  (Large counts sit next to the diagonal: in row-major input
+        // they fill their own tiles, so the rounds that run the term loop are few without a third class.)
+        {
+            const unsigned b0 = codes & 0x5555u, b1 = (codes >> 1) & 0x5555u;
+            ones += __popc(~b0 & ~b1 & 0x5555u); nans += __popc(b0 & ~b1);
+        }
+        const unsigned nA = __popc(~codes & (codes >> 1) & 0x5555u), nB = __popc(codes & (codes >> 1) & 0x5555u);
+        const unsigned packed = nA | (nB << 16);
         unsigned inc = packed;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -366,19 +369,19 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
             if (lane >= o) inc += y;
         }
         const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-        const unsigned tA = tot & 1023u, tB = (tot >> 10) & 1023u, tC = tot >> 20;
+        const unsigned tA = tot & 0xffffu, tB = tot >> 16;
         const unsigned exc = inc - packed;
-        unsigned at_a = exc & 1023u, at_b = tA + ((exc >> 10) & 1023u), at_c = tA + tB + (exc >> 20);
+        unsigned at_a = exc & 0xffffu, at_b = tA + (exc >> 16);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const unsigned cd = (codes >> (3 * s)) & 7u;
-            const unsigned pos = cd == 2u ? at_a : (cd == 3u ? at_b : at_c);
-            at_a += cd == 2u; at_b += cd == 3u; at_c += cd == 4u;
+            const unsigned cd = (codes >> (2 * s)) & 3u;
+            const unsigned pos = cd == 2u ? at_a : at_b;
+            at_a += cd == 2u; at_b += cd == 3u;
             if (cd >= 2u) ws.list[pos] = (unsigned char)((s >> 2) * 128 + lane * 4 + (s & 3));
         }
         __syncwarp();
         // ---- rounds of 32 entries; the next round's gathers are in flight while one computes
-        const int n_list = (int)(tA + tB + tC);
+        const int n_list = (int)(tA + tB);
         StEntry E;
         st_fetch<HAS_BIAS>(E, Q, B, s_m1, s_m2, s_c, ws.list, lane, n_list, k0R, L);
         for (int kb = 0; kb < n_list; kb += 32) {
