@@ -229,10 +229,17 @@ class Workload(object):
         lib = _lib.load()
         R, K = wl["R"], wl["max_dist"] // wl["R"]
         self.R, self.K, self.max_dist = R, K, wl["max_dist"]
-        self.bins = [-(-HG19[c] // R) for c in wl["chroms"]]
+        chrom_list = list(wl["chroms"])
+        if share_of:
+            # a single-GPU stand-in for a larger box: the genome of this run is what `world` of `share_of` GPUs would hold as
+            # WHOLE chromosomes (longest-processing-time packing), so that possible pairs, S and the spline stay consistent
+            pairs_all = [int(lib.bbk_synth_n_pairs(-(-HG19[c] // R), K)) for c in chrom_list]
+            lpt = plan_shards(pairs_all, share_of, mode="lpt")
+            chrom_list = [chrom_list[c] for c in sorted(c for r in range(world) for (c, _, _) in lpt[r])]
+        self.chrom_list = chrom_list
+        self.bins = [-(-HG19[c] // R) for c in chrom_list]
         self.pairs = [int(lib.bbk_synth_n_pairs(nb, K)) for nb in self.bins]
-        # share_of: this run holds `world` of the share_of pieces of the genome (single-GPU stand-in for a larger box)
-        plan = plan_shards(self.pairs, share_of or world)
+        plan = plan_shards(self.pairs, world)
         mine = plan[rank]
         self.P_total = sum(n for r in range(world) for (_, _, n) in plan[r])
         self.sizes = [n for (_, _, n) in mine]
@@ -243,12 +250,12 @@ class Workload(object):
         self.mid1, self.mid2, self.count = (torch.zeros(self.rows, dtype=torch.int32, device=dev) for _ in range(3))
         bias_host = []
         for ci, nb in enumerate(self.bins):
-            rng = np.random.default_rng(SEED + 7919 * (wl["chroms"][ci] + 1))
+            rng = np.random.default_rng(SEED + 7919 * (chrom_list[ci] + 1))
             bias_host.append(np.exp(rng.normal(0.0, 0.25, size=nb)))
         self.bias_host = bias_host
         for (c, first, n), off in zip(mine, starts):
             bdev = torch.from_numpy(bias_host[c]).to(dev)
-            _lib.check(lib.bbk_synth_contacts_range(self.bins[c], K, R, wl["depth"], DECAY, SEED + 1000003 * c, _lib.ptr(bdev), first, n,
+            _lib.check(lib.bbk_synth_contacts_range(self.bins[c], K, R, wl["depth"], DECAY, SEED + 1000003 * chrom_list[c], _lib.ptr(bdev), first, n,
                                                     ctypes_ptr(self.mid1, off), ctypes_ptr(self.mid2, off), ctypes_ptr(self.count, off),
                                                     _lib.stream_ptr()), "bbk_synth_contacts_range")
             torch.cuda.synchronize()
@@ -396,7 +403,7 @@ def _measure(args, wl_name, world, rank, dev, full, out):
     bpp = 104 if two_pass else BYTES_PER_PAIR
     out["whole_pass_frac"] = bpp * W.P_total / (ms_per_step * 1e-3) / 1e9 / (peak * world)
     out["launches_per_step"] = launches_per_step
-    out["workload_name"] = wl["name"] + (" (%d of 8 pieces: a single-GPU stand-in for the 8-GPU box)" % world if share_of else "")
+    out["workload_name"] = wl["name"] + (" (stand-in for an 8-GPU box: the %d whole chromosomes %d of 8 GPUs would hold, %s)" % (len(W.chrom_list), world, ",".join(str(c + 1) for c in W.chrom_list)) if share_of else "")
     out["W"], out["gp"], out["fit"] = W, gp, fit
     if not full or two_pass:
         if two_pass:
