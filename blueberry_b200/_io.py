@@ -13,6 +13,7 @@ SIGNATURES = {
     "bbkio_write_significances": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), _i32, _vp, _vp, _vp, _vp, _vp,
                                                  _vp, _vp, _i64, _i32, _i32, ctypes.POINTER(_i64)]),
     "bbkio_format_double": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
+    "bbkio_unpack_scores": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32]),
     "bbkio_read_interactions": (ctypes.c_int, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
     "bbkio_table_rows": (_i64, [_vp]),
     "bbkio_table_n_chrom": (_i32, [_vp]),
@@ -102,3 +103,18 @@ def format_double(x):
     buf = ctypes.create_string_buffer(64)
     n = load().bbkio_format_double(float(x), buf)
     return buf.raw[:n].decode()
+
+
+def unpack_scores(codes, chunks, values_p, values_q, m, p_out=None, q_out=None, threads=0, want_q=True):
+    """The packed form of a pass' p / q columns (bbk_pack_scores) back into dense float64 columns, bit for bit.
+    codes: uint32 words (16 rows each); chunks: the 24-byte chunk records as a uint8 / structured buffer; values_p / values_q:
+    float64 lists.  All numpy arrays (or anything exposing ctypes.data through numpy).  Returns (p, q) (q None if not wanted)."""
+    lib = load()
+    m = int(m)
+    p = p_out if p_out is not None else np.empty(m, dtype=np.float64)
+    q = (q_out if q_out is not None else np.empty(m, dtype=np.float64)) if want_q else None
+    rc = lib.bbkio_unpack_scores(_ptr(codes), _ptr(chunks), _ptr(values_p), _ptr(values_q), m, _ptr(p), _ptr(q), int(threads))
+    if rc != 0:
+        _raise(lib, "bbkio_unpack_scores", rc)
+    return p, q
+

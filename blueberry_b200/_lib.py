@@ -53,6 +53,11 @@ class DeferredList(ctypes.Structure):
 
 
 TILE_ROWS = 2048
+PACK_CHUNK = 4096
+
+
+class PackState(ctypes.Structure):
+    _fields_ = [("n_p", ctypes.c_uint64), ("n_q", ctypes.c_uint64), ("overflow", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class Candidates(ctypes.Structure):
@@ -102,6 +107,9 @@ SIGNATURES = {
     "bbk_score_pairs": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, ctypes.POINTER(BiasTable), _vp, _i64,
                                        _vp, _vp, _vp, ctypes.POINTER(Candidates), ctypes.POINTER(DeferredList), _vp, _vp]),
     "bbk_score_deferred": (ctypes.c_int, [ctypes.POINTER(DeferredList), _vp, _vp, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp]),
+    "bbk_pack_chunks": (_i64, [_i64]),
+    "bbk_pack_code_words": (_i64, [_i64]),
+    "bbk_pack_scores": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "bbk_bh_qvalues_listed": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp, _sz, _vp]),
     "bbk_bh_select_listed": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "bbk_bh_gathered_workspace_bytes": (_sz, [_i32, _i64]),

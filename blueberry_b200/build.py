@@ -23,6 +23,7 @@ SOURCES = [
     ("fit_stage.cu", ["-fmad=false"]),
     ("pvalue.cu", []),
     ("bh.cu", []),
+    ("pack.cu", []),
     ("band.cu", []),
     ("decimate.cu", []),
     ("contactmap.cu", []),

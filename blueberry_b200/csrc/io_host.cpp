@@ -1,4 +1,5 @@
 // io_host.cpp - libbbkio.so: the significances writer of include/bbk_io.h (host only).
+#include <algorithm>
 #include <atomic>
 #include <charconv>
 #include <cmath>
@@ -439,3 +440,53 @@ extern "C" int bbkio_table_copy(const BbkioTable* t, int32_t* chr1, int64_t* mid
     return BBKIO_OK;
 }
 extern "C" void bbkio_table_free(BbkioTable* t) { delete t; }
+
+// ---- bbkio_unpack_scores: the packed p / q columns of a pass (bbk_pack_scores) back into dense columns -------------------
+extern "C" int bbkio_unpack_scores(const uint32_t* codes, const void* chunks_v, const double* values_p, const double* values_q,
+                                   int64_t m, double* p, double* q, int32_t threads) {
+    if (m < 0 || (m > 0 && (!codes || !chunks_v || !p))) { set_error("bbkio_unpack_scores: null pointer / negative size"); return BBKIO_E_INVALID; }
+    if (m == 0) return BBKIO_OK;
+    struct Chunk { uint64_t base_p, base_q; uint32_t n_p, n_q; };
+    static_assert(sizeof(Chunk) == 24, "chunk records are 24 bytes");
+    const Chunk* chunks = static_cast<const Chunk*>(chunks_v);
+    const int64_t CH = 4096;
+    const int64_t n_chunks = (m + CH - 1) / CH;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if ((int64_t)nt > n_chunks) nt = (int)n_chunks;
+    uint64_t qnan_bits = 0x7ff8000000000000ull;
+    double qnan;
+    memcpy(&qnan, &qnan_bits, 8);
+    std::atomic<int> bad(0);
+    auto work = [&](int t) {
+        const int64_t lo = n_chunks * t / nt, hi = n_chunks * (t + 1) / nt;
+        for (int64_t c = lo; c < hi; ++c) {
+            const double* vp = values_p ? values_p + chunks[c].base_p : nullptr;
+            const double* vq = values_q ? values_q + chunks[c].base_q : nullptr;
+            const int64_t r0 = c * CH, r1 = std::min(m, r0 + CH);
+            uint32_t ip = 0, iq = 0;
+            for (int64_t r = r0; r < r1; r += 16) {
+                uint32_t w = codes[r >> 4];
+                const int64_t e = std::min<int64_t>(r + 16, r1);
+                for (int64_t i = r; i < e; ++i, w >>= 2) {
+                    const uint32_t cd = w & 3u;
+                    if (cd == 0u) { p[i] = 1.0; if (q) q[i] = 1.0; }
+                    else if (cd == 1u) { p[i] = qnan; if (q) q[i] = qnan; }
+                    else {
+                        if (!vp) { bad = 1; return; }
+                        p[i] = vp[ip++];
+                        if (cd == 3u) { if (!vq) { bad = 1; return; } const double v = vq[iq++]; if (q) q[i] = v; }
+                        else if (q) q[i] = 1.0;
+                    }
+                }
+            }
+            if (ip != chunks[c].n_p || iq != chunks[c].n_q) { bad = 1; return; }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    if (bad) { set_error("bbkio_unpack_scores: the code words and the chunk table disagree (or a value list is missing)"); return BBKIO_E_INVALID; }
+    return BBKIO_OK;
+}

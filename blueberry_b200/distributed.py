@@ -334,7 +334,10 @@ class HostStream(object):
     class _Slot(object):
         pass
 
-    def __init__(self, genome_pass, sizes, chroms, slots=2):
+    def __init__(self, genome_pass, sizes, chroms, slots=2, packed=False, cap_p=None, cap_q=None):
+        """packed: results cross the host link as two bits per row + the values that are not 1.0 / NaN (bbk_pack_scores);
+        submit_packed() returns a PackedScores whose dense() rebuilds the float64 columns bit for bit.  cap_p / cap_q: rows
+        the packed value lists can hold (default rows / 2 and rows / 16; a pass that needs more comes back dense)."""
         self.gp = genome_pass
         self.sizes, self.chroms = [int(x) for x in sizes], [int(x) for x in chroms]
         self.starts = layout_rows(self.sizes)[0]
@@ -356,6 +359,21 @@ class HostStream(object):
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.s_run.wait_stream(torch.cuda.current_stream(dev))
         self.submitted = 0
+        self.packed = bool(packed)
+        self._pending = None
+        if self.packed:
+            lib = genome_pass.lib
+            self.cap_p = int(cap_p) if cap_p else max(self.rows // 2, 1024)
+            self.cap_q = int(cap_q) if cap_q else max(self.rows // 16, 1024)
+            self.n_words, self.n_chunks = int(lib.bbk_pack_code_words(self.rows)), int(lib.bbk_pack_chunks(self.rows))
+            for s in self.slots:
+                s.codes = torch.empty(self.n_words, dtype=torch.int32, device=dev)
+                s.chunks = torch.empty(self.n_chunks * 24, dtype=torch.uint8, device=dev)
+                s.vals_p = torch.empty(self.cap_p, dtype=torch.float64, device=dev)
+                s.vals_q = torch.empty(self.cap_q, dtype=torch.float64, device=dev) if genome_pass.q_values else None
+                s.pack_state = torch.zeros(ctypes.sizeof(_lib.PackState), dtype=torch.uint8, device=dev)
+                s.h_pack_state = torch.zeros(ctypes.sizeof(_lib.PackState), dtype=torch.uint8).pin_memory()
+                s.counts_ready = torch.cuda.Event()
 
     def submit(self, h_mid1, h_mid2, h_count, h_p, h_q=None, n_tests=-1):
         """Enqueue one pass over the host table; returns the event that fires when p (and q) are on the host."""
@@ -388,6 +406,79 @@ class HostStream(object):
         s.index = self.submitted - 1
         return s.out_done
 
+    # ------------------------------------------------------------------ packed results
+    def submit_packed(self, h_mid1, h_mid2, h_count, out, n_tests=-1):
+        """Like submit(), but p / q come back packed into `out` (a PackedScores made by packed_buffers()).  The sizes of the two
+        value lists are only known once the pass has run, so their copies are issued lazily: by the NEXT submit_packed() (after
+        it has put its own inbound copies on the wire) or by drain().  Returns `out`; out.done fires when it is complete."""
+        if not self.packed:
+            raise ValueError("this stream was not created with packed=True")
+        for t in (h_mid1, h_mid2, h_count):
+            if not t.is_pinned() or t.numel() < self.rows:
+                raise ValueError("host columns must be pinned and hold at least %d rows" % self.rows)
+        s = self.slots[self.submitted % len(self.slots)]
+        self.submitted += 1
+        n = self.rows
+        gp = self.gp
+        self.s_in.wait_event(s.run_done)
+        with torch.cuda.stream(self.s_in):
+            s.mid1.copy_(h_mid1[:n], non_blocking=True)
+            s.mid2.copy_(h_mid2[:n], non_blocking=True)
+            s.count.copy_(h_count[:n], non_blocking=True)
+            s.in_ready.record()
+        # the previous pass' value lists: their sizes are on the host by now (or soon); their copies overlap this pass' inbound ones
+        self._finalize_pending()
+        self.s_run.wait_event(s.in_ready)
+        self.s_run.wait_event(s.out_done)
+        with torch.cuda.stream(self.s_run):
+            gp.attach(s.shards, s.p, s.q)
+            gp.enqueue(n_tests)
+            s.fit.copy_(gp.eng.fit_result, non_blocking=True)
+            _lib.check(gp.lib.bbk_pack_scores(_lib.ptr(s.p), _lib.ptr(s.q), n, _lib.ptr(s.codes), _lib.ptr(s.chunks), _lib.ptr(s.vals_p),
+                                              self.cap_p, _lib.ptr(s.vals_q), self.cap_q if s.vals_q is not None else 0,
+                                              _lib.ptr(s.pack_state), _lib.stream_ptr(self.s_run)), "bbk_pack_scores")
+            gp.eng.launches += 2
+            s.run_done.record()
+        self.s_out.wait_event(s.run_done)
+        with torch.cuda.stream(self.s_out):
+            s.h_pack_state.copy_(s.pack_state, non_blocking=True)
+            s.counts_ready.record()
+            out.codes.copy_(s.codes, non_blocking=True)
+            out.chunks.copy_(s.chunks, non_blocking=True)
+            s.h_fit.copy_(s.fit, non_blocking=True)
+        s.index = self.submitted - 1
+        out.rows, out.want_q = n, s.q is not None
+        out.done = None
+        self._pending = (s, out)
+        return out
+
+    def _finalize_pending(self):
+        if self._pending is None:
+            return
+        s, out = self._pending
+        self._pending = None
+        s.counts_ready.synchronize()
+        st = _lib.PackState.from_buffer_copy(s.h_pack_state.numpy().tobytes())
+        out.n_p, out.n_q, out.overflow = int(st.n_p), int(st.n_q), bool(st.overflow)
+        with torch.cuda.stream(self.s_out):
+            if out.overflow:                                     # more values than the lists hold: this pass comes back dense
+                out.dense_p = torch.empty(self.rows, dtype=torch.float64).pin_memory()
+                out.dense_p.copy_(s.p, non_blocking=True)
+                if s.q is not None:
+                    out.dense_q = torch.empty(self.rows, dtype=torch.float64).pin_memory()
+                    out.dense_q.copy_(s.q, non_blocking=True)
+            else:
+                if out.n_p:
+                    out.vals_p[:out.n_p].copy_(s.vals_p[:out.n_p], non_blocking=True)
+                if out.n_q and s.vals_q is not None:
+                    out.vals_q[:out.n_q].copy_(s.vals_q[:out.n_q], non_blocking=True)
+            s.out_done.record()
+        out.done = s.out_done
+
+    def packed_buffers(self):
+        """Pinned host buffers for one packed result."""
+        return PackedScores(self.rows, self.n_words, self.n_chunks, self.cap_p, self.cap_q if self.gp.q_values else 0)
+
     def fit_of(self, index):
         """Fit result of submission `index` once its outputs are on the host (raises the reference's exception for a failed
         fit); PassEngine.reference_smoothing(result) tells whether that pass must be repeated with the reference's own s."""
@@ -398,4 +489,40 @@ class HostStream(object):
         return PassEngine.decode_fit(s.h_fit.numpy().tobytes())
 
     def drain(self):
+        self._finalize_pending()
         self.s_out.synchronize()
+
+
+class PackedScores(object):
+    """One pass' p / q columns as they cross the host link (bbk_pack_scores): two bits per row, a chunk table and the values
+    that are not 1.0 / NaN, in pinned host memory.  dense() rebuilds the float64 columns bit for bit (libbbkio, all cores)."""
+
+    def __init__(self, rows, n_words, n_chunks, cap_p, cap_q):
+        self.rows = int(rows)
+        self.codes = torch.empty(n_words, dtype=torch.int32).pin_memory()
+        self.chunks = torch.empty(n_chunks * 24, dtype=torch.uint8).pin_memory()
+        self.vals_p = torch.empty(max(cap_p, 1), dtype=torch.float64).pin_memory()
+        self.vals_q = torch.empty(max(cap_q, 1), dtype=torch.float64).pin_memory() if cap_q else None
+        self.n_p = self.n_q = 0
+        self.overflow = False
+        self.want_q = cap_q > 0
+        self.dense_p = self.dense_q = None
+        self.done = None
+
+    def nbytes(self):
+        """Bytes that crossed the link for this result."""
+        if self.overflow:
+            return 8 * self.rows * (2 if self.dense_q is not None else 1) + self.codes.numel() * 4 + self.chunks.numel()
+        return self.codes.numel() * 4 + self.chunks.numel() + 8 * (self.n_p + self.n_q)
+
+    def dense(self, p_out=None, q_out=None, threads=0):
+        """(p, q) as dense numpy float64 columns (q None without q-values)."""
+        from . import _io
+        if self.done is None:
+            raise RuntimeError("the result is not complete yet: call HostStream.drain() (or submit the next pass) first")
+        self.done.synchronize()
+        if self.overflow:
+            return self.dense_p.numpy(), (self.dense_q.numpy() if self.dense_q is not None else None)
+        return _io.unpack_scores(self.codes.numpy(), self.chunks.numpy(), self.vals_p.numpy(),
+                                 self.vals_q.numpy() if self.vals_q is not None else None, self.rows, p_out, q_out, threads,
+                                 want_q=self.want_q)

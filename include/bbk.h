@@ -239,6 +239,39 @@ int bbk_score_deferred(const BbkDeferredList* deferred, const BbkFitResult* d_fi
                        int64_t* d_p_hist, const BbkCandidates* cands, BbkScoreState* d_state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Output packing                                         the output side of fithic.py:410-435, for the host link
+ *
+ * Most rows carry no information in their numbers (zero-count pairs: p = 1.0, q = 1.0; rows the reference does not emit:
+ * NaN; q = 1.0 for all but the significant rows), and the end-to-end call is bound by the host link.  bbk_pack_scores turns
+ * the dense p / q columns into two bits per row + the values that are not implied:
+ *     code 0  p = 1.0, q = 1.0     code 1  p = NaN, q = NaN     code 2  p in d_values_p, q = 1.0     code 3  p and q in the lists
+ * d_codes: one uint32 per 16 rows (row r: bits 2 (r % 16) of word r / 16), bbk_pack_code_words(m) words.
+ * d_chunks: one record per BBK_PACK_CHUNK rows, bbk_pack_chunks(m) records: where the chunk's packed values start in
+ * each list and how many there are (chunks land in the lists in no particular order; rows inside a chunk keep theirs).
+ * d_q may be NULL (no q-values: codes 0..2).  A list that is too small sets BbkPackState.overflow (values beyond the
+ * capacity are dropped; the caller falls back to the dense columns).  Lossless: bbkio_unpack_scores (bbk_io.h) rebuilds
+ * the dense columns bit for bit.
+ * ------------------------------------------------------------------------------------------- */
+#define BBK_PACK_CHUNK 4096
+typedef struct BbkPackChunk {
+    uint64_t base_p;         /* first packed p of the chunk in d_values_p */
+    uint64_t base_q;         /* first packed q of the chunk in d_values_q */
+    uint32_t n_p;            /* rows of the chunk with code >= 2 */
+    uint32_t n_q;            /* rows of the chunk with code 3 */
+} BbkPackChunk;
+typedef struct BbkPackState {
+    uint64_t n_p;            /* values in d_values_p */
+    uint64_t n_q;            /* values in d_values_q */
+    int32_t overflow;
+    int32_t reserved;
+} BbkPackState;
+int64_t bbk_pack_chunks(int64_t m);
+int64_t bbk_pack_code_words(int64_t m);
+int bbk_pack_scores(const double* d_p, const double* d_q, int64_t m, uint32_t* d_codes, BbkPackChunk* d_chunks,
+                    double* d_values_p, int64_t capacity_p, double* d_values_q, int64_t capacity_q,
+                    BbkPackState* d_state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K5  Benjamini-Hochberg q-values as the reference computes them: a FORWARD running max of
  *     min(p * N / rank, 1)   (fithic.py:466-487, blueberry.pyx:40-75) - not the textbook reverse
  *     cumulative minimum.  q comes back in input order; NaN p (dropped rows) -> NaN q, not ranked.

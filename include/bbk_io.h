@@ -51,6 +51,12 @@ const char* bbkio_table_chrom_name(const BbkioTable* t, int32_t id);
 int bbkio_table_copy(const BbkioTable* t, int32_t* chr1, int64_t* mid1, int32_t* chr2, int64_t* mid2, int64_t* count);
 void bbkio_table_free(BbkioTable* t);
 
+/* The packed form of a pass' p / q columns (bbk_pack_scores, bbk.h: two bits per row + the values that are not 1.0 / NaN)
+ * back into dense columns, bit for bit.  codes: one uint32 per 16 rows; chunks: 24-byte records {uint64 base_p, uint64 base_q,
+ * uint32 n_p, uint32 n_q}, one per 4096 rows; q may be NULL.  threads <= 0: all online cores. */
+int bbkio_unpack_scores(const uint32_t* codes, const void* chunks, const double* values_p, const double* values_q,
+                        int64_t m, double* p, double* q, int32_t threads);
+
 /* "{}".format(float64) into buf (at least 32 bytes); returns the length.  Exposed for the parity tests. */
 int bbkio_format_double(double x, char* buf);
 

@@ -323,6 +323,94 @@ def test_fit_transform_arrays_pinned_and_wide_inputs():
         model.fit_transform_arrays(c["chrom"], c["mid1"], c["chrom"], big, c["count"], fc, fm)
 
 
+def _pack_roundtrip(p, q, dev, cap_p=None, cap_q=None):
+    """bbk_pack_scores on the device, bbkio_unpack_scores on the host."""
+    import torch
+    from blueberry_b200 import _io, _lib
+    lib = _lib.load()
+    m = len(p)
+    dp = torch.from_numpy(p).to(dev)
+    dq = torch.from_numpy(q).to(dev) if q is not None else None
+    cap_p = m if cap_p is None else cap_p
+    cap_q = (m if cap_q is None else cap_q) if q is not None else 0
+    codes = torch.zeros(max(int(lib.bbk_pack_code_words(m)), 1), dtype=torch.int32, device=dev)
+    chunks = torch.zeros(max(int(lib.bbk_pack_chunks(m)), 1) * 24, dtype=torch.uint8, device=dev)
+    vp = torch.zeros(max(cap_p, 1), dtype=torch.float64, device=dev)
+    vq = torch.zeros(max(cap_q, 1), dtype=torch.float64, device=dev)
+    state = torch.zeros(ctypes.sizeof(_lib.PackState), dtype=torch.uint8, device=dev)
+    _lib.check(lib.bbk_pack_scores(_lib.ptr(dp), _lib.ptr(dq), m, _lib.ptr(codes), _lib.ptr(chunks), _lib.ptr(vp), cap_p,
+                                   _lib.ptr(vq) if q is not None else None, cap_q, _lib.ptr(state), _lib.stream_ptr()), "bbk_pack_scores")
+    torch.cuda.synchronize()
+    st = _lib.PackState.from_buffer_copy(state.cpu().numpy().tobytes())
+    if st.overflow:
+        return st, None, None
+    po, qo = _io.unpack_scores(codes.cpu().numpy(), chunks.cpu().numpy(), vp.cpu().numpy(), vq.cpu().numpy() if q is not None else None,
+                               m, want_q=q is not None)
+    return st, po, qo
+
+
+@pytest.mark.parametrize("m", [0, 1, 15, 16, 17, 4095, 4096, 4097, 70001, 1 << 20])
+def test_pack_scores_roundtrip_is_lossless(m):
+    import torch
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(m + 1)
+    p = rng.random(m)
+    kind = rng.integers(0, 10, m)
+    p[kind < 5] = 1.0
+    p[kind == 5] = np.nan
+    p[kind == 6] = 0.0
+    p[kind == 7] = 5e-324 * rng.integers(1, 100, int((kind == 7).sum()))          # denormals
+    q = np.where(np.isnan(p), np.nan, 1.0)
+    sig = (kind >= 8) & ~np.isnan(p)
+    q[sig] = np.minimum(p[sig] * 3.0, 1.0)
+    q[(kind == 4)] = 0.25                                                         # p == 1.0 with q < 1 (the ones fix)
+    st, po, qo = _pack_roundtrip(p, q, dev)
+    assert st.overflow == 0 and int(st.n_p) == int(((p != 1.0) | (q != 1.0))[~(np.isnan(p) & np.isnan(q))].sum())
+    assert np.array_equal(po.view(np.uint64), p.view(np.uint64)) and np.array_equal(qo.view(np.uint64), q.view(np.uint64))
+    st, po, qo = _pack_roundtrip(p, None, dev)                                    # without q-values
+    assert np.array_equal(po.view(np.uint64), p.view(np.uint64)) and qo is None
+    if m >= 4096:
+        st, po, qo = _pack_roundtrip(p, q, dev, cap_p=10, cap_q=10)               # too small: flagged, nothing written out of bounds
+        assert st.overflow == 1
+
+
+def test_host_stream_packed_results_equal_dense():
+    """The end-to-end stream with packed results (two bits per row + the values that are not 1.0 / NaN over the host link)
+    gives the same p / q, bit for bit, as the dense columns; a pass that overflows the value lists comes back dense."""
+    import torch
+    from blueberry_b200.distributed import GenomePass, HostStream, layout_rows
+    dev = torch.device("cuda", 0)
+    eng, shards = _random_shards(2, dev)
+    shards = [s for s in shards if s.chr1 is None]
+    gp = GenomePass(eng, group=False, q_values=True)
+    gp.attach(shards)
+    gp.run()
+    p_ref, q_ref = gp.p.cpu().numpy().copy(), gp.q.cpu().numpy().copy()
+    sizes, chroms = [s.n for s in shards], [s.chrom for s in shards]
+    starts, rows = layout_rows(sizes)
+    rows = max(rows, 4)
+    h = [torch.zeros(rows, dtype=torch.int32).pin_memory() for _ in range(3)]
+    for s, a in zip(shards, starts):
+        h[0][a:a + s.n] = s.mid1.cpu(); h[1][a:a + s.n] = s.mid2.cpu(); h[2][a:a + s.n] = s.count.cpu()
+    real = np.zeros(rows, bool)
+    for s, a in zip(shards, starts):
+        real[a:a + s.n] = True
+    for caps in ((rows, rows), (8, 8)):
+        gp2 = GenomePass(eng, group=False, q_values=True)
+        pipe = HostStream(gp2, sizes, chroms, slots=2, packed=True, cap_p=caps[0], cap_q=caps[1])
+        outs = [pipe.packed_buffers() for _ in range(3)]
+        for o in outs:
+            pipe.submit_packed(h[0], h[1], h[2], o)
+        pipe.drain()
+        for o in outs:
+            assert o.overflow == (caps[0] == 8)
+            p, q = o.dense()
+            assert _same(p[real], p_ref[:rows][real]) and _same(q[real], q_ref[:rows][real])
+            assert np.isnan(p[~real]).all()
+        if caps[0] != 8:
+            assert outs[0].nbytes() < 16 * rows + 4096
+
+
 def _torchrun(world, script, timeout=900):
     env = dict(os.environ)
     env["MASTER_ADDR"] = "127.0.0.1"

@@ -162,3 +162,37 @@ def test_reader_fails_like_the_reference_on_malformed_rows(io, tmp_path, bad, ms
         _ref_parse(path)
     with pytest.raises(io.BbkIoError):
         io.read_interactions(str(tmp_path / "missing.gz"))
+
+
+def test_unpack_scores_against_a_handmade_packing():
+    """bbkio_unpack_scores (the host half of bbk_pack_scores): codes 0 / 1 / 2 / 3 = (1.0, 1.0) / (NaN, NaN) / (p, 1.0) / (p, q),
+    values taken from the chunk's blocks in row order; a chunk table that disagrees with the codes is an error."""
+    from blueberry_b200 import _io
+    rng = np.random.default_rng(5)
+    m = 4096 + 77                                             # two chunks, the second one partial
+    codes = np.zeros((m + 15) // 16, dtype=np.uint32)
+    exp_p, exp_q = np.ones(m), np.ones(m)
+    lists = [([], []), ([], [])]
+    for r in range(m):
+        cd = int(rng.integers(0, 4))
+        codes[r >> 4] |= np.uint32(cd << (2 * (r % 16)))
+        vp, vq = lists[r // 4096]
+        if cd == 1:
+            exp_p[r] = exp_q[r] = np.nan
+        elif cd >= 2:
+            exp_p[r] = rng.random(); vp.append(exp_p[r])
+            if cd == 3:
+                exp_q[r] = rng.random(); vq.append(exp_q[r])
+    chunks = np.zeros(2, dtype=[("bp", "<u8"), ("bq", "<u8"), ("np", "<u4"), ("nq", "<u4")])
+    # the second chunk's values come FIRST in the lists (chunks land in no particular order)
+    chunks["bp"] = [len(lists[1][0]), 0]; chunks["bq"] = [len(lists[1][1]), 0]
+    chunks["np"] = [len(lists[0][0]), len(lists[1][0])]; chunks["nq"] = [len(lists[0][1]), len(lists[1][1])]
+    vals_p, vals_q = np.array(lists[1][0] + lists[0][0]), np.array(lists[1][1] + lists[0][1])
+    p, q = _io.unpack_scores(codes, chunks.view(np.uint8), vals_p, vals_q, m, threads=2)
+    assert np.array_equal(p.view(np.uint64), exp_p.view(np.uint64)) and np.array_equal(q.view(np.uint64), exp_q.view(np.uint64))
+    p, q = _io.unpack_scores(codes, chunks.view(np.uint8), vals_p, vals_q, m, want_q=False)
+    assert np.array_equal(p.view(np.uint64), exp_p.view(np.uint64)) and q is None
+    chunks["np"][0] += 1
+    with pytest.raises(_io.BbkIoError):
+        _io.unpack_scores(codes, chunks.view(np.uint8), vals_p, vals_q, m)
+
