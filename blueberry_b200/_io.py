@@ -14,6 +14,8 @@ SIGNATURES = {
                                                  _vp, _vp, _i64, _i32, _i32, ctypes.POINTER(_i64)]),
     "bbkio_format_double": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
     "bbkio_unpack_scores": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32]),
+    "bbkio_unpack_scores_keep": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32]),
+    "bbkio_copy_bytes": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _i32]),
     "bbkio_read_interactions": (ctypes.c_int, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
     "bbkio_table_rows": (_i64, [_vp]),
     "bbkio_table_n_chrom": (_i32, [_vp]),
@@ -105,7 +107,14 @@ def format_double(x):
     return buf.raw[:n].decode()
 
 
-def unpack_scores(codes, chunks, values_p, values_q, m, p_out=None, q_out=None, threads=0, want_q=True):
+def copy_bytes(dst_ptr, src_ptr, nbytes, threads=0):
+    """memcpy by all cores (raw addresses)."""
+    rc = load().bbkio_copy_bytes(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), int(nbytes), int(threads))
+    if rc != 0:
+        _raise(load(), "bbkio_copy_bytes", rc)
+
+
+def unpack_scores(codes, chunks, values_p, values_q, m, p_out=None, q_out=None, threads=0, want_q=True, keep_out=None):
     """The packed form of a pass' p / q columns (bbk_pack_scores) back into dense float64 columns, bit for bit.
     codes: uint32 words (16 rows each); chunks: the 24-byte chunk records as a uint8 / structured buffer; values_p / values_q:
     float64 lists.  All numpy arrays (or anything exposing ctypes.data through numpy).  Returns (p, q) (q None if not wanted)."""
@@ -113,7 +122,11 @@ def unpack_scores(codes, chunks, values_p, values_q, m, p_out=None, q_out=None, 
     m = int(m)
     p = p_out if p_out is not None else np.empty(m, dtype=np.float64)
     q = (q_out if q_out is not None else np.empty(m, dtype=np.float64)) if want_q else None
-    rc = lib.bbkio_unpack_scores(_ptr(codes), _ptr(chunks), _ptr(values_p), _ptr(values_q), m, _ptr(p), _ptr(q), int(threads))
+    if keep_out is not None:
+        rc = lib.bbkio_unpack_scores_keep(_ptr(codes), _ptr(chunks), _ptr(values_p), _ptr(values_q), m, _ptr(p), _ptr(q), _ptr(keep_out),
+                                          int(threads))
+    else:
+        rc = lib.bbkio_unpack_scores(_ptr(codes), _ptr(chunks), _ptr(values_p), _ptr(values_q), m, _ptr(p), _ptr(q), int(threads))
     if rc != 0:
         _raise(lib, "bbkio_unpack_scores", rc)
     return p, q

@@ -442,8 +442,8 @@ extern "C" int bbkio_table_copy(const BbkioTable* t, int32_t* chr1, int64_t* mid
 extern "C" void bbkio_table_free(BbkioTable* t) { delete t; }
 
 // ---- bbkio_unpack_scores: the packed p / q columns of a pass (bbk_pack_scores) back into dense columns -------------------
-extern "C" int bbkio_unpack_scores(const uint32_t* codes, const void* chunks_v, const double* values_p, const double* values_q,
-                                   int64_t m, double* p, double* q, int32_t threads) {
+static int unpack_scores_impl(const uint32_t* codes, const void* chunks_v, const double* values_p, const double* values_q,
+                              int64_t m, double* p, double* q, uint8_t* keep, int32_t threads) {
     if (m < 0 || (m > 0 && (!codes || !chunks_v || !p))) { set_error("bbkio_unpack_scores: null pointer / negative size"); return BBKIO_E_INVALID; }
     if (m == 0) return BBKIO_OK;
     struct Chunk { uint64_t base_p, base_q; uint32_t n_p, n_q; };
@@ -470,11 +470,12 @@ extern "C" int bbkio_unpack_scores(const uint32_t* codes, const void* chunks_v, 
                 const int64_t e = std::min<int64_t>(r + 16, r1);
                 for (int64_t i = r; i < e; ++i, w >>= 2) {
                     const uint32_t cd = w & 3u;
-                    if (cd == 0u) { p[i] = 1.0; if (q) q[i] = 1.0; }
-                    else if (cd == 1u) { p[i] = qnan; if (q) q[i] = qnan; }
+                    if (cd == 0u) { p[i] = 1.0; if (q) q[i] = 1.0; if (keep) keep[i] = 1; }
+                    else if (cd == 1u) { p[i] = qnan; if (q) q[i] = qnan; if (keep) keep[i] = 0; }
                     else {
                         if (!vp) { bad = 1; return; }
                         p[i] = vp[ip++];
+                        if (keep) keep[i] = p[i] <= 1.0 ? 1 : 0;
                         if (cd == 3u) { if (!vq) { bad = 1; return; } const double v = vq[iq++]; if (q) q[i] = v; }
                         else if (q) q[i] = 1.0;
                     }
@@ -490,3 +491,33 @@ extern "C" int bbkio_unpack_scores(const uint32_t* codes, const void* chunks_v, 
     if (bad) { set_error("bbkio_unpack_scores: the code words and the chunk table disagree (or a value list is missing)"); return BBKIO_E_INVALID; }
     return BBKIO_OK;
 }
+
+extern "C" int bbkio_unpack_scores(const uint32_t* codes, const void* chunks_v, const double* values_p, const double* values_q,
+                                   int64_t m, double* p, double* q, int32_t threads) {
+    return unpack_scores_impl(codes, chunks_v, values_p, values_q, m, p, q, nullptr, threads);
+}
+
+extern "C" int bbkio_unpack_scores_keep(const uint32_t* codes, const void* chunks_v, const double* values_p, const double* values_q,
+                                        int64_t m, double* p, double* q, uint8_t* keep, int32_t threads) {
+    return unpack_scores_impl(codes, chunks_v, values_p, values_q, m, p, q, keep, threads);
+}
+
+// ---- bbkio_copy_bytes: a large host copy by all cores (numpy columns into pinned staging memory and back) ---------------
+extern "C" int bbkio_copy_bytes(void* dst, const void* src, size_t n, int32_t threads) {
+    if (n == 0) return BBKIO_OK;
+    if (!dst || !src) { set_error("bbkio_copy_bytes: null pointer"); return BBKIO_E_INVALID; }
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    const size_t min_piece = (size_t)4 << 20;
+    if ((size_t)nt > n / min_piece) nt = (int)std::max<size_t>(1, n / min_piece);
+    auto work = [&](int t) {
+        const size_t lo = n / nt * t, hi = t == nt - 1 ? n : n / nt * (t + 1);
+        memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    return BBKIO_OK;
+}
+

@@ -20,13 +20,14 @@ as in the reference (fithic.py:121-133 runs one pass).  No PNG is drawn.
 
 There is no CPU fallback: without libbbk.so and a CUDA device these functions raise.
 """
+import ctypes
 import gzip
 import sys
 
 import numpy as np
 import torch
 
-from . import _lib
+from . import _io, _lib
 from .engine import BiasTables, PassEngine, Shard
 
 # ---- module globals of the reference (fithic.py:25-45), refreshed by the stage functions ----
@@ -157,8 +158,14 @@ def _bias_tables(bias_dic, resolution, device, n_chrom_hint=0):
             values.append(np.zeros(0))
             mid0.append(0)
             continue
-        mids = np.fromiter(sub.keys(), dtype=np.int64, count=len(sub))
-        vals = np.fromiter(sub.values(), dtype=np.float64, count=len(sub))
+        if isinstance(sub, tuple):                               # (mids, values) arrays, first occurrences only
+            mids, vals = sub
+        else:
+            mids = np.fromiter(sub.keys(), dtype=np.int64, count=len(sub))
+            vals = np.fromiter(sub.values(), dtype=np.float64, count=len(sub))
+        # a NaN bias makes the reference's prior NaN and the row is dropped (fithic.py:431-434); NaN is the table's "no such
+        # locus" mark, so such a value is stored as +inf: the prior comes out as +-inf or NaN and the row is dropped all the same
+        vals = np.where(np.isnan(vals), np.inf, vals)
         m0 = int(mids.min())
         off = mids - m0
         if (off % R).any():
@@ -230,7 +237,10 @@ def _to_device_i32(a, dev, lo=0, hi=None):
         if k >= 2:
             ev.synchronize()                                   # the DMA that last read this buffer has finished
         h = buf[:4 * (stop - start)].view(torch.int32)
-        np.copyto(h.numpy(), chunk, casting="unsafe")
+        if chunk.dtype == np.int32 and chunk.flags.c_contiguous:
+            _io.copy_bytes(h.data_ptr(), chunk.ctypes.data, 4 * (stop - start))     # all cores: one thread's memcpy is half the link
+        else:
+            np.copyto(h.numpy(), chunk, casting="unsafe")
         out[start:stop].copy_(h, non_blocking=True)
         ev.record(stream)
     for ev in evs:
@@ -264,6 +274,64 @@ def _rows_to_shards(chr1, mid1, chr2, mid2, count, lo, hi, dev, max_runs=64):
             bounds = [0] + cuts.tolist() + [n]
             return [Shard(m1[a:b].clone(), m2[a:b].clone(), cn[a:b].clone(), chrom=int(c1[a])) for a, b in zip(bounds[:-1], bounds[1:])]
     return [Shard(m1, m2, cn, _to_device_i32(c1, dev), _to_device_i32(c2, dev))]
+
+
+_out_pinned = {}
+
+
+def _pinned_cache(dev, name, nbytes):
+    """A pinned host buffer of at least nbytes, kept per device and purpose (pinning memory costs more than the copy)."""
+    key = (str(dev), name)
+    buf = _out_pinned.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8).pin_memory()
+        _out_pinned[key] = buf
+    return buf
+
+
+def _scores_to_host(p_rows, q_rows, dev):
+    """The pass' p / q columns as numpy arrays, plus keep = (p <= 1): packed on the device (bbk_pack_scores: two bits per row +
+    the values that are not 1.0 / NaN), moved through pinned buffers that are allocated once, unpacked by all host cores."""
+    lib = _lib.load()
+    n = int(p_rows.numel())
+    p = np.empty(n, dtype=np.float64)
+    q = np.empty(n, dtype=np.float64) if q_rows is not None else None
+    keep = np.empty(n, dtype=np.bool_)
+    if n == 0:
+        return p, q, keep
+    if p_rows.data_ptr() & 15 or (q_rows is not None and q_rows.data_ptr() & 15):
+        p_rows = p_rows.clone()
+        q_rows = q_rows.clone() if q_rows is not None else None
+    words, nch = int(lib.bbk_pack_code_words(n)), int(lib.bbk_pack_chunks(n))
+    st = _lib.stream_ptr()
+    cap_p, cap_q = max(n // 2, 1024), (max(n // 16, 1024) if q_rows is not None else 0)
+    for attempt in range(2):
+        codes = torch.empty(words, dtype=torch.int32, device=dev)
+        chunks = torch.empty(nch * 24, dtype=torch.uint8, device=dev)
+        vals_p = torch.empty(cap_p, dtype=torch.float64, device=dev)
+        vals_q = torch.empty(max(cap_q, 1), dtype=torch.float64, device=dev)
+        state = torch.zeros(ctypes.sizeof(_lib.PackState), dtype=torch.uint8, device=dev)
+        _lib.check(lib.bbk_pack_scores(_lib.ptr(p_rows), _lib.ptr(q_rows), n, _lib.ptr(codes), _lib.ptr(chunks), _lib.ptr(vals_p), cap_p,
+                                       _lib.ptr(vals_q) if q_rows is not None else None, cap_q, _lib.ptr(state), st), "bbk_pack_scores")
+        ps = _lib.PackState.from_buffer_copy(state.cpu().numpy().tobytes())
+        if not ps.overflow:
+            break
+        cap_p, cap_q = n, (n if q_rows is not None else 0)       # every row carries a value: lists as long as the columns
+    n_p, n_q = int(ps.n_p), int(ps.n_q)
+    h_codes = _pinned_cache(dev, "codes", 4 * words)[:4 * words].view(torch.int32)
+    h_chunks = _pinned_cache(dev, "chunks", 24 * nch)[:24 * nch]
+    h_vp = _pinned_cache(dev, "vals_p", 8 * max(n_p, 1))[:8 * max(n_p, 1)].view(torch.float64)
+    h_vq = _pinned_cache(dev, "vals_q", 8 * max(n_q, 1))[:8 * max(n_q, 1)].view(torch.float64)
+    h_codes.copy_(codes, non_blocking=True)
+    h_chunks.copy_(chunks, non_blocking=True)
+    if n_p:
+        h_vp[:n_p].copy_(vals_p[:n_p], non_blocking=True)
+    if n_q:
+        h_vq[:n_q].copy_(vals_q[:n_q], non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    _io.unpack_scores(h_codes.numpy(), h_chunks.numpy(), h_vp.numpy(), h_vq.numpy() if q_rows is not None else None, n, p, q,
+                      want_q=q_rows is not None, keep_out=keep.view(np.uint8))
+    return p, q, keep
 
 
 def _to_host(t):
@@ -342,15 +410,12 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
     out.fit = fit
     out.frag = info
     out.rows = (lo, hi)
-    host = {"p": _to_host(p_rows), "q": _to_host(q_rows) if want_q else None,
-            "x": _to_host(eng.x[:fit.n_out]), "y": _to_host(eng.y[:fit.n_out]),
+    host = {"x": _to_host(eng.x[:fit.n_out]), "y": _to_host(eng.y[:fit.n_out]),
             "spline_y": _to_host(eng.spline_y[:fit.L]), "spline_raw": _to_host(eng.spline_raw[:fit.L]),
             "possible": _to_host(eng.possible), "observed": _to_host(eng.obs_sum), "bin_of_key": _to_host(eng.bin_of_key),
             "totals": _to_host(eng.totals), "first": _to_host(first) if first is not None else None}
+    out.p, out.q, out.keep = _scores_to_host(p_rows, q_rows if want_q else None, dev)    # keep: fithic.py:434 (NaN = not scored or dropped)
     torch.cuda.current_stream(dev).synchronize()
-    out.p = host["p"].numpy()
-    out.q = host["q"].numpy() if want_q else None
-    out.keep = out.p <= 1                                       # fithic.py:434 (NaN = not scored or dropped)
     out.x = host["x"].numpy()
     out.y = host["y"].numpy()
     out.spline_x = (np.arange(fit.L, dtype=np.int64) + fit.k0) * int(resolution)
@@ -424,8 +489,11 @@ def _bias_dict_from_arrays(bias_chrom, bias_mid, bias_val):
     out = {}
     key = bias_chrom.astype(np.int64) * (1 << 40) + (bias_mid + (1 << 39))
     _, first = np.unique(key, return_index=True)
-    for i in np.sort(first):
-        out.setdefault(int(bias_chrom[i]), {})[int(bias_mid[i])] = float(v[i])
+    first = np.sort(first)
+    ch = bias_chrom[first].astype(np.int64)
+    for c in np.unique(ch):
+        sel = first[ch == c]
+        out[int(c)] = (bias_mid[sel], v[sel])                    # arrays instead of a dict per chromosome (_bias_tables takes both)
     return out
 
 

@@ -56,6 +56,11 @@ void bbkio_table_free(BbkioTable* t);
  * uint32 n_p, uint32 n_q}, one per 4096 rows; q may be NULL.  threads <= 0: all online cores. */
 int bbkio_unpack_scores(const uint32_t* codes, const void* chunks, const double* values_p, const double* values_q,
                         int64_t m, double* p, double* q, int32_t threads);
+/* the same, and keep[i] = (p[i] <= 1): the rows the reference emits (fithic.py:434) */
+int bbkio_unpack_scores_keep(const uint32_t* codes, const void* chunks, const double* values_p, const double* values_q,
+                             int64_t m, double* p, double* q, uint8_t* keep, int32_t threads);
+/* a large host copy by `threads` cores (<= 0: all): numpy columns into pinned staging memory and back */
+int bbkio_copy_bytes(void* dst, const void* src, size_t n, int32_t threads);
 
 /* "{}".format(float64) into buf (at least 32 bytes); returns the length.  Exposed for the parity tests. */
 int bbkio_format_double(double x, char* buf);

@@ -207,6 +207,34 @@ def test_config1_full_size_against_oracle():
     assert np.array_equal(out.q[out.keep], qref)
 
 
+def test_nan_and_odd_bias_values_follow_the_reference():
+    """A bias file may hold anything float() parses: `nan` passes read_bias_file's range test (fithic.py:147-149) and makes the
+    prior NaN, so every row touching that locus is dropped (fithic.py:431-434) - also next to a discarded (-1) locus and for
+    zero counts; `inf` is > 2 and becomes -1.  The dense device table marks missing loci with NaN, so these must not be
+    mistaken for missing ones."""
+    from blueberry_b200 import synth
+    from blueberry_b200.fithic import FitHiC
+    from oracle import fithic_oracle as fo
+    R, bins, max_dist = 10000, [260], 1_200_000
+    fc, fm = synth.make_fragments(bins, R)
+    bias = synth.make_bias(bins, 4, sigma=0.3)[0]
+    bias[[7, 50, 51, 200]] = np.nan
+    bias[[60, 120]] = np.inf
+    bias[90] = 0.1                                              # discarded: -1
+    c = synth.make_contacts(bins, R, max_dist, 200.0, 9, [np.where(np.isfinite(bias), bias, 1.0)])
+    bc = np.zeros(bins[0], dtype=np.int32)
+    keep_idx = np.r_[0:30, 31:bins[0]]                          # one locus missing from the file altogether
+    model = FitHiC("nanbias", R, max_dist=max_dist)
+    out = model.fit_transform_arrays(None, c["mid1"], None, c["mid2"], c["count"], fc, fm, bias=(bc[keep_idx], fm[keep_idx], bias[keep_idx]), q_values=True)
+    bd, _ = fo.read_bias_arrays(bc[keep_idx], fm[keep_idx], bias[keep_idx])
+    ref = fo.fithic_arrays(fc, fm, None, c["mid1"], None, c["mid2"], c["count"], R, 100, model.min_dist, model.max_dist, bias=bd)
+    assert np.array_equal(out.keep, ref.keep)
+    touched = np.isin(c["mid1"], fm[[7, 50, 51, 200]]) | np.isin(c["mid2"], fm[[7, 50, 51, 200]])
+    assert touched.any() and not out.keep[touched].any()
+    k = ref.keep & (ref.p > 0)
+    assert np.abs(np.log10(out.p[k]) - np.log10(ref.p[k])).max() <= 1e-6
+
+
 def test_host_pipeline_matches_serial_passes():
     """engine.HostPipeline: five different libraries (different sizes and seeds) streamed through two device slots
     give bit-for-bit the p and q of the same libraries run one at a time on the default stream."""
