@@ -437,12 +437,13 @@ def _measure(args, wl_name, world, rank, dev, full, out):
             _lib.check(lib.bbk_score_begin(_lib.ptr(gp.score_state), _lib.ptr(eng.p_hist), st), "bbk_score_begin")
             _lib.check(lib.bbk_score_guard(_lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), _lib.ptr(gp.score_state), st), "bbk_score_guard")
             ev[0].record()
-            for sh, off in zip(gp.shards, gp.offsets):
-                if sh.n:
-                    _lib.check(lib.bbk_score_pairs(_lib.ptr(sh.mid1), _lib.ptr(sh.mid2), _lib.ptr(sh.count), sh.n, sh.chrom, eng.R,
-                                                   eng.min_dist, eng.max_dist, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), bias, flags,
-                                                   off, _lib.ptr(gp.p), _lib.ptr(gp.q), _lib.ptr(eng.p_hist), ctypes.byref(gp.cands),
-                                                   ctypes.byref(gp.deferred), _lib.ptr(gp.score_state), st), "bbk_score_pairs")
+            live = [(sh, off) for sh, off in zip(gp.shards, gp.offsets) if sh.n]
+            for (sh, off), st_i in zip(live, eng.fan_out(len(live))):
+                _lib.check(lib.bbk_score_pairs(_lib.ptr(sh.mid1), _lib.ptr(sh.mid2), _lib.ptr(sh.count), sh.n, sh.chrom, eng.R,
+                                               eng.min_dist, eng.max_dist, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), bias, flags,
+                                               off, _lib.ptr(gp.p), _lib.ptr(gp.q), _lib.ptr(eng.p_hist), ctypes.byref(gp.cands),
+                                               ctypes.byref(gp.deferred), _lib.ptr(gp.score_state), st_i), "bbk_score_pairs")
+            eng.fan_in()
             ev[1].record()
             _lib.check(lib.bbk_score_deferred(ctypes.byref(gp.deferred), _lib.ptr(eng.fit_result), _lib.ptr(gp.p), _lib.ptr(gp.q),
                                               _lib.ptr(eng.p_hist), ctypes.byref(gp.cands), _lib.ptr(gp.score_state), st), "bbk_score_deferred")

@@ -185,14 +185,14 @@ class GenomePass(object):
         eng.launches += 1
         if self.force_exact:
             self.score_state[24:28] = torch.tensor([1, 0, 0, 0], dtype=torch.uint8, device=self.device)     # BbkScoreState.exact
-        for sh, off in zip(self.shards, self.offsets):
-            if sh.n == 0:
-                continue
+        live = [(sh, off) for sh, off in zip(self.shards, self.offsets) if sh.n]
+        for (sh, off), st_i in zip(live, eng.fan_out(len(live))):
             _lib.check(lib.bbk_score_pairs(_lib.ptr(sh.mid1), _lib.ptr(sh.mid2), _lib.ptr(sh.count), sh.n, sh.chrom, eng.R,
                                            eng.min_dist, eng.max_dist, _lib.ptr(eng.fit_result), _lib.ptr(eng.spline_y), bias, flags,
                                            off, _lib.ptr(self.p), q, hist, cands, ctypes.byref(self.deferred),
-                                           _lib.ptr(self.score_state), st), "bbk_score_pairs")
+                                           _lib.ptr(self.score_state), st_i), "bbk_score_pairs")
             eng.launches += 1
+        eng.fan_in()
         _lib.check(lib.bbk_score_deferred(ctypes.byref(self.deferred), _lib.ptr(eng.fit_result), _lib.ptr(self.p), q, hist, cands,
                                           _lib.ptr(self.score_state), st), "bbk_score_deferred")
         eng.launches += 1

@@ -134,17 +134,43 @@ class PassEngine(object):
         self.bias = tables
 
     # ------------------------------------------------------------------ stages
+    def fan_out(self, n_jobs):
+        """Stream pointers for n_jobs independent per-shard launches of one stage: the current stream and two side streams in
+        turn, so that the tail of one shard's persistent kernel overlaps the head of the next (23 chromosomes = 23 tails
+        otherwise).  Call fan_in() after the launches."""
+        main = torch.cuda.current_stream(self.device)
+        if n_jobs <= 1:
+            self._fan = None
+            return [_lib.stream_ptr(main)] * max(n_jobs, 1)
+        if getattr(self, "_sides", None) is None:
+            self._sides = [torch.cuda.Stream(self.device) for _ in range(2)]
+            self._fan_ev = [torch.cuda.Event() for _ in range(3)]
+        self._fan_ev[0].record(main)
+        for sd in self._sides:
+            sd.wait_event(self._fan_ev[0])
+        lanes = [main] + self._sides
+        self._fan = main
+        return [_lib.stream_ptr(lanes[i % 3]) for i in range(n_jobs)]
+
+    def fan_in(self):
+        if getattr(self, "_fan", None) is None:
+            return
+        for sd, ev in zip(self._sides, self._fan_ev[1:]):
+            ev.record(sd)
+            self._fan.wait_event(ev)
+        self._fan = None
+
     def hist(self, shards):
         st = _lib.stream_ptr()
         _lib.check(self.lib.bbk_hist_init(_lib.ptr(self.obs_sum), self.nkeys, _lib.ptr(self.totals), st), "bbk_hist_init")
         self.launches += 1
-        for sh in shards:
-            if sh.n == 0:
-                continue
+        live = [sh for sh in shards if sh.n]
+        for sh, st_i in zip(live, self.fan_out(len(live))):
             _lib.check(self.lib.bbk_hist_pairs(_lib.ptr(sh.chr1), _lib.ptr(sh.chr2), _lib.ptr(sh.mid1), _lib.ptr(sh.mid2),
                                                _lib.ptr(sh.count), sh.n, self.R, self.min_dist, self.max_dist, self.nkeys,
-                                               _lib.ptr(self.obs_sum), _lib.ptr(self.totals), st), "bbk_hist_pairs")
+                                               _lib.ptr(self.obs_sum), _lib.ptr(self.totals), st_i), "bbk_hist_pairs")
             self.launches += 1
+        self.fan_in()
 
     def hist_excluding(self, shards, p_list, p_outlier):
         """Second-pass histogram: K1 over the records whose first-pass p is NOT <= p_outlier."""
