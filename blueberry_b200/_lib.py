@@ -107,6 +107,8 @@ SIGNATURES = {
     "bbk_score_pairs": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, ctypes.POINTER(BiasTable), _vp, _i64,
                                        _vp, _vp, _vp, ctypes.POINTER(Candidates), ctypes.POINTER(DeferredList), _vp, _vp]),
     "bbk_score_deferred": (ctypes.c_int, [ctypes.POINTER(DeferredList), _vp, _vp, _vp, _vp, ctypes.POINTER(Candidates), _vp, _vp]),
+    "bbk_extract_workspace_bytes": (_sz, [_i64]),
+    "bbk_extract_contacts": (ctypes.c_int, [_vp, _i64, _f64, _f64, _i32, _f64, _f64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "bbk_pack_chunks": (_i64, [_i64]),
     "bbk_pack_code_words": (_i64, [_i64]),
     "bbk_pack_scores": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),

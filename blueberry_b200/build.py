@@ -24,6 +24,7 @@ SOURCES = [
     ("pvalue.cu", []),
     ("bh.cu", []),
     ("pack.cu", []),
+    ("extract.cu", []),
     ("band.cu", []),
     ("decimate.cu", []),
     ("contactmap.cu", []),

@@ -239,6 +239,20 @@ int bbk_score_deferred(const BbkDeferredList* deferred, const BbkFitResult* d_fi
                        int64_t* d_p_hist, const BbkCandidates* cands, BbkScoreState* d_state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Gather for the genome-wide q-value step               replaces utils.extract_contacts, utils.py:31-90
+ *
+ * d_map: a Fit-Hi-C result table, (n, 5) float64 rows (mid1, mid2, contactCount, p, q) = FithicContactMap.map
+ * (datatypes.pyx:314).  Keeps, in order, the rows with p <= alpha (use_alpha != 0; utils.py:72-73) and
+ * low <= mid2 - mid1 <= high (:80-83; the reference's LOW_/HIGH_FITHIC_CUTOFF), written as
+ * (chromosome, mid1, mid2, contactCount, p) (:76-77) to d_out (capacity rows; rows beyond it are counted, not written).
+ * d_n_out receives the number of rows kept.  Workspace: bbk_extract_workspace_bytes(n).
+ * ------------------------------------------------------------------------------------------- */
+size_t bbk_extract_workspace_bytes(int64_t n);
+int bbk_extract_contacts(const double* d_map, int64_t n, double chromosome, double alpha, int32_t use_alpha, double low,
+                         double high, double* d_out, int64_t capacity, int64_t* d_n_out, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Output packing                                         the output side of fithic.py:410-435, for the host link
  *
  * Most rows carry no information in their numbers (zero-count pairs: p = 1.0, q = 1.0; rows the reference does not emit:

@@ -68,3 +68,60 @@ def normalize_dense(matrix, kr_norm, kr_expected, n_bins):
                 m[j, j + i] /= den
                 m[j + i, j] = m[j, j + i]
     return np.nan_to_num(m)
+
+
+HIGH_FITHIC_CUTOFF = 10000000   # utils.py:25
+LOW_FITHIC_CUTOFF = 25000       # utils.py:26
+
+
+def extract_contacts(map5, chromosome, alpha=None):
+    """utils.extract_contacts (utils.py:69-84) on an in-memory table: p <= alpha (:72-73), columns shifted right with the
+    chromosome in front (:76-77), band filter on mid2 - mid1 (:80-83).  Returns (k, 5) rows (chromosome, mid1, mid2, count, p).
+    Pinned by executing the reference's own function (oracle/run_reference.py: run_reference_extract_contacts)."""
+    contact = np.array(map5, dtype=np.float64, copy=True).reshape(-1, 5)
+    if alpha is not None:
+        contact = contact[contact[:, 3] <= alpha]
+    contact[:, 1:] = contact[:, :-1].copy()
+    contact[:, 0] = chromosome
+    distances = contact[:, 2] - contact[:, 1]
+    return contact[(distances <= HIGH_FITHIC_CUTOFF) & (distances >= LOW_FITHIC_CUTOFF)]
+
+
+def count_band_regions(regions):
+    """blueberry.pyx:77-91: pairs (i, j < i) with LOW <= regions[i] - regions[j] <= HIGH."""
+    r = np.asarray(regions, dtype=np.float64)
+    t = 0
+    for i in range(len(r)):
+        d = r[i] - r[:i]
+        t += int(((d >= LOW_FITHIC_CUTOFF) & (d <= HIGH_FITHIC_CUTOFF)).sum())
+    return t
+
+
+def benjamini_hochberg_sorted(p_sorted, n):
+    """blueberry.pyx:40-75 on ALREADY sorted p: q[i] = max(q[i-1], min(p[i] * n / (i + 1), 1)) with Python's min / max."""
+    q = np.zeros(len(p_sorted))
+    prev = 0.0
+    for i, p in enumerate(np.asarray(p_sorted, dtype=np.float64)):
+        bh = p * n / (i + 1)
+        bh = min(bh, 1)
+        bh = max(bh, prev)
+        prev = bh
+        q[i] = bh
+    return q
+
+
+def genome_qvalues(maps, alpha=None):
+    """The composition of SURVEY.md 3.2: extract every chromosome, n = sum of count_band_regions(union1d(mid1, mid2)),
+    sort the p-values of all chromosomes, benjamini_hochberg(sorted p, n), q back in concatenation order.
+    maps: {chromosome: (n, 5) table}.  Returns (contacts (m, 5), q (m,), n)."""
+    parts, n = [], 0
+    for chrom, m in maps.items():
+        m = np.asarray(m, dtype=np.float64)
+        n += count_band_regions(regions(m))
+        parts.append(extract_contacts(m, chrom, alpha))
+    contacts = np.concatenate(parts) if parts else np.zeros((0, 5))
+    order = np.argsort(contacts[:, 4], kind="stable")
+    q = np.empty(len(order))
+    q[order] = benjamini_hochberg_sorted(contacts[order, 4], n)
+    return contacts, q, n
+

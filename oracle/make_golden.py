@@ -156,6 +156,35 @@ def _contact_map_case():
     print("contact_map", before.shape, "records", len(sel), "nonzero after", int(np.count_nonzero(after)))
 
 
+def _extract_case():
+    """utils.extract_contacts (utils.py:31-90) run from the reference's own function source on two chromosomes, and the
+    genome-wide q-values composed from it as in SURVEY.md 3.2 with the reference's compiled benjamini_hochberg."""
+    rng = np.random.default_rng(41)
+    bb = ref_loader.load_reference_cython()
+    save, parts, n_total = {}, [], 0
+    for chrom, n in ((3, 5000), (11, 3500)):
+        m1 = rng.integers(0, 3000, n) * 5000 + 2500
+        m2 = m1 + rng.integers(0, 2400, n) * 5000                      # distances 0 .. 12 Mb: both ends of the band are crossed
+        p = rng.random(n) ** 6
+        p[rng.choice(n, 40, replace=False)] = 1.0
+        p[:30] = p[30:60]                                              # tied p-values
+        mp = np.stack([m1, m2, rng.integers(1, 90, n), p, np.full(n, -1.0)], axis=1).astype(np.float64)
+        run_reference.write_reference_significances(mp, chrom, 5000)
+        mp = run_reference.reference_map_as_read(chrom, 5000)          # what the reference holds after ITS read of the file
+        contact, band = run_reference.run_reference_extract_contacts(chrom, 5000, alpha=0.2, n_regions=True)
+        contact_all = run_reference.run_reference_extract_contacts(chrom, 5000)
+        save["map_%d" % chrom], save["ref_contacts_%d" % chrom], save["ref_band_%d" % chrom] = mp, contact, np.int64(band)
+        save["ref_contacts_noalpha_%d" % chrom] = contact_all
+        parts.append(contact)
+        n_total += int(band)
+    allc = np.concatenate(parts)
+    order = np.argsort(allc[:, 4], kind="stable")
+    q = np.empty(len(order))
+    q[order] = np.asarray(bb.benjamini_hochberg(np.ascontiguousarray(allc[order, 4]), n_total))
+    np.savez_compressed(os.path.join(GOLDEN, "extract_contacts.npz"), alpha=0.2, chroms=np.array([3, 11]), ref_q=q, ref_n=np.int64(n_total), **save)
+    print("extract_contacts", [len(x) for x in parts], "band total", n_total, "q<=0.01:", int((q <= 0.01).sum()))
+
+
 def main():
     if not ref_loader.reference_available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -171,6 +200,7 @@ def main():
     _pass2_case()
     _decimate_case()
     _contact_map_case()
+    _extract_case()
 
 
 if __name__ == "__main__":

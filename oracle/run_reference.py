@@ -185,3 +185,53 @@ def run_reference_contact_map(pos1, pos2, count, kr_norm, kr_expected, resolutio
     regions = np.array(cm.regions, copy=True)
     cm.normalize()
     return before, np.array(cm.matrix, copy=True), regions, int(cm.n_bins)
+
+
+def write_reference_significances(map5, chromosome, resolution):
+    """A significances file (fithic.py:410-435 format) with these rows where the compiled reference's FithicContactMap will look
+    for it: its DATA_DIR template (a module global, datatypes.pyx:26) is pointed at a temporary directory."""
+    import gzip
+    dt = ref_loader.load_reference_datatypes()
+    tmp = tempfile.mkdtemp(prefix="bbk_refex_")
+    dt.DATA_DIR = os.path.join(tmp, "{0}.chr{1}.res{2}.significances.txt.gz")
+    with gzip.open(dt.DATA_DIR.format("cell", chromosome, resolution), "wt") as fh:
+        fh.write("chr1\tfragmentMid1\tchr2\tfragmentMid2\tcontactCount\tp-value\tq-value\n")
+        for mid1, mid2, cnt, p, q in np.asarray(map5, dtype=np.float64):
+            fh.write("chr{0}\t{1}\tchr{0}\t{2}\t{3}\t{4}\t{5}\n".format(chromosome, int(mid1), int(mid2), int(cnt), repr(float(p)), repr(float(q))))
+    return dt
+
+
+def reference_map_as_read(chromosome, resolution):
+    """The table as the reference's FithicContactMap holds it after reading the file write_reference_significances wrote
+    (datatypes.pyx:314: pandas' C parser with its default float conversion, which is NOT round-trip exact - the p-values it
+    yields can differ from the written ones in the last bit, so goldens store THIS table as the input)."""
+    dt = ref_loader.load_reference_datatypes()
+    return np.array(dt.FithicContactMap("cell", chromosome, resolution).map, copy=True)
+
+
+def run_reference_extract_contacts(chromosome, resolution, alpha=None, n_regions=None):
+    """utils.extract_contacts (utils.py:31-90) itself, on the file write_reference_significances wrote: the function's source is
+    read from where it lies and exec'd with a closed list of edits - its two Python-2 print statements (:61, :66) become calls,
+    `e.message` (:66) becomes `e` - against the reference's own FithicContactMap (datatypes.pyx compiled verbatim) and its own
+    count_band_regions (blueberry.pyx compiled verbatim)."""
+    import textwrap
+    dt = ref_loader.load_reference_datatypes()
+    bb = ref_loader.load_reference_cython()
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "blueberry", "utils.py")
+    lines = open(path).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.startswith("def extract_contacts("))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("def "))
+    body = lines[start:end]
+    edits = 0
+    for i, l in enumerate(body):
+        st = l.strip()
+        if st.startswith("print "):
+            body[i] = l[:len(l) - len(l.lstrip())] + "print(" + st[len("print "):].replace("e.message", "e") + ")"
+            edits += 1
+    if edits != 2:
+        raise RuntimeError("reference utils.py extract_contacts changed; the edit list no longer applies")
+    src = textwrap.dedent("\n".join(body).replace("\t", "    "))
+    ns = {"numpy": np, "FithicContactMap": dt.FithicContactMap, "count_band_regions": bb.count_band_regions,
+          "HIGH_FITHIC_CUTOFF": 10000000, "LOW_FITHIC_CUTOFF": 25000}
+    exec(compile(src, path, "exec"), ns)
+    return ns["extract_contacts"]("cell", chromosome, resolution, alpha, n_regions)

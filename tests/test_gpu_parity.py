@@ -10,6 +10,8 @@ Bars (DESIGN.md "Parity contract"):
 """
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 
@@ -445,3 +447,38 @@ def test_hist_kernel_edge_sizes_against_oracle(n, variant, torch_cuda):
     assert np.array_equal(eng.obs_sum.cpu().numpy(), ref2.observed)
     assert [int(v) for v in t] == [ref2.S, ref2.intra_in_range_count, ref2.intra_all_sum, ref2.intra_all_count,
                                    ref2.inter_all_sum, ref2.inter_all_count, ref2.min_obs_dist, ref2.max_obs_dist]
+
+
+def test_extract_contacts_and_genome_qvalues_on_the_device():
+    """bbk_extract_contacts (the order-preserving compaction behind utils.extract_contacts) and utils.genome_qvalues against
+    the reference golden (bit for bit: rows, band counts, q) and, on a larger random table, against the oracle."""
+    from blueberry_b200 import utils
+    from blueberry_b200.datatypes import FithicContactMap
+    from oracle import datatypes_oracle as do
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extract_contacts.npz"))
+    alpha = float(g["alpha"])
+    maps = {int(c): g["map_%d" % c] for c in g["chroms"]}
+    for c, m in maps.items():
+        out, band = utils.extract_contacts_from_map(m, c, alpha, regions=do.regions(m))
+        assert np.array_equal(out, g["ref_contacts_%d" % c]) and band == int(g["ref_band_%d" % c])
+        assert np.array_equal(utils.extract_contacts_from_map(m, c), g["ref_contacts_noalpha_%d" % c])
+    contacts, q, n = utils.genome_qvalues(maps, alpha)
+    assert n == int(g["ref_n"])
+    assert np.array_equal(contacts, np.concatenate([g["ref_contacts_%d" % c] for c in g["chroms"]]))
+    assert np.array_equal(q, g["ref_q"])
+    # maps given as FithicContactMap objects, no alpha, sizes that are not multiples of the chunk, an empty chromosome
+    rng = np.random.default_rng(123)
+    big = {}
+    for c, n_rows in ((1, 70001), (2, 0), (9, 1025)):
+        m1 = rng.integers(0, 4000, n_rows) * 5000 + 2500
+        m2 = m1 + rng.integers(0, 2300, n_rows) * 5000
+        p = rng.random(n_rows) ** 8
+        if n_rows:
+            p[rng.choice(n_rows, max(n_rows // 50, 1), replace=False)] = np.nan
+        big[c] = np.stack([m1, m2, rng.integers(1, 40, n_rows), p, np.full(n_rows, -1.0)], axis=1).astype(np.float64).reshape(-1, 5)
+    for a in (0.05, None):
+        want_c, want_q, want_n = do.genome_qvalues(big, a)
+        got_c, got_q, got_n = utils.genome_qvalues({c: FithicContactMap.from_arrays(m) for c, m in big.items()}, a)
+        assert got_n == want_n and np.array_equal(got_c, want_c, equal_nan=True)
+        assert np.array_equal(got_q, want_q, equal_nan=True)
+

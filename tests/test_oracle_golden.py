@@ -115,3 +115,22 @@ def test_contact_map_oracle_matches_compiled_reference_output():
     kr[5] = 0.0
     with pytest.raises(ZeroDivisionError):
         do.normalize_dense(m, kr, g["kr_expected"], int(g["ref_n_bins"]))
+
+
+def test_extract_contacts_and_genome_qvalues_oracle_match_reference_output():
+    """utils.extract_contacts (utils.py:31-90) and the genome-wide q-value composition around it: golden
+    minted by executing the reference's own function source against its compiled FithicContactMap / count_band_regions /
+    benjamini_hochberg (oracle/make_golden.py: _extract_case)."""
+    import os
+    from oracle import datatypes_oracle as do
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "extract_contacts.npz"))
+    alpha = float(g["alpha"])
+    maps = {int(c): g["map_%d" % c] for c in g["chroms"]}
+    for c, m in maps.items():
+        assert np.array_equal(do.extract_contacts(m, c, alpha), g["ref_contacts_%d" % c])
+        assert np.array_equal(do.extract_contacts(m, c), g["ref_contacts_noalpha_%d" % c])
+        assert do.count_band_regions(do.regions(m)) == int(g["ref_band_%d" % c])
+    contacts, q, n = do.genome_qvalues(maps, alpha)
+    assert n == int(g["ref_n"]) and np.array_equal(q, g["ref_q"])
+    assert np.array_equal(contacts, np.concatenate([g["ref_contacts_%d" % c] for c in g["chroms"]]))
+

@@ -66,3 +66,21 @@ def test_live_reference_contact_map():
     m, reg = do.contact_map_dense(b1 * R, b2 * R, cnt, n_bins, R)
     assert n_bins == nb and np.array_equal(m, before) and np.array_equal(reg, regions)
     assert np.array_equal(do.normalize_dense(m, kr, ke, n_bins), after)
+
+
+def test_live_reference_extract_contacts():
+    """utils.extract_contacts executed from the reference's own source (two print statements edited) on a file read by the
+    reference's own FithicContactMap, against the oracle's restatement on the table as that class read it."""
+    from oracle import run_reference as rr, datatypes_oracle as do
+    rng = np.random.default_rng(77)
+    n = 1500
+    m1 = rng.integers(0, 2500, n) * 5000 + 2500
+    m2 = m1 + rng.integers(0, 2300, n) * 5000
+    mp = np.stack([m1, m2, rng.integers(1, 40, n), rng.random(n) ** 5, np.full(n, -1.0)], axis=1).astype(np.float64)
+    rr.write_reference_significances(mp, 5, 5000)
+    held = rr.reference_map_as_read(5, 5000)
+    got, band = rr.run_reference_extract_contacts(5, 5000, alpha=0.1, n_regions=True)
+    assert np.array_equal(do.extract_contacts(held, 5, 0.1), got)
+    assert do.count_band_regions(do.regions(held)) == band
+    assert np.array_equal(do.extract_contacts(held, 5), rr.run_reference_extract_contacts(5, 5000))
+
