@@ -61,6 +61,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _true_reference():
+    """The unmodified reference timed end to end (gz text in / out, one core) in the build container by
+    tools/time_true_reference.py - /root/reference does not exist on the GPU box, so this is a committed measurement."""
+    path = os.path.join(ROOT, "profiles", "true_reference_timing.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
 def _k4_sources_sha():
     h = hashlib.sha256()
     for f in ("pvalue.cu", "pvalue_lists.inl"):
@@ -205,6 +216,7 @@ def run_reference_arm(args, out_fd):
         "config": {"workload": wl["name"] + " (bounded sample per step)", "resolution": wl["R"],
                    "n_bins": N_BINS, "max_dist": wl["max_dist"]},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "true_reference": _true_reference(),
                          "note": "oracle/fithic_oracle.py (numpy / scipy restatement of fithic.py, ~100x faster than the reference's "
                                  "per-line Python; the unmodified reference itself needs /root/reference, absent on the GPU box - "
                                  "its rate, timed in the build container, is in DESIGN.md section 5)"},
@@ -606,7 +618,7 @@ def run_ours(args, out_fd):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, pairs, wall_c, _ = cpu_baseline(1, wl, nb=4500)
-        cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
+        cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port", "true_reference": _true_reference(),
                "sample": "one %d-bin block of the same workload (%.1fM records): histogram, binning, spline, bdtrc scoring, BH; "
                          "oracle/fithic_oracle.py on 1 of %d host cores, %.1f s" % (4500, pairs / 1e6, os.cpu_count() or 1, wall_c)}
 
