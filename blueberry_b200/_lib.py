@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbbk.so")
 
 FIT_S_GIVEN = 7777          # input value of FitResult.status: use FitResult.smoothing as s
+FIT_TOO_MANY_BINS = -13
 PHIST_BINS = 4096
 PHIST_LEN = PHIST_BINS + 2
 BH_UNSORTED = 0

@@ -293,6 +293,9 @@ class GenomePass(object):
         import torch.distributed as dist
         for _ in range(6):
             raw, score, ov = self.read_state()
+            if _lib.FitResult.from_buffer_copy(raw).status == _lib.FIT_TOO_MANY_BINS and self.eng.grow_bins():
+                self.enqueue(self.n_tests, smoothing=self._smoothing)      # more bins than the default buffers hold: one per key
+                continue
             fit = PassEngine.decode_fit(raw)
             again = False
             s_ref = PassEngine.reference_smoothing(fit)          # None once the pass ran with the reference's own s

@@ -121,6 +121,20 @@ class PassEngine(object):
         self.bh_ws = None
         self.launches = 0
 
+    def grow_bins(self):
+        """Room for one bin per distance key (the most fithic.py:188-209 can emit: once S - total reaches 0 every remaining key
+        closes a bin).  Returns False when the buffers already have that size."""
+        if self.max_bins >= self.nkeys:
+            return False
+        dev = self.device
+        self.max_bins = max(4, self.nkeys)
+        self.x = torch.zeros(self.max_bins, dtype=torch.float64, device=dev)
+        self.y = torch.zeros(self.max_bins, dtype=torch.float64, device=dev)
+        self.knots = torch.zeros(self.max_bins + 4, dtype=torch.float64, device=dev)
+        self.coefs = torch.zeros(self.max_bins + 4, dtype=torch.float64, device=dev)
+        self.fit_ws = torch.zeros(int(self.lib.bbk_fit_workspace_bytes(self.max_bins, self.nkeys)), dtype=torch.uint8, device=dev)
+        return True
+
     # ------------------------------------------------------------------ setup
     def set_fragments(self, n_frags, max_frag):
         """possible[] from per-chromosome fragment counts (fithic.py:302-311)."""
@@ -369,8 +383,9 @@ class PassEngine(object):
     def run(self, shards, p_outs, q_outs=None, n_tests=-1, group=None, smoothing=None):
         """The whole pass over `shards`; p_outs[i] (float64, len shards[i].n) receives the p-values.
 
-        q_outs (optional): per-shard q buffers.  q-values are computed per call over ALL shards
-        given here when they share one contiguous p buffer (see fithic.fit_transform_arrays).
+        q_outs (optional): per-shard q buffers.  Each shard's q-values are ranked on their own (one Benjamini-Hochberg step
+        and one default N per shard - the per-chromosome result files of datatypes.pyx:26); for ONE ranking over several
+        shards or ranks use distributed.GenomePass, which is what fithic.fit_transform_arrays runs.
         """
         self.hist(shards)
         self.allreduce_stats(group)
