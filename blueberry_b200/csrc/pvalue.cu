@@ -902,7 +902,7 @@ extern "C" int bbk_score_deferred(const BbkDeferredList* deferred, const BbkFitR
         }
     }
     // the list length is only known on the device: a grid that covers the device, rounds handed out by stride
-    score_deferred_kernel<<<(unsigned)(bbk_num_sms() * 2), PV_THREADS, sizeof(DfShared), st>>>(D);
+    score_deferred_kernel<<<(unsigned)(bbk_num_sms() * 3), PV_THREADS, sizeof(DfShared), st>>>(D);
     BBK_CHECK_LAUNCH("score_deferred_kernel");
     return BBK_OK;
 }

@@ -38,7 +38,7 @@ constexpr int ST_WROWS = 256;                      // rows of a warp tile: a lan
 constexpr int ST_CTAS_PER_SM = 3;
 constexpr int ST_BUF = 64;                         // warp-private output buffers: flushed as soon as they hold 32
 constexpr int SMALL_C = 8;                         // counts up to here: the lower tail with its factors written out
-constexpr int LOW_C_MAX = 32;                      // counts up to here: the lower tail as a loop (count - 1 terms); above: deferred
+constexpr int LOW_C_MAX = 64;                      // counts up to here: the lower tail as a loop (count - 1 terms); above: deferred
 constexpr double LOWER_MIN_P = 1e-4;               // below this the lower-tail form has lost digits: deferred
 constexpr double LEAN_MAX_PRIOR = 9.765625e-4;     // 2^-10: ln(1-q) and q/(1-q) as short series
 constexpr double BIAS_FLAG_MAX = 4.0;              // bias values in [0, 4] (and absent loci) carry no flag bit
@@ -564,7 +564,7 @@ struct DfShared {
     unsigned hist[BBK_PHIST_BINS];
 };
 
-__global__ void __launch_bounds__(PV_THREADS, 2) score_deferred_kernel(DfParams D) {
+__global__ void __launch_bounds__(PV_THREADS, 3) score_deferred_kernel(DfParams D) {
     extern __shared__ __align__(16) unsigned char df_raw[];
     DfShared& sh = *reinterpret_cast<DfShared*>(df_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
