@@ -74,7 +74,7 @@ def _true_reference():
 
 def _k4_sources_sha():
     h = hashlib.sha256()
-    for f in ("pvalue.cu", "pvalue_lists.inl"):
+    for f in ("pvalue.cu", "pvalue_tiles.inl"):
         with open(os.path.join(ROOT, "blueberry_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
