@@ -1134,23 +1134,24 @@ extern "C" int bbk_bh_rank_gathered(const uint64_t* d_keys_all, int64_t n_all, c
 // ---- the same with the gather left on the device: no candidate count ever travels to the host -------------------------
 // Every rank sends a fixed-capacity block [count | keys[0 .. cap)] (d_keys of bbk_bh_select with its count in front); the
 // all-gather delivers `world` such blocks.  Here: prefix the counts, compact the blocks into one key array, rank it, and
-// scatter this rank's slice of the q-values back to its rows.  A count above cap sets *d_overflow (the host looks at it when
-// it reads the results and repeats the step with a larger capacity).
+// scatter this rank's slice of the q-values back to its rows.  A count above cap puts the largest count into *d_overflow (the host looks
+// at it when it reads the results and repeats the step with a capacity that fits).
 namespace {
 
 __global__ void gathered_prepare_kernel(const unsigned long long* recv, int world, long long cap, const unsigned long long* state_in,
                                         BhState* st, unsigned long long* offsets, int* overflow) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long run = 0;
+    unsigned long long run = 0, most = 0;
     int ov = 0;
     for (int r = 0; r < world; ++r) {
         unsigned long long c = recv[(size_t)r * (size_t)(cap + 1)];
+        if (c > most) most = c;
         if (c > (unsigned long long)cap) { ov = 1; c = (unsigned long long)cap; }
         offsets[r] = run;
         run += c;
     }
     offsets[world] = run;
-    if (ov) *overflow = 1;
+    if (ov) *overflow = most < 0x7fffffffull ? (int)most : 0x7fffffff;      // the capacity that would have sufficed
     st->n_cand = run; st->tau_key = state_in[1]; st->n_tests = (long long)state_in[2]; st->n_ones = state_in[3];
     st->n_nan = 0; st->n_valid = 0; st->q_ones = 1.0; st->total_max = 0.0; st->need_ones_fix = 0;
     for (int p = 0; p < NPASS; ++p) st->skip[p] = 0;

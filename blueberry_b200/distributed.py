@@ -309,7 +309,10 @@ class GenomePass(object):
                 dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
                 ov_any, again, max_rows = int(flags[0].item()), bool(int(flags[1].item())), int(flags[2].item())
                 if ov_any:
-                    self.gather_cap = max(4, min(self.gather_cap * 8, max_rows))
+                    # ov_any = the largest candidate count of any rank: the next power of two with a quarter of headroom (the
+                    # all-gather moves the whole capacity, so it should fit, not dwarf, what is sent)
+                    need = max(int(ov_any * 1.25), 2 * self.gather_cap)
+                    self.gather_cap = max(4, min(1 << (need - 1).bit_length(), max_rows))
                     self.gather_overflow.zero_()
                     self._alloc_gather()
                     again = True

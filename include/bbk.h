@@ -352,7 +352,7 @@ int bbk_bh_select_listed(const double* d_p, int64_t m, int64_t n_tests, const in
  * bbk_bh_pack_count - and one all-gather delivers `world` such blocks (d_recv: world * (cap + 1) u64).
  * bbk_bh_rank_gathered_padded prefixes the counts, compacts the blocks, ranks them (forward running max, as
  * bbk_bh_rank_gathered) and scatters THIS rank's slice back: d_q_dst[d_idx_local[i]] = q of this rank's candidate i.
- * A count above cap sets *d_overflow (int32, never cleared here); the host checks it when it reads the results and repeats
+ * A count above cap puts the largest count of any rank into *d_overflow (int32, never cleared here); the host checks it when it reads the results and repeats
  * the q-value step with a larger capacity.  d_q_ones[2] as bbk_bh_rank_gathered.  Workspace:
  * bbk_bh_gathered_workspace_bytes(world, cap). */
 size_t bbk_bh_gathered_workspace_bytes(int32_t world, int64_t cap);
