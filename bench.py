@@ -359,21 +359,14 @@ def _measure(args, wl_name, world, rank, dev, full, out):
 
     two_pass = wl["two_pass"]
     if two_pass:
-        # config 4: pass 1 -> statistics without the outliers -> refit -> every record scored again (engine.run_second_pass)
-        eng, sh = W.eng, W.shards[0]
-        P = sh.n
-        p_first = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
-        p2 = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
-        q2 = torch.empty((P + 1) & ~1, dtype=torch.float64, device=dev)[:P]
+        # config 4: pass 1 (p only) -> statistics without the outliers -> refit -> every record scored again, with q-values
+        gp1 = GenomePass(W.eng, q_values=False)
+        gp1.attach(W.shards)
         p_outlier = 1.0 / float(W.possible_in_range)
 
         def step():
-            eng.hist([sh]); eng.allreduce_stats(None); eng.fit()
-            eng.pvalues(sh, p_first, with_hist=False)
-            eng.hist_excluding([sh], [p_first], p_outlier); eng.allreduce_stats(None); eng.fit()
-            eng.p_hist.zero_()
-            eng.pvalues(sh, p2, with_hist=True, q_out=q2)
-            eng.qvalues(p2, q2, n_tests=-1, use_hist=True, prepared=True)
+            gp1.enqueue()
+            gp.enqueue(exclude=(gp1.p, p_outlier))
     else:
         def step():
             gp.enqueue()
@@ -382,7 +375,7 @@ def _measure(args, wl_name, world, rank, dev, full, out):
     for _ in range(warm):
         step()
     barrier()
-    fit = gp.finish() if not two_pass else W.eng.read_fit()     # raises for a failed fit; settles the gather capacity
+    fit = gp.finish()                                           # raises for a failed fit; settles the gather capacity
     W.eng.launches = 0
     step()
     launches_per_step = W.eng.launches
@@ -629,7 +622,7 @@ def run_ours(args, out_fd):
             "scaling": "strong" if args.workload != "cfg5" or world >= 8 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": main["workload_name"], "pairs_total": main["P_total"], "pairs_rank0": main["P_local"],
                        "resolution": wl["R"], "max_dist": wl["max_dist"], "n_bins": N_BINS, "biases": True,
-                       "entry_point": "blueberry_b200.distributed.GenomePass" if not wl["two_pass"] else "blueberry_b200.engine.PassEngine (two passes)",
+                       "entry_point": "blueberry_b200.distributed.GenomePass" + (" (two passes: enqueue(), then enqueue(exclude=(p_first, 1/possibleIntraInRangeCount)))" if wl["two_pass"] else ""),
                        "sharding": "distributed.plan_shards: equal record counts, whole chromosomes, row blocks where a chromosome straddles a cut",
                        "q_values": "genome-wide (histogram all-reduce + fixed-capacity candidate all-gather, no host round trip)" if world > 1 else "genome-wide (one rank)",
                        "l2": "inputs (%.2f GB on rank 0) exceed the 126 MB L2" % sizes_gb,

@@ -197,10 +197,13 @@ class GenomePass(object):
                                           _lib.ptr(self.score_state), st), "bbk_score_deferred")
         eng.launches += 1
 
-    def enqueue(self, n_tests=-1, smoothing=None, marks=None):
+    def enqueue(self, n_tests=-1, smoothing=None, marks=None, exclude=None):
         """Enqueue the whole pass on the current stream; no host synchronisation.
         marks (optional dict): filled with CUDA events at the stage boundaries (name -> event recorded AFTER that stage),
-        for per-stage timing."""
+        for per-stage timing.
+        exclude (optional): (p_first, p_outlier) - the refit pass of BASELINE config 4: the statistics (K1) skip the records
+        whose first-pass p (p_first: a buffer laid out like this pass' p) is <= p_outlier, then EVERY record is scored with
+        the refitted S and spline (definition in include/bbk.h, bbk_hist_pairs_excluding)."""
         import torch.distributed as dist
         eng, lib = self.eng, self.lib
         main = torch.cuda.current_stream(self.device)
@@ -222,7 +225,12 @@ class GenomePass(object):
         elif want_q:
             eng.p_hist.zero_()
             eng.launches += 1
-        eng.hist(self.shards)
+        if exclude is not None:
+            p_first, p_outlier = exclude
+            eng.hist_excluding(self.shards, [p_first[o:o + sh.n] for sh, o in zip(self.shards, self.offsets)], p_outlier)
+        else:
+            eng.hist(self.shards)
+        self._exclude = exclude
         mark("hist")
         if self.world > 1:
             eng.allreduce_stats(self.group)
@@ -294,7 +302,7 @@ class GenomePass(object):
         for _ in range(6):
             raw, score, ov = self.read_state()
             if _lib.FitResult.from_buffer_copy(raw).status == _lib.FIT_TOO_MANY_BINS and self.eng.grow_bins():
-                self.enqueue(self.n_tests, smoothing=self._smoothing)      # more bins than the default buffers hold: one per key
+                self.enqueue(self.n_tests, smoothing=self._smoothing, exclude=getattr(self, "_exclude", None))      # more bins than the default buffers hold: one per key
                 continue
             fit = PassEngine.decode_fit(raw)
             again = False
@@ -319,11 +327,11 @@ class GenomePass(object):
             if not again:
                 self.last_score = score
                 return fit
-            self.enqueue(self.n_tests, smoothing=self._smoothing)
+            self.enqueue(self.n_tests, smoothing=self._smoothing, exclude=getattr(self, "_exclude", None))
         raise _lib.BbkError("the pass did not settle after 6 attempts")
 
-    def run(self, n_tests=-1, smoothing=None):
-        self.enqueue(n_tests, smoothing)
+    def run(self, n_tests=-1, smoothing=None, exclude=None):
+        self.enqueue(n_tests, smoothing, exclude=exclude)
         return self.finish()
 
 

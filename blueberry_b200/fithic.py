@@ -374,27 +374,19 @@ def _run_pass(resolution, n_bins, min_dist, max_dist, frag_chrom, frag_mid, chr1
         else:
             shard = Shard(_to_device_i32(mid1, dev), _to_device_i32(mid2, dev), _to_device_i32(count, dev),
                           _to_device_i32(chr1, dev), _to_device_i32(chr2, dev))
-        n = shard.n
-        p = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n]
-        q = torch.empty(_pad16(n), dtype=torch.float64, device=dev)[:n] if want_q else None
-        # pass 1 without q-values, then the refit on the non-outliers scores every record again.  The kernel takes
-        # s = min(y) * min(y); the reference's `min(y)**2` is libm's pow, one ulp off for ~0.09 % of inputs: when the two
-        # differ (checked on the host once the pass is through) the pass is run again with the reference's s.
-        eng.run([shard], [p], None)
-        s_ref = eng.reference_smoothing(eng.read_fit())
-        if s_ref is not None:
-            eng.run([shard], [p], None, smoothing=s_ref)
-            eng.read_fit()
+        # pass 1 without q-values, then the refit on the non-outliers scores every record again.  (GenomePass.finish repeats a
+        # pass with the reference's own s when the kernel's min(y) * min(y) is not libm's min(y)**2: one ulp off for ~0.09 % of inputs.)
+        gp1 = GenomePass(eng, group=False, q_values=False)
+        gp1.attach([shard])
+        gp1.run()
         in_rng = _in_range_possible(eng.possible.cpu().numpy(), resolution, min_dist, max_dist)
         if in_rng <= 0:
             raise ZeroDivisionError("float division by zero (possibleIntraInRangeCount == 0)")
-        first = p.clone()
-        eng.run_second_pass([shard], [first], [p], 1.0 / in_rng, [q] if want_q else None, n_tests=nt)
-        s_ref = eng.reference_smoothing(eng.read_fit())
-        if s_ref is not None:
-            eng.run_second_pass([shard], [first], [p], 1.0 / in_rng, [q] if want_q else None, n_tests=nt, smoothing=s_ref)
-        fit = eng.read_fit()                                    # raises what the reference would raise
-        p_rows, q_rows = p, q
+        gp2 = GenomePass(eng, group=False, q_values=want_q)
+        gp2.attach([shard])
+        fit = gp2.run(n_tests=nt, exclude=(gp1.p, 1.0 / in_rng))      # raises what the reference would raise
+        first = gp1.shard_p(0)
+        p_rows, q_rows = gp2.shard_p(0), (gp2.shard_q(0) if want_q else None)
     else:
         gp = GenomePass(eng, group=group, q_values=want_q)
         shards = _rows_to_shards(chr1, mid1, chr2, mid2, count, lo, hi, dev)
