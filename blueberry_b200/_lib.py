@@ -40,7 +40,7 @@ class FitResult(ctypes.Structure):
 
 class BiasTable(ctypes.Structure):
     _fields_ = [("d_bias", ctypes.c_void_p), ("d_chrom_base", ctypes.c_void_p), ("d_mid0", ctypes.c_void_p),
-                ("n_chrom", ctypes.c_int32)]
+                ("n_chrom", ctypes.c_int32), ("step", ctypes.c_int64)]
 
 
 class ScoreState(ctypes.Structure):

@@ -249,6 +249,7 @@ struct PvParams {
     int shard_chrom;
     long long R, min_dist, max_dist;
     FastDiv div;
+    FastDiv bdiv;        // the bias tables' grid step (the resolution unless BbkBiasTable.step says otherwise)
     const BbkFitResult* fit;
     const double* spline_y;
     const double* bias;
@@ -271,7 +272,7 @@ __device__ __forceinline__ BiasRow bias_row(const PvParams& P, int chrom) {
     r.base = __ldg(&P.chrom_base[chrom]);
     r.nloc = __ldg(&P.chrom_base[chrom + 1]) - r.base;
     r.mid0 = __ldg(&P.mid0[chrom]);
-    r.span = (unsigned long long)r.nloc * (unsigned long long)P.div.R;
+    r.span = (unsigned long long)r.nloc * (unsigned long long)P.bdiv.R;
     return r;
 }
 
@@ -283,12 +284,12 @@ __device__ __forceinline__ double bias_lookup(const PvParams& P, const BiasRow& 
     unsigned idx;
     if (FAST) {
         if (off >= (1ll << 31)) return 1.0;                      // (cannot happen with int32 coordinates >= 0)
-        idx = fastdiv31((unsigned)off, P.div);
+        idx = fastdiv31((unsigned)off, P.bdiv);
     } else {
         if (off >= (1ll << 32)) return 1.0;
-        idx = fastdiv((unsigned)off, P.div);
+        idx = fastdiv((unsigned)off, P.bdiv);
     }
-    if (idx * P.div.R != (unsigned)off) return 1.0;
+    if (idx * P.bdiv.R != (unsigned)off) return 1.0;
     double v = __ldg(&P.bias[row.base + idx]);
     return isnan(v) ? 1.0 : v;
 }
@@ -303,12 +304,12 @@ __device__ __forceinline__ bool bias_index(const PvParams& P, const BiasRow& row
     unsigned idx;
     if (FAST) {
         ok = ok && off < (1ll << 31);
-        idx = fastdiv31((unsigned)off, P.div);
+        idx = fastdiv31((unsigned)off, P.bdiv);
     } else {
         ok = ok && off < (1ll << 32);
-        idx = fastdiv((unsigned)off, P.div);
+        idx = fastdiv((unsigned)off, P.bdiv);
     }
-    ok = ok && idx * P.div.R == (unsigned)off;
+    ok = ok && idx * P.bdiv.R == (unsigned)off;
     *at = ok ? row.base + (long long)idx : 0ll;
     return ok;
 }
@@ -732,9 +733,11 @@ static int pvalues_impl(const int32_t* d_chr1, const int32_t* d_chr2, const int3
     bool has_bias = bias && bias->d_bias;
     if (has_bias) {
         BBK_REQUIRE(bias->d_chrom_base && bias->d_mid0 && bias->n_chrom > 0, "bbk_pvalues: incomplete bias table");
+        BBK_REQUIRE(bias->step >= 0 && bias->step < (1ll << 32), "bbk_pvalues: the bias tables' step must be in [0, 2^32)");
         P.bias = bias->d_bias; P.chrom_base = (const long long*)bias->d_chrom_base; P.mid0 = (const long long*)bias->d_mid0;
         P.n_chrom = bias->n_chrom;
     }
+    P.bdiv = (has_bias && bias->step > 0) ? make_fastdiv((uint64_t)bias->step) : P.div;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_tables(st);
     if (rc != BBK_OK) return rc;
@@ -838,9 +841,11 @@ extern "C" int bbk_score_pairs(const int32_t* d_mid1, const int32_t* d_mid2, con
     if (has_bias) {
         BBK_REQUIRE(bias->d_chrom_base && bias->d_mid0 && bias->n_chrom > 0, "bbk_score_pairs: incomplete bias table");
         BBK_REQUIRE(d_bias_flags, "bbk_score_pairs: a bias table needs its flag bits (bbk_bias_flags)");
+        BBK_REQUIRE(bias->step == 0 || (bias->step > 1 && bias->step < (1ll << 31)), "bbk_score_pairs: the bias tables' step must be 0 or in [2, 2^31)");
         Q.bias = bias->d_bias; Q.chrom_base = (const long long*)bias->d_chrom_base; Q.mid0 = (const long long*)bias->d_mid0;
         Q.n_chrom = bias->n_chrom; Q.flags = d_bias_flags;
     }
+    Q.bdiv = (has_bias && bias->step > 0) ? make_fastdiv((uint64_t)bias->step) : Q.div;
     Q.out_base = out_base; Q.p = d_p; Q.q = d_q; Q.p_hist = (long long*)d_p_hist;
     if (cands && cands->capacity > 0) {
         BBK_REQUIRE(cands->d_keys && cands->d_rows, "bbk_score_pairs: incomplete candidate list");

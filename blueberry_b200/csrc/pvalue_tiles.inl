@@ -69,6 +69,7 @@ struct StShared {
 struct StParams {
     const int* mid1; const int* mid2; const int* count; long long n_pairs;
     int shard_chrom; long long min_dist, max_dist; FastDiv div;
+    FastDiv bdiv;                                  // the bias tables' grid step (= div unless BbkBiasTable.step says otherwise)
     const BbkFitResult* fit; const double* spline_y;
     const double* bias; const long long* chrom_base; const long long* mid0; int n_chrom; const unsigned* flags;
     long long out_base; double* p; double* q; long long* p_hist;
@@ -185,12 +186,13 @@ __device__ __forceinline__ void st_fetch(StEntry& E, const StParams& Q, const St
         E.y = __ldg(Q.spline_y + i);
         if (HAS_BIAS) {
             if (B.wide) {
-                E.v1 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)R, m1); E.v2 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)R, m2);
+                E.v1 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)Q.bdiv.R, m1); E.v2 = st_bias_wide(B.tab, B.nloc, B.mid0, (long long)Q.bdiv.R, m2);
             } else if (B.spanu) {
                 const unsigned o1 = (unsigned)m1 - B.mid0u, o2 = (unsigned)m2 - B.mid0u;
-                const unsigned x1 = st_div(o1 & 0x7fffffffu, Q.div), x2 = st_div(o2 & 0x7fffffffu, Q.div);
-                if (o1 < B.spanu && x1 * R == o1) E.v1 = __ldg(B.tab + x1);                  // fithic.py:418-425: on the grid, inside the table
-                if (o2 < B.spanu && x2 * R == o2) E.v2 = __ldg(B.tab + x2);
+                const unsigned g = Q.bdiv.R;
+                const unsigned x1 = st_div(o1 & 0x7fffffffu, Q.bdiv), x2 = st_div(o2 & 0x7fffffffu, Q.bdiv);
+                if (o1 < B.spanu && x1 * g == o1) E.v1 = __ldg(B.tab + x1);                  // fithic.py:418-425: on the grid, inside the table
+                if (o2 < B.spanu && x2 * g == o2) E.v2 = __ldg(B.tab + x2);
             }
         }
     }
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
         B.mid0 = __ldg(&Q.mid0[Q.shard_chrom]);
         B.tab = Q.bias + base;
         if (B.nloc > 0) {
-            const unsigned long long span = (unsigned long long)B.nloc * R;
+            const unsigned long long span = (unsigned long long)B.nloc * Q.bdiv.R;
             if (B.mid0 >= 0 && B.mid0 < (1ll << 31) && span < (1ull << 31) && base + B.nloc < (1ll << 32)) {
                 B.mid0u = (unsigned)B.mid0; B.spanu = (unsigned)span;
                 B.flg = Q.flags + (base >> 5); B.fbit0 = (unsigned)(base & 31);
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
     }
     const bool zero_slow = exact || B.wide;                                    // count <= 0 rows go through their prior
     const bool use_flags = HAS_BIAS && B.flg != nullptr && !zero_slow;
+    const bool same_grid = Q.bdiv.R == R;                                      // bias loci on the rows' own grid (the usual case)
     for (int i = tid; i < ST_HBINS; i += ST_THREADS) sh.hist[i] = 0;
     if (tid < 64) sh.exp2[tid] = exp2((double)tid * (1.0 / 64.0));
     if (tid >= 64 && tid < 64 + LOW_C_MAX) sh.rcp[tid - 64] = tid > 64 ? 1.0 / (double)(tid - 64) : 0.0;
@@ -319,15 +322,15 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM) score_tiles_kernel
                 const unsigned t1 = (unsigned)((a1.x ^ a1.y) | (a1.x ^ a1.z) | (a1.x ^ a1.w));
                 const unsigned t2 = ((unsigned)(a2.y - a2.x) - R) | ((unsigned)(a2.z - a2.y) - R) | ((unsigned)(a2.w - a2.z) - R);
                 const unsigned o2 = (unsigned)a2.x - B.mid0u;
-                if ((t1 | t2) == 0u && o2 < B.spanu && o2 + 3u * R < B.spanu) {
+                if ((t1 | t2) == 0u && same_grid && o2 < B.spanu && o2 + 3u * R < B.spanu) {
                     const unsigned b = st_div(o2, Q.div) + B.fbit0;
                     const unsigned w0 = __ldg(B.flg + (b >> 5)), w1 = __ldg(B.flg + (b >> 5) + 1);   // (the bit map has a spare word at its end)
-                    const bool f1 = st_flagged(B, Q.div, a1.x);
+                    const bool f1 = st_flagged(B, Q.bdiv, a1.x);
                     slow = f1 ? 0xfu : (__funnelshift_r(w0, w1, b & 31) & 0xfu);
                 } else {
                     const int m1s[4] = {a1.x, a1.y, a1.z, a1.w}, m2s[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) slow |= (st_flagged(B, Q.div, m1s[e]) || st_flagged(B, Q.div, m2s[e])) ? (1u << e) : 0u;
+                    for (int e = 0; e < 4; ++e) slow |= (st_flagged(B, Q.bdiv, m1s[e]) || st_flagged(B, Q.bdiv, m2s[e])) ? (1u << e) : 0u;
                 }
             }
             unsigned cls = st_classes(a1, a2, ac, lo_u, span_u, slow);

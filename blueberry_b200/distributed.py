@@ -134,7 +134,7 @@ class GenomePass(object):
         mixed = any(sh.chr1 is not None for sh in self.shards)
         if mixed and self.world > 1:
             raise ValueError("multi-GPU passes take one-chromosome shards (no chromosome columns)")
-        self.listed = self._range_ok and not mixed
+        self.listed = self._range_ok and not mixed and not (self.eng.bias is not None and self.eng.bias.step == 1)
         if self.listed:
             # rows the streaming pass defers (large counts, significant rows): a few per cent; an overflow repeats the pass
             cap = int(list_capacity) if list_capacity else min(m, max(1 << 20, m // 4))

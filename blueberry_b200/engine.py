@@ -65,8 +65,10 @@ class BiasTables(object):
     Out-of-range biases must already be mapped to -1 (read_bias_file does that, fithic.py:147-149).
     """
 
-    def __init__(self, values, mid0, device):
+    def __init__(self, values, mid0, device, step=0):
+        """step: distance between neighbouring entries of every table; 0 = the resolution of the pass."""
         self.n_chrom = len(values)
+        self.step = int(step)
         base = np.zeros(self.n_chrom + 1, dtype=np.int64)
         for c, v in enumerate(values):
             base[c + 1] = base[c] + len(v)
@@ -74,7 +76,7 @@ class BiasTables(object):
         self.bias = torch.from_numpy(flat).to(device)
         self.chrom_base = torch.from_numpy(base).to(device)
         self.mid0 = torch.from_numpy(np.asarray(mid0, dtype=np.int64)).to(device)
-        self.struct = _lib.BiasTable(self.bias.data_ptr(), self.chrom_base.data_ptr(), self.mid0.data_ptr(), self.n_chrom)
+        self.struct = _lib.BiasTable(self.bias.data_ptr(), self.chrom_base.data_ptr(), self.mid0.data_ptr(), self.n_chrom, self.step)
         # one flag bit per entry (value < 0 or > 4) for bbk_score_pairs: count <= 0 rows look at two bits, not two values
         lib = _lib.load()
         n = int(self.bias.numel())

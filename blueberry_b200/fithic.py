@@ -147,16 +147,20 @@ def _frag_info(frag_chrom, frag_mid, resolution):
     return info
 
 
+MAX_BIAS_ENTRIES = 1 << 27          # dense bias tables: at most 1 GiB of float64
+
+
 def _bias_tables(bias_dic, resolution, device, n_chrom_hint=0):
-    """biasDic {chrom id: {mid: bias}} -> dense device tables on the grid mid0 + i*R."""
+    """biasDic {chrom id: {mid: bias}} -> dense device tables on the grid mid0 + i*step.  Loci on the fragment grid (the usual
+    bias file) give step = resolution; any other set of loci is put on the coarsest grid that holds them all (the gcd of their
+    offsets and the resolution), so that biasDic[chr][mid] (fithic.py:418-425) finds exactly the loci of the file."""
     R = int(resolution)
     n_chrom = max([n_chrom_hint] + [c + 1 for c in bias_dic])
-    values, mid0 = [], []
+    per_chrom, step = [], R
     for c in range(n_chrom):
         sub = bias_dic.get(c)
         if not sub:
-            values.append(np.zeros(0))
-            mid0.append(0)
+            per_chrom.append(None)
             continue
         if isinstance(sub, tuple):                               # (mids, values) arrays, first occurrences only
             mids, vals = sub
@@ -168,14 +172,24 @@ def _bias_tables(bias_dic, resolution, device, n_chrom_hint=0):
         vals = np.where(np.isnan(vals), np.inf, vals)
         m0 = int(mids.min())
         off = mids - m0
-        if (off % R).any():
-            raise NotImplementedError("bias loci of chromosome id %d are not on one %d-bp grid; the device bias "
-                                      "table is dense (fixed-size windows)" % (c, R))
-        tab = np.full(int(off.max() // R) + 1, np.nan)
-        tab[off // R] = vals
+        step = int(np.gcd.reduce(np.concatenate([[step], off[off > 0]]))) if (off > 0).any() else step
+        per_chrom.append((m0, off, vals))
+    total = sum(int(off.max() // step) + 1 for (m0, off, vals) in (x for x in per_chrom if x is not None))
+    if total > MAX_BIAS_ENTRIES:
+        raise NotImplementedError("the bias loci only share a %d-bp grid: the dense device bias tables would need %d entries "
+                                  "(limit %d)" % (step, total, MAX_BIAS_ENTRIES))
+    values, mid0 = [], []
+    for x in per_chrom:
+        if x is None:
+            values.append(np.zeros(0))
+            mid0.append(0)
+            continue
+        m0, off, vals = x
+        tab = np.full(int(off.max() // step) + 1, np.nan)
+        tab[off // step] = vals
         values.append(tab)
         mid0.append(m0)
-    return BiasTables(values, mid0, device)
+    return BiasTables(values, mid0, device, step=0 if step == R else step)
 
 
 # =================================================================================================

@@ -159,6 +159,7 @@ typedef struct BbkBiasTable {
     const int64_t* d_chrom_base; /* [n_chrom + 1] offsets into d_bias */
     const int64_t* d_mid0;       /* [n_chrom] mid of entry 0 of each chromosome */
     int32_t n_chrom;
+    int64_t step;                /* distance between neighbouring entries; 0 = the resolution of the pass (bias loci on the fragment grid) */
 } BbkBiasTable;
 
 int bbk_pvalues(const int32_t* d_chr1, const int32_t* d_chr2, const int32_t* d_mid1, const int32_t* d_mid2,

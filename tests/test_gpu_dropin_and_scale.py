@@ -235,6 +235,44 @@ def test_nan_and_odd_bias_values_follow_the_reference():
     assert np.abs(np.log10(out.p[k]) - np.log10(ref.p[k])).max() <= 1e-6
 
 
+@pytest.mark.parametrize("shift", [2500, 1234])
+def test_bias_loci_off_the_fragment_grid(shift):
+    """The reference takes ANY bias file: biasDic[chr][mid] is an exact-key lookup (fithic.py:418-425).  Loci that are not on the
+    fragments' grid put the dense device tables on the coarsest grid that holds them all; rows whose mids hit such a locus get
+    its bias, rows on the vacated grid positions get 1.0 - through the streaming K4 and through the general kernel."""
+    from blueberry_b200 import synth
+    from blueberry_b200.fithic import FitHiC
+    from oracle import fithic_oracle as fo
+    R, bins, max_dist = 10000, [240], 1_000_000
+    fc, fm = synth.make_fragments(bins, R)
+    bias = synth.make_bias(bins, 6, sigma=0.3)[0]
+    c = synth.make_contacts(bins, R, max_dist, 150.0, 13, [bias])
+    bm = fm.copy()
+    moved = np.array([5, 40, 41, 130, 239])
+    bm[moved] += shift                                          # these loci are NOT where the fragments are
+    m1, m2 = c["mid1"].copy(), c["mid2"].copy()
+    rng = np.random.default_rng(shift)
+    for j in moved:                                             # some rows sit exactly on the moved loci, the others keep the vacated mids
+        hit = np.flatnonzero(c["mid2"] == fm[j])
+        take = hit[rng.random(len(hit)) < 0.5]
+        m2[take] = bm[j]
+    bc = np.zeros(bins[0], dtype=np.int32)
+    model = FitHiC("offgrid", R, max_dist=max_dist)
+    bd, _ = fo.read_bias_arrays(bc, bm, bias)
+    ref = fo.fithic_arrays(fc, fm, None, m1, None, m2, c["count"], R, 100, model.min_dist, model.max_dist, bias=bd)
+    for chrom_cols in (False, True):                            # compact shard (streaming K4) / chromosome columns (general kernel)
+        ch = np.zeros(len(m1), dtype=np.int32) if chrom_cols else None
+        if chrom_cols:
+            ch2 = ch.copy()
+            out = model.fit_transform_arrays(ch, m1, ch2, m2, c["count"], fc, fm, bias=(bc, bm, bias), q_values=True)
+        else:
+            out = model.fit_transform_arrays(None, m1, None, m2, c["count"], fc, fm, bias=(bc, bm, bias), q_values=True)
+        assert np.array_equal(out.keep, ref.keep)
+        k = ref.keep & (ref.p > 0)
+        assert np.abs(np.log10(out.p[k]) - np.log10(ref.p[k])).max() <= 1e-6
+    assert len(np.unique(ref.p[np.isin(m2, bm[moved])])) > 1    # the moved loci were really used
+
+
 def test_host_pipeline_matches_serial_passes():
     """engine.HostPipeline: five different libraries (different sizes and seeds) streamed through two device slots
     give bit-for-bit the p and q of the same libraries run one at a time on the default stream."""
