@@ -853,7 +853,8 @@ extern "C" int bbk_score_pairs(const int32_t* d_mid1, const int32_t* d_mid2, con
     }
     Q.d_row = deferred->d_row; Q.d_cnt = deferred->d_count; Q.d_prior = deferred->d_prior; Q.d_cap = deferred->capacity;
     Q.st = d_state;
-    const long long need = (n_pairs + BBK_TILE_ROWS - 1) / BBK_TILE_ROWS;
+    const long long tile_rows = (long long)ST_WARPS * ST_WROWS;
+    const long long need = (n_pairs + tile_rows - 1) / tile_rows;
     long long grid = (long long)bbk_num_sms() * ST_CTAS_PER_SM;
     if (need < grid) grid = need;
     cudaStream_t st = (cudaStream_t)stream;
