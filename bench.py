@@ -562,7 +562,9 @@ def _measure(args, wl_name, world, rank, dev, full, out):
         best = min(times[1:])
         out["e2e_dropin"] = {"call": "FitHiC.fit_transform_arrays(numpy columns) -> numpy p, q", "workload": "chr1 of the same genome",
                              "pairs": n, "ms_per_call": 1e3 * best, "value": n / best, "unit": "pairs/s", "n_gpus": 1,
-                             "h2d_bytes": 12 * n, "d2h_bytes": 16 * n, "kept_rows": int(res.keep.sum())}
+                             "h2d_bytes": 12 * n, "result_bytes_dense": 16 * n,
+                             "note": "numpy (pageable) columns in, numpy p / q / keep out; the results cross the link packed and are unpacked by all host cores",
+                             "kept_rows": int(res.keep.sum())}
 
 
 def _score_state(gp):
