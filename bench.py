@@ -493,7 +493,7 @@ def _measure(args, wl_name, world, rank, dev, full, out):
     torch.cuda.empty_cache()
     pipe = HostStream(gp, W.sizes, W.chroms, slots=2, packed=True)
     outs = [pipe.packed_buffers() for _ in range(2)]
-    e2e_steps = max(2, min(args.steps, 10 if W.P_local < 200_000_000 else 3))
+    e2e_steps = max(2, min(args.steps, 10 if W.P_local < 200_000_000 else 6))
     for k in range(2):
         pipe.submit_packed(h_in[0], h_in[1], h_in[2], outs[k % 2])
     pipe.drain(); torch.cuda.synchronize()
