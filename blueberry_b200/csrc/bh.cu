@@ -549,6 +549,7 @@ constexpr int RK_THREADS = 1024;
 constexpr int RK_WARPS = RK_THREADS / 32;
 constexpr int RK_IPT = 4;
 constexpr int RK_TILE = RK_THREADS * RK_IPT;
+constexpr size_t RK_DYN_SMEM = (size_t)RK_TILE * (sizeof(unsigned long long) + sizeof(unsigned));   // the staged tile
 
 struct RankParams {
     BhLayout L;
@@ -604,6 +605,10 @@ __global__ void __launch_bounds__(RK_THREADS, 1) bh_rank_kernel(RankParams R) {
     __shared__ int sh_skip;
     __shared__ double wv[RK_WARPS];
     __shared__ long long wh[RK_WARPS];
+    __shared__ unsigned gstart[256], tstart[256];    // per digit: global position / staged position of the tile's run
+    extern __shared__ __align__(16) unsigned char rk_dyn[];
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(rk_dyn);               // [RK_TILE] the tile in digit order
+    unsigned* svals = reinterpret_cast<unsigned*>(rk_dyn + (size_t)RK_TILE * sizeof(unsigned long long));
     BhState* st = R.L.st;
     const long long n = R.n_host >= 0 ? R.n_host : (long long)st->n_cand;
     const int b = blockIdx.x, Ge = rk_eff_blocks(n, gridDim.x);
@@ -685,21 +690,46 @@ __global__ void __launch_bounds__(RK_THREADS, 1) bh_rank_kernel(RankParams R) {
                         loc[it] = before + rk;
                     }
                     __syncthreads();
-                    if (t < 256) {   // exclusive scan over warps, per digit; advance the running cursor of this CTA
-                        unsigned run = base[t];
+                    // The tile leaves through shared memory in digit order: a digit's elements of this tile are one contiguous run
+                    // in the output, so consecutive threads write consecutive addresses (scattering straight from registers
+                    // touched up to 32 sectors per warp store for 8-byte elements).
+                    unsigned cnt = 0, x = 0;
+                    if (t < 256) {   // per digit: the warps' shares become offsets inside the tile's run; advance the CTA's cursor
+                        const unsigned run = base[t];
+                        gstart[t] = run;
 #pragma unroll 8
-                        for (int w = 0; w < RK_WARPS; ++w) { unsigned v = whist[w][t]; whist[w][t] = run; run += v; }
-                        base[t] = run;
+                        for (int w = 0; w < RK_WARPS; ++w) { unsigned v = whist[w][t]; whist[w][t] = cnt; cnt += v; }
+                        base[t] = run + cnt;
+                        x = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                        if (lane == 31) wsum[warp] = x;
+                    }
+                    __syncthreads();
+                    if (t < 256) {
+                        unsigned before = 0;
+                        for (int w = 0; w < warp; ++w) before += wsum[w];
+                        tstart[t] = before + x - cnt;                    // where the digit's run starts inside the staged tile
                     }
                     __syncthreads();
 #pragma unroll
                     for (int it = 0; it < RK_IPT; ++it) {
                         if (wbase + it * 32 + lane < c.hi) {
                             const unsigned dg = (unsigned)(key[it] >> shift) & 255u;
-                            const unsigned pos = whist[warp][dg] + loc[it];
-                            kout[pos] = key[it];
-                            iout[pos] = val[it];
+                            const unsigned lp = tstart[dg] + whist[warp][dg] + loc[it];
+                            skeys[lp] = key[it];
+                            svals[lp] = val[it];
                         }
+                    }
+                    __syncthreads();
+                    const long long left = c.hi - tile;
+                    const int n_tile = left < RK_TILE ? (int)left : RK_TILE;
+                    for (int k = t; k < n_tile; k += RK_THREADS) {
+                        const unsigned long long kk = skeys[k];
+                        const unsigned dg = (unsigned)(kk >> shift) & 255u;
+                        const unsigned pos = gstart[dg] + ((unsigned)k - tstart[dg]);
+                        kout[pos] = kk;
+                        iout[pos] = svals[k];
                     }
                     __syncthreads();
                 }
@@ -801,7 +831,9 @@ int rank_grid() {            // CTAs of bh_rank_kernel that are resident togethe
     static int g = 0;
     if (g == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_rank_kernel<true>, RK_THREADS, 0) != cudaSuccess || per_sm < 1) return 0;
+        if (cudaFuncSetAttribute(bh_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_DYN_SMEM) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(bh_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_DYN_SMEM) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_rank_kernel<true>, RK_THREADS, RK_DYN_SMEM) != cudaSuccess || per_sm < 1) return 0;
         g = bbk_num_sms();
     }
     return g;
@@ -813,7 +845,7 @@ int launch_rank(const BhLayout& L, double* q, long long* rank, cudaStream_t st) 
     RankParams R;
     R.L = L; R.q = q; R.rank = rank; R.n_host = -1; R.src = 0;
     void* args[] = {&R};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel<true>, dim3(g), dim3(RK_THREADS), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel<true>, dim3(g), dim3(RK_THREADS), args, RK_DYN_SMEM, st);
     if (e != cudaSuccess) { bbk_set_error("bh_rank_kernel: %s", cudaGetErrorString(e)); return BBK_E_CUDA; }
     return BBK_OK;
 }
@@ -838,7 +870,7 @@ int bbk_sort_pairs(void* workspace, long long capacity, long long n_host, int sr
     RankParams R;
     R.L = L; R.q = nullptr; R.rank = nullptr; R.n_host = n_host; R.src = src;
     void* args[] = {&R};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel<false>, dim3(g), dim3(RK_THREADS), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bh_rank_kernel<false>, dim3(g), dim3(RK_THREADS), args, RK_DYN_SMEM, st);
     if (e != cudaSuccess) { bbk_set_error("bbk_sort_pairs: %s", cudaGetErrorString(e)); return BBK_E_CUDA; }
     return BBK_OK;
 }
