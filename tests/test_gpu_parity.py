@@ -482,3 +482,31 @@ def test_extract_contacts_and_genome_qvalues_on_the_device():
         assert got_n == want_n and np.array_equal(got_c, want_c, equal_nan=True)
         assert np.array_equal(got_q, want_q, equal_nan=True)
 
+
+def test_extract_contacts_reads_the_result_file_like_the_reference(tmp_path):
+    """utils.extract_contacts(celltype, chromosome, resolution, alpha, n_regions) - the reference's signature: the chromosome's
+    significances file is found through the DATA_DIR template (datatypes.pyx:26), read like FithicContactMap reads it, filtered
+    on the device; a chromosome without a file gives (zeros((0, 5)), 0) and a message, like utils.py:65-67."""
+    from blueberry_b200 import _io, utils
+    from blueberry_b200.datatypes import FithicContactMap
+    from oracle import datatypes_oracle as do
+    rng = np.random.default_rng(8)
+    n = 3000
+    m1 = rng.integers(0, 2500, n) * 5000 + 2500
+    m2 = m1 + rng.integers(0, 2300, n) * 5000
+    p = rng.random(n) ** 5
+    path = str(tmp_path / "{0}.chr{1}.res{2}.sig.txt.gz")
+    _io.write_significances(path.format("cellX", 7, 5000), ["chr7"], None, m1, None, m2, rng.integers(1, 30, n), p, None)
+    old = utils.DATA_DIR
+    utils.DATA_DIR = path
+    try:
+        got, band = utils.extract_contacts("cellX", 7, 5000, alpha=0.2, n_regions=True)
+        held = FithicContactMap(path.format("cellX", 7, 5000), 5000).map
+        assert np.array_equal(got, do.extract_contacts(held, 7, 0.2))
+        assert band == do.count_band_regions(do.regions(held))
+        assert np.array_equal(utils.extract_contacts("cellX", 7, 5000), do.extract_contacts(held, 7))
+        empty, zero = utils.extract_contacts("cellX", 8, 5000, alpha=0.2, n_regions=True)
+        assert empty.shape == (0, 5) and zero == 0
+    finally:
+        utils.DATA_DIR = old
+
