@@ -13,11 +13,12 @@
 //                  carries a flag bit in the bias bit map (value < 0 or > 4: the prior has to be looked at) - one bit per
 //                  locus instead of an 8-byte gather, which is what made the 1 kb workloads latency-bound.  The result of
 //                  every such row (1.0 / NaN) replaces the row in the tile; rows that need arithmetic go on the warp's
-//                  list, sorted count <= 1 | 2..8 | rest.
+//                  list, sorted count <= 1 | rest.
 //         rounds   32 list entries at a time, every lane busy on the same path; the gathers of the NEXT round (spline value,
 //                  two bias values) are in flight while a round computes.  prior = splineY[i] * (b1 * b2), fithic.py:429-431;
 //                      count == 1     1 - (1-q)^S                                (bdtrc's closed form)
-//                      2..SMALL_C     1 - (1-q)^S (1 + r1 + r1 r2 + ...), count-1 terms (the lower tail)
+//                      2..LOW_C_MAX   1 - (1-q)^S (1 + r1 + r1 r2 + ...), count-1 terms (the lower tail; the terms written
+//                                     out up to SMALL_C, a loop above)
 //                  rows this cannot finish - larger counts, a prior outside (0, 2^-10), a lower-tail result below 1e-4
 //                  (digits lost in the subtraction), tiny S - are DEFERRED: (row, count, prior) goes to a global list.
 //         output   the warp writes its 256 rows of p (and q = 1.0 / NaN) with full coalesced 128-bit stores; no partial
