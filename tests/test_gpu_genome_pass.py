@@ -348,6 +348,42 @@ def test_config2_shape_sample_against_oracle():
     assert gp.last_score.exact == 0
 
 
+def test_config4_shape_sample_two_pass_against_oracle():
+    """BASELINE config 4's shape (1 kb, 2 Mb cap, D = 2001, depth 60: ~93 % of the records have count 0), both passes -
+    the fit, the outlier cut at 1 / possibleIntraInRangeCount, the refit over the remaining records, every record scored
+    again - on a 4000-bin chromosome = 6.0e6 records, through the drop-in entry point, against the oracle's composition of
+    the reference's functions."""
+    import warnings
+    from blueberry_b200 import synth
+    from blueberry_b200.fithic import FitHiC
+    from oracle import fithic_oracle as fo
+    R, bins, max_dist = 1000, [4000], 2_000_000
+    fc, fm = synth.make_fragments(bins, R)
+    bias = synth.make_bias(bins, 4)
+    c = synth.make_contacts(bins, R, max_dist, 60.0, 404, bias)
+    assert 0.85 < float((c["count"] == 0).mean()) < 0.97
+    bd, _ = fo.read_bias_arrays(np.zeros(bins[0], dtype=np.int64), fm, bias[0])
+    model = FitHiC("unused", R, n_bins=100, max_dist=max_dist, min_dist=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r1, r2, outlier, thr = fo.fithic_two_pass_arrays(fc, fm, c["chrom"], c["mid1"], c["chrom"], c["mid2"], c["count"], R, 100,
+                                                         model.min_dist, model.max_dist, bias=bd)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        assert not (r1.keep & (np.abs(r1.p / thr - 1.0) < 1e-9)).any()          # no record sits on the outlier threshold
+    assert int(outlier.sum()) > 0
+    barr = (np.zeros(bins[0], dtype=np.int32), fm.copy(), bias[0])
+    out = model.fit_transform_arrays(c["chrom"], c["mid1"], c["chrom"], c["mid2"], c["count"], fc, fm, bias=barr, refit=True, q_values=True)
+    assert np.array_equal(out.observed, r2.contacts.observed)
+    assert out.totals["observedIntraInRangeSum"] == r2.contacts.S
+    assert np.array_equal(out.x, np.array(r2.x)) and np.array_equal(out.y, np.array(r2.y))
+    assert np.array_equal(out.spline_y, r2.spline_y)
+    assert np.array_equal(out.keep, r2.keep)
+    sel = r2.keep & (r2.p >= 1e-300)
+    ok, nbad = log10_close(out.p[sel], r2.p[sel], 1e-5)
+    assert ok, "%d p-values differ by more than 1e-5 in log10" % nbad
+    assert np.array_equal(out.q[out.keep], fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum())))
+
+
 def test_list_overflow_is_detected_and_repaired():
     import torch
     from blueberry_b200.distributed import GenomePass
