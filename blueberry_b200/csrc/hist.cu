@@ -1,7 +1,11 @@
 // hist.cu - K1: contact histogram by genomic distance (reference: read_interactions, fithic.py:229-270).
 //
 // HBM-bound integer kernel: 12 B/pair in (mid1, mid2, count as int32 SoA), O(D) out.
-//   * 128-bit streaming loads (L1::no_allocate), two groups of 4 records in flight per thread;
+//   * the usual case (no chromosome columns, distances below 2^31, a table of a few thousand keys) takes its records through
+//     shared memory: every warp owns two stages of 256 records x 3 columns filled by bulk asynchronous copies (cp.async.bulk +
+//     mbarrier, the TMA unit), so a warp has 6 KB in flight without holding a register and refills a stage as soon as its 8
+//     records per lane are in registers; the other cases use 128-bit streaming loads (L1::no_allocate), two groups of 4
+//     records in flight per thread;
 //   * per-CTA shared-memory histogram (u32, flushed to the global int64 table before it can
 //     overflow); warp-aggregated: when every active lane of a warp hits the same distance
 //     (diagonal-major input) the counts are summed with REDUX and one lane issues the atomic,
@@ -18,6 +22,30 @@ constexpr int HIST_THREADS = 512;
 constexpr int SMALL_COUNT_LIMIT = 4096;          // counts below this go through the u32 shared histogram
 constexpr long long FLUSH_PAIRS = 1ll << 20;     // 2^20 pairs * 4095 < 2^32: flush before a bin can overflow
 constexpr int MAX_SMEM_KEYS = 40960;             // 160 KB of u32 bins
+
+constexpr int HIST_WROWS = 256;                  // staged path: records of a warp tile (two int4 groups per lane)
+constexpr int HIST_STAGE_INTS = 3 * HIST_WROWS;  // mid1 | mid2 | count
+constexpr size_t HIST_STAGE_BYTES = (size_t)(HIST_THREADS / 32) * 2 * HIST_STAGE_INTS * sizeof(int);   // per CTA: 16 warps x 2 stages x 3 KB
+static_assert((HIST_THREADS / 32) * HIST_WROWS == 2 * HIST_THREADS * 4, "a CTA tile (2 groups of 4 records per thread) is one warp tile per warp");
+
+__device__ __forceinline__ unsigned h_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void h_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(h_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void h_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(h_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool h_mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(h_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (TMA unit, no registers), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void h_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(h_smem_u32(dst)), "l"(src), "r"(bytes), "r"(h_smem_u32(bar)) : "memory");
+}
 
 struct HistParams {
     const int32_t* chr1;
@@ -104,7 +132,7 @@ struct FastAcc {
     int in_range, intra_cnt, inter_cnt, dmin, dmax;
 };
 
-template <bool FULL, bool HAS_CHR>
+template <bool FULL, bool HAS_CHR, bool EXCL = true>
 __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned* sh, int4 m1, int4 m2, int4 c, int4 x1, int4 x2,
                                                    bool live_group, unsigned excl, FastAcc& a) {
     const int m1s[4] = {m1.x, m1.y, m1.z, m1.w}, m2s[4] = {m2.x, m2.y, m2.z, m2.w}, cs[4] = {c.x, c.y, c.z, c.w};
@@ -113,7 +141,7 @@ __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned
     bool ok[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const bool live = (FULL || live_group) && !((excl >> e) & 1u);
+        const bool live = (FULL || live_group) && (!EXCL || !((excl >> e) & 1u));   // (EXCL = false: the caller has no exclusion mask)
         const unsigned ud = (unsigned)m2s[e] - (unsigned)m1s[e];                      // fithic.py:247
         const bool in_range = live && m2s[e] >= m1s[e] && (ud - P.lo_u) <= P.span_u;  // fithic.py:256-257
         const int d = (int)ud;                                                        // < 2^31 when in_range
@@ -144,16 +172,21 @@ __device__ __forceinline__ void process_group_fast(const HistParams& P, unsigned
         small[e] = ok[e] && (unsigned)cs[e] < (unsigned)SMALL_COUNT_LIMIT && key[e] < (unsigned)P.nkeys_s;
         if (ok[e] && !small[e]) atomicAdd((unsigned long long*)&P.obs_sum[key[e]], (unsigned long long)(long long)cs[e]);
     }
-    // warp-uniform distance?  (every lane's 4 keys equal lane 0's first key, all of them "small" or zero-count)
+    // warp-uniform distance?  (diagonal-major input: every lane's 4 keys equal lane 0's first key, all of them "small" or
+    // zero-count.)  Row-major input fails the first, cheap test - a lane's first and last key against lane 0's - at once.
     const unsigned kref = __shfl_sync(0xffffffffu, key[0], 0);
-    bool mine_uniform = true;
+    bool uniform = __all_sync(0xffffffffu, key[0] == kref && key[3] == kref);
     int ssum = 0;
+    if (uniform) {
+        bool mine_uniform = true;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        mine_uniform = mine_uniform && (!ok[e] || (small[e] && key[e] == kref));
-        ssum += small[e] ? cs[e] : 0;
+        for (int e = 0; e < 4; ++e) {
+            mine_uniform = mine_uniform && (!ok[e] || (small[e] && key[e] == kref));
+            ssum += small[e] ? cs[e] : 0;
+        }
+        uniform = __all_sync(0xffffffffu, mine_uniform);
     }
-    if (__all_sync(0xffffffffu, mine_uniform)) {
+    if (uniform) {
         unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)ssum);
         if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&sh[phys_bin((int)kref, P.quarter)], tot);
     } else {
@@ -176,11 +209,29 @@ __device__ __forceinline__ void flush_hist(const HistParams& P, unsigned* sh) {
     __syncthreads();
 }
 
-template <bool HAS_CHR, bool FAST>
+// the records of a warp's part of CTA tile `tile` into its stage `stage` (one lane)
+__device__ __forceinline__ void hist_issue_tile(const HistParams& P, int* wbuf, unsigned long long* bars, long long tile, int warp, int stage) {
+    const long long r0 = tile * (2ll * HIST_THREADS * 4) + (long long)warp * HIST_WROWS;
+    int* dst = wbuf + stage * HIST_STAGE_INTS;
+    const unsigned bytes = HIST_WROWS * sizeof(int);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the stage's last readers (generic proxy) are done
+    h_mbar_expect_tx(&bars[stage], 3u * bytes);
+    h_bulk_g2s(dst, P.mid1 + r0, bytes, &bars[stage]);
+    h_bulk_g2s(dst + HIST_WROWS, P.mid2 + r0, bytes, &bars[stage]);
+    h_bulk_g2s(dst + 2 * HIST_WROWS, P.count + r0, bytes, &bars[stage]);
+}
+
+template <bool HAS_CHR, bool FAST, bool STAGED>
 __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kernel(HistParams P) {
-    extern __shared__ unsigned sh[];
+    static_assert(!STAGED || (FAST && !HAS_CHR), "the staged path is the fast path without chromosome columns");
+    extern __shared__ __align__(128) unsigned sh[];
     __shared__ long long red[8][HIST_THREADS / 32];
+    __shared__ unsigned long long bars[HIST_THREADS / 32][2];              // staged path: a warp's two "stage has landed" barriers
     for (int i = threadIdx.x; i < 4 * P.quarter; i += blockDim.x) sh[i] = 0;
+    if (STAGED && (threadIdx.x & 31) == 0) {
+        h_mbar_init(&bars[threadIdx.x >> 5][0], 1); h_mbar_init(&bars[threadIdx.x >> 5][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     Acc a = {0, 0, 0, 0, 0, 0, 500000000ll, 0ll};                      // fithic.py:40-41 initial min / max
@@ -197,7 +248,46 @@ __global__ void __launch_bounds__(HIST_THREADS, HAS_CHR ? 1 : 2) hist_pairs_kern
     const long long tile_groups = 2ll * blockDim.x;
     const long long n_tiles = (n_groups + tile_groups - 1) / tile_groups;
     long long tile = blockIdx.x;
-    if (FAST) {
+    if (STAGED) {
+        // full tiles through the warp's two stages: wait for the stage, take the 8 records of the lane into registers, refill
+        // the stage with the tile after next, then do the arithmetic
+        const long long full_tiles = n_groups / tile_groups;
+        const double2* pe = reinterpret_cast<const double2*>(P.p_excl);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int* wbuf = reinterpret_cast<int*>(sh + 4 * P.quarter) + warp * (2 * HIST_STAGE_INTS);    // 16 * quarter bytes: 16-byte aligned
+        if (lane == 0) {
+            if (tile < full_tiles) hist_issue_tile(P, wbuf, bars[warp], tile, warp, 0);
+            if (tile + gridDim.x < full_tiles) hist_issue_tile(P, wbuf, bars[warp], tile + gridDim.x, warp, 1);
+        }
+        for (int k = 0; tile < full_tiles; tile += gridDim.x, ++k) {
+            const int stage = k & 1;
+            const unsigned parity = (unsigned)(k >> 1) & 1u;
+            while (!h_mbar_try_wait(&bars[warp][stage], parity)) { }
+            const int4* sv = reinterpret_cast<const int4*>(wbuf + stage * HIST_STAGE_INTS);
+            const int4 a1 = sv[lane], a2 = sv[HIST_WROWS / 4 + lane], ac = sv[2 * (HIST_WROWS / 4) + lane];
+            const int4 b1 = sv[32 + lane], b2 = sv[HIST_WROWS / 4 + 32 + lane], bc = sv[2 * (HIST_WROWS / 4) + 32 + lane];
+            __syncwarp();
+            if (lane == 0 && tile + 2ll * gridDim.x < full_tiles) hist_issue_tile(P, wbuf, bars[warp], tile + 2ll * gridDim.x, warp, stage);
+            const int4 z = make_int4(0, 0, 0, 0);
+            if (pe) {                                  // (uniform: the refit pass)
+                const long long g0 = tile * tile_groups + (long long)warp * (HIST_WROWS / 4) + lane, g1 = g0 + 32;
+                const double2 u0 = ld_stream_double2(pe + 2 * g0), v0 = ld_stream_double2(pe + 2 * g0 + 1);
+                const double2 u1 = ld_stream_double2(pe + 2 * g1), v1 = ld_stream_double2(pe + 2 * g1 + 1);
+                const unsigned xa = (u0.x <= P.p_thr ? 1u : 0u) | (u0.y <= P.p_thr ? 2u : 0u) | (v0.x <= P.p_thr ? 4u : 0u) | (v0.y <= P.p_thr ? 8u : 0u);
+                const unsigned xb = (u1.x <= P.p_thr ? 1u : 0u) | (u1.y <= P.p_thr ? 2u : 0u) | (v1.x <= P.p_thr ? 4u : 0u) | (v1.y <= P.p_thr ? 8u : 0u);
+                process_group_fast<true, false, true>(P, sh, a1, a2, ac, z, z, true, xa, fa);
+                process_group_fast<true, false, true>(P, sh, b1, b2, bc, z, z, true, xb, fa);
+            } else {
+                process_group_fast<true, false, false>(P, sh, a1, a2, ac, z, z, true, 0u, fa);
+                process_group_fast<true, false, false>(P, sh, b1, b2, bc, z, z, true, 0u, fa);
+            }
+            since_flush += 4 * tile_groups;
+            if (since_flush >= FLUSH_PAIRS) {      // uniform across the CTA
+                flush_hist(P, sh);
+                since_flush = 0;
+            }
+        }
+    } else if (FAST) {
         // full tiles: no bounds predicates, the loads of a thread go out back to back
         const long long full_tiles = n_groups / tile_groups;
         const double2* pe = reinterpret_cast<const double2*>(P.p_excl);
@@ -385,21 +475,26 @@ static int hist_pairs_impl(const int32_t* d_chr1, const int32_t* d_chr2, const i
     if (P.nkeys_s == 0) P.quarter = 0;
     P.obs_sum = (long long*)d_obs_sum; P.totals = (long long*)d_totals;
     size_t smem = (size_t)4 * P.quarter * sizeof(unsigned);
+    // records through shared memory (bulk copies) when two CTAs with their stages still fit an SM: 2 x (table + 96 KB + static + 1 KB) <= 228 KB
+    const bool staged = fast && !d_chr1 && 2 * (smem + HIST_STAGE_BYTES + 4096) <= 228 * 1024;
+    if (staged) smem += HIST_STAGE_BYTES;
 
     int sms = bbk_num_sms();
     long long groups = n_pairs >> 2;
     long long need = (groups + 2ll * HIST_THREADS - 1) / (2ll * HIST_THREADS);
-    int per_sm = smem > 100 * 1024 ? 1 : 2;
+    int per_sm = (!staged && smem > 100 * 1024) ? 1 : 2;
     long long grid = (long long)sms * per_sm;
     if (need < grid) grid = need > 0 ? need : 1;
     cudaStream_t st = (cudaStream_t)stream;
-#define BBK_HIST_LAUNCH(C, F)                                                                                                   \
-    do {                                                                                                                         \
-        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        hist_pairs_kernel<C, F><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);                                                  \
+#define BBK_HIST_LAUNCH(C, F, G)                                                                                                    \
+    do {                                                                                                                            \
+        BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<C, F, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        if (G) BBK_CHECK_CUDA(cudaFuncSetAttribute(hist_pairs_kernel<C, F, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+        hist_pairs_kernel<C, F, G><<<(unsigned)grid, HIST_THREADS, smem, st>>>(P);                                                  \
     } while (0)
-    if (d_chr1) { if (fast) BBK_HIST_LAUNCH(true, true); else BBK_HIST_LAUNCH(true, false); }
-    else        { if (fast) BBK_HIST_LAUNCH(false, true); else BBK_HIST_LAUNCH(false, false); }
+    if (d_chr1) { if (fast) BBK_HIST_LAUNCH(true, true, false); else BBK_HIST_LAUNCH(true, false, false); }
+    else if (staged) BBK_HIST_LAUNCH(false, true, true);
+    else        { if (fast) BBK_HIST_LAUNCH(false, true, false); else BBK_HIST_LAUNCH(false, false, false); }
 #undef BBK_HIST_LAUNCH
     BBK_CHECK_LAUNCH("hist_pairs_kernel");
     return BBK_OK;
