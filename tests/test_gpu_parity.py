@@ -393,10 +393,11 @@ def test_second_pass_against_composed_reference_golden(torch_cuda):
 
 
 # K1 works on tiles of 4096 records (two groups of four per thread, 512 threads); sizes on either side of the tile and
-# group boundaries, all four kernel variants (32-bit fast path / general, without / with chromosome columns), coordinates that
+# group boundaries, all five kernel variants (32-bit fast path with the records staged through shared memory / the same with a
+# table too large for the stages ("fast_wide") / general, fast and general with chromosome columns), coordinates that
 # wrap a 32-bit subtraction, off-grid and negative distances, counts above the shared-histogram limit and below zero.
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 4093, 4095, 4096, 4097, 4099, 8192, 8195, 12288 + 7, 100003, 1_300_001])
-@pytest.mark.parametrize("variant", ["fast", "general", "chrom", "chrom_general"])
+@pytest.mark.parametrize("variant", ["fast", "fast_wide", "general", "chrom", "chrom_general"])
 def test_hist_kernel_edge_sizes_against_oracle(n, variant, torch_cuda):
     torch = torch_cuda
     from blueberry_b200.engine import PassEngine, Shard
@@ -421,7 +422,10 @@ def test_hist_kernel_edge_sizes_against_oracle(n, variant, torch_cuda):
     if variant.startswith("chrom"):
         chr1 = rng.integers(0, 3, size=n).astype(np.int32)
         chr2 = np.where(rng.random(n) < 0.9, chr1, (chr1 + 1) % 3).astype(np.int32)
-    min_dist, max_dist = {"fast": (2 * R, 600 * R), "general": (-1, -1), "chrom": (R, 800 * R), "chrom_general": (-1, 650 * R)}[variant]
+    if variant == "fast_wide":
+        nkeys = 6000                                                 # 2 x (table + stages) does not fit an SM: streaming loads
+    min_dist, max_dist = {"fast": (2 * R, 600 * R), "fast_wide": (2 * R, 5900 * R), "general": (-1, -1), "chrom": (R, 800 * R),
+                          "chrom_general": (-1, 650 * R)}[variant]
     ref = fo.read_interactions(nkeys, R, chr1, mid1, chr2, mid2, count, min_dist, max_dist)
 
     dev = torch.device("cuda:0")
