@@ -10,11 +10,12 @@ Default workload (config.workload): BASELINE config 3 - the 23 hg19 chromosomes 
 the metric is quoted on ("at 1/2/4/8 B200").  The SAME genome is scored at every N (strong scaling): the records are
 cut into N equal pieces along the chromosomes (distributed.plan_shards: whole chromosomes, a chromosome that straddles
 a cut is split into row blocks), through the public multi-GPU entry point distributed.GenomePass: K1 per shard ->
-all-reduce of the distance table (NCCL) -> fit -> K4 (classification overlapped with the fit, then the dense work
-lists) -> genome-wide Benjamini-Hochberg q-values (histogram all-reduce + one fixed-capacity all-gather).
+all-reduce of the distance table (NCCL) -> fit -> K4 (one streaming kernel per shard + the patch pass over the deferred
+rows) -> genome-wide Benjamini-Hochberg q-values (histogram all-reduce + one fixed-capacity all-gather).
 With --gpus 8 the line also carries BASELINE config 5 (genome-wide 1 kb, 2 Mb cap, 6,029,643,315 records) as
 cfg5_ms_per_step / cfg5_frac.  Other workloads: --workload cfg2 (chr1 @ 5 kb), cfg4 (chr1 @ 1 kb, two passes), cfg5.
-A "step" is one whole pass over the resident records.
+A "step" is one whole pass over the resident records; ms_per_step / value are one pass on its own.  two_passes_in_flight
+(one GPU by default, --overlap on elsewhere) is the throughput when independent passes alternate on two streams.
 """
 import argparse
 import hashlib
