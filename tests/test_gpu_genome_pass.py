@@ -384,6 +384,43 @@ def test_config4_shape_sample_two_pass_against_oracle():
     assert np.array_equal(out.q[out.keep], fo.benjamini_hochberg_correction(out.p[out.keep], int(out.keep.sum())))
 
 
+def test_two_passes_in_flight_equal_serial_passes():
+    """Independent passes on two streams, each with its own engine and GenomePass (bench.py's two_passes_in_flight): the same
+    records through both lanes, and different records through the two lanes at once, against each lane run alone."""
+    import torch
+    from blueberry_b200 import synth
+    from blueberry_b200.distributed import GenomePass
+    from blueberry_b200.engine import Shard
+    dev = torch.device("cuda", 0)
+    R, bins, max_dist = 5000, [900, 700], 2_000_000
+    bias = synth.make_bias(bins, 5)
+    lanes = []
+    for seed, depth in ((11, 80.0), (12, 9.0)):
+        c = synth.make_contacts(bins, R, max_dist, depth, seed, bias)
+        shards = []
+        for ci in range(len(bins)):
+            sel = np.flatnonzero(c["chrom"] == ci)
+            shards.append(Shard(_t32(c["mid1"][sel], dev), _t32(c["mid2"][sel], dev), _t32(c["count"][sel], dev), chrom=ci))
+        gp = GenomePass(_engine(bins, R, 0, max_dist, bias, dev), group=False, q_values=True)
+        gp.attach(shards)
+        gp.run()
+        lanes.append((gp, gp.p.clone(), gp.q.clone(), torch.cuda.Stream(dev)))
+    torch.cuda.synchronize()
+    main = torch.cuda.current_stream(dev)
+    for gp, _, _, st in lanes:
+        gp.p.fill_(7.0); gp.q.fill_(7.0)
+        st.wait_stream(main)
+    for _ in range(3):
+        for gp, _, _, st in lanes:
+            with torch.cuda.stream(st):
+                gp.enqueue()
+    for gp, p_alone, q_alone, st in lanes:
+        with torch.cuda.stream(st):
+            gp.finish()
+        assert _same(gp.p.cpu().numpy()[:gp.rows], p_alone.cpu().numpy()[:gp.rows])
+        assert _same(gp.q.cpu().numpy()[:gp.rows], q_alone.cpu().numpy()[:gp.rows])
+
+
 def test_list_overflow_is_detected_and_repaired():
     import torch
     from blueberry_b200.distributed import GenomePass
